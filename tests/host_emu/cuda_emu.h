@@ -1,0 +1,100 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY.
+// A minimal std::thread emulation of the CUDA execution model (one std::thread per CUDA thread,
+// std::barrier for __syncthreads/__syncwarp, exchange buffers for warp shuffles) so that the
+// kernels under xnode-wan-pde-solver_b200/csrc can be compiled with g++ -DXW_EMU and their
+// results compared with the oracle on a CPU-only machine.  Never linked into the product library.
+#pragma once
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace emu {
+
+struct Block {
+    int bdim = 0;
+    std::unique_ptr<std::barrier<>> bar;
+    std::vector<std::unique_ptr<std::barrier<>>> wbar;
+    std::vector<uint64_t> xchg;           // [nwarps][32]
+    std::vector<unsigned char> smem;
+};
+
+inline thread_local int tid = 0, bid = 0, bdim = 1, gdim = 1;
+inline thread_local Block* blk = nullptr;
+inline std::mutex atomic_mu;
+
+inline void warp_sync() { blk->wbar[tid >> 5]->arrive_and_wait(); }
+
+template <typename T>
+inline T shfl_idx(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    uint64_t raw = 0;
+    std::memcpy(&raw, &v, sizeof(T));
+    uint64_t* buf = &blk->xchg[(size_t)(tid >> 5) * 32];
+    buf[tid & 31] = raw;
+    warp_sync();
+    uint64_t got = buf[src_lane & 31];
+    warp_sync();
+    T out;
+    std::memcpy(&out, &got, sizeof(T));
+    return out;
+}
+template <typename T>
+inline T shfl_xor(T v, int m) { return shfl_idx(v, (tid & 31) ^ m); }
+
+template <typename T>
+inline T atomic_add(T* p, T v) {
+    std::lock_guard<std::mutex> g(atomic_mu);
+    T old = *p;
+    *p = old + v;
+    return old;
+}
+
+// run `f()` as a kernel body over grid x block threads with `smem_bytes` of dynamic shared memory
+template <typename F>
+inline void launch(int grid, int block, size_t smem_bytes, F f) {
+    for (int b = 0; b < grid; ++b) {
+        Block B;
+        B.bdim = block;
+        B.bar = std::make_unique<std::barrier<>>(block);
+        int nw = (block + 31) / 32;
+        for (int w = 0; w < nw; ++w) {
+            int cnt = std::min(32, block - 32 * w);
+            B.wbar.emplace_back(std::make_unique<std::barrier<>>(cnt));
+        }
+        B.xchg.assign((size_t)nw * 32, 0);
+        B.smem.assign(smem_bytes + 64, 0);
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (int t = 0; t < block; ++t) {
+            th.emplace_back([&, t]() {
+                tid = t; bid = b; bdim = block; gdim = grid; blk = &B;
+                f();
+            });
+        }
+        for (auto& x : th) x.join();
+    }
+}
+
+inline unsigned char* dyn_smem() {
+    uintptr_t p = reinterpret_cast<uintptr_t>(blk->smem.data());
+    p = (p + 15) & ~uintptr_t(15);
+    return reinterpret_cast<unsigned char*>(p);
+}
+
+}  // namespace emu
+
+#define XW_SYNCTHREADS() emu::blk->bar->arrive_and_wait()
+#define XW_SYNCWARP() emu::warp_sync()
+#define XW_SHFL_XOR(v, m) emu::shfl_xor((v), (m))
+#define XW_SHFL_IDX(v, l) emu::shfl_idx((v), (l))
+#define XW_TID (emu::tid)
+#define XW_BID (emu::bid)
+#define XW_BDIM (emu::bdim)
+#define XW_GDIM (emu::gdim)
+#define XW_ATOMIC_ADD_F(p, v) emu::atomic_add<float>((p), (v))
+#define XW_ATOMIC_ADD_D(p, v) emu::atomic_add<double>((p), (v))

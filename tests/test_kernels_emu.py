@@ -1,0 +1,64 @@
+"""CPU: the CUDA kernels compiled for the host emulator (tests/host_emu) against the golden vectors
+of the unmodified reference and against the closed-form oracle.  This checks kernel LOGIC (indexing,
+staging, reverse sweeps, reductions) without a GPU; the `-m gpu` tests check the real sm_100a build."""
+import numpy as np
+import pytest
+
+import xnode_wan_b200 as xw
+from oracle import closed_form as cf
+from tests import _golden as G
+from tests import _lowlevel as LL
+from tests.host_emu import build_emu
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return xw._lib.XwLib(build_emu.build())
+
+
+def check_against(r, ref, gu, gv, tol_loss=2e-5, tol_grad=1e-3):
+    for k in ("I", "S", "init", "bdry"):
+        assert abs(r[k] - ref[k]) <= tol_loss * abs(ref[k]) + 1e-9, k
+    for k in ("loss_u", "loss_v"):
+        assert abs(r[k] - ref[k]) <= 1e-4 * abs(ref[k]) + 1e-6, k
+    for a, b in zip(r["grads_u"], gu):
+        assert G.rel(a, b) < tol_grad
+    for a, b in zip(r["grads_v"], gv):
+        assert G.rel(a, b) < tol_grad
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_emulated_kernels_match_reference_golden(emu, name):
+    c = G.load(name)
+    z = c["z"]
+    r = LL.run_case(emu, LL.NumpyBackend(), c)
+    ref = {k: float(z[k]) for k in ("I", "S", "init", "bdry", "loss_u", "loss_v")}
+    assert np.abs(r["u"] - z["u"]).max() < 2e-5
+    check_against(r, ref, c["gu"], c["gv"])
+
+
+def test_emulated_kernels_dense_a_and_b_match_oracle(emu):
+    """constant dense a_ij and b_i (not exercised by any shipped config): compare with the oracle"""
+    c = G.load("cube_d3_small_nets")
+    rng = np.random.default_rng(0)
+    a = np.eye(3) + 0.3 * rng.standard_normal((3, 3))
+    b = rng.standard_normal(3)
+    coef = dict(c["coef"], a=a, b=b)
+    z = c["z"]
+    refs = {}
+    for ph in ("u", "v"):
+        refs[ph] = cf.weak_form(c["thu"], c["thv"], z["X"], z["XV"], z["BX"], coef, c["cfg"], ph)
+    r = LL.run_case(emu, LL.NumpyBackend(), c, coef_a=a, coef_b=b)
+    ref = {k: refs["u"][k] for k in ("I", "S", "init", "bdry", "loss_u")}
+    ref["loss_v"] = refs["v"]["loss_v"]
+    check_against(r, ref, refs["u"]["grads"], refs["v"]["grads"])
+
+
+def test_capi_rejects_unsupported(emu):
+    import ctypes as C
+    d = xw._lib.Dims(5, 64, 10, 8, 50, 9, 1)
+    assert emu.cdll.xw_workspace_bytes(C.byref(d), 10, 5) == 0
+    assert b"u_hidden_dim" in emu.cdll.xw_last_error()
+    d = xw._lib.Dims(5, 20, 10, 8, 50, 9, 7)
+    assert emu.cdll.xw_workspace_bytes(C.byref(d), 10, 5) == 0
+    assert b"solver" in emu.cdll.xw_last_error()

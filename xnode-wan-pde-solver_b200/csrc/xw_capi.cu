@@ -1,0 +1,394 @@
+// xw_capi.cu -- C ABI (include/xnode_wan_b200.h) over the kernels in xw_kernels.cuh.
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a -> libxnode_wan_b200.so.
+// The same file compiles with g++ -DXW_EMU -x c++ into the CPU logic-test library
+// (tests/host_emu); that build is test infrastructure and is never shipped or loaded by the
+// product package.
+#include "../../include/xnode_wan_b200.h"
+#include "xw_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#ifdef XW_EMU
+struct Dev { int sms = 2; size_t smem_optin = 227 * 1024; };
+const Dev* device() { static Dev d; return &d; }
+#define XW_LAUNCH(kern, grid, block, smem, stream, ...)                              \
+    do { emu::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); }); } while (0)
+#define XW_CHECK_LAUNCH(name) 0
+#define XW_SET_SMEM(kern, bytes) 0
+#else
+struct Dev { int sms; size_t smem_optin; };
+const Dev* device() {
+    static Dev d{0, 0};
+    static bool init = false, ok = false;
+    if (!init) {
+        init = true;
+        int dev = 0;
+        cudaDeviceProp p;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
+            d.sms = p.multiProcessorCount;
+            d.smem_optin = p.sharedMemPerBlockOptin;
+            ok = true;
+        }
+    }
+    return ok ? &d : nullptr;
+}
+#define XW_LAUNCH(kern, grid, block, smem, stream, ...) \
+    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+int check_launch(const char* name) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("%s: launch failed: %s", name, cudaGetErrorString(e));
+    return 0;
+}
+#define XW_CHECK_LAUNCH(name) check_launch(name)
+template <class K>
+int set_smem(K kern, size_t bytes, const char* name) {
+    if (bytes <= 48 * 1024) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail("%s: cannot opt in to %zu bytes of shared memory: %s", name, bytes, cudaGetErrorString(e));
+    return 0;
+}
+#define XW_SET_SMEM(kern, bytes) set_smem(kern, bytes, #kern)
+#endif
+
+// compiled capacities (exact for configs/cube_pde.yaml: H=20, hh=10, Hv=50); smaller nets are
+// zero-padded into them, larger ones are rejected (no silent fallback).
+constexpr int kH = 20, kHH = 10, kHV = 50;
+constexpr int kBlkFwd = 128;
+
+int check_dims(const xw_dims* m) {
+    if (!m) return fail("dims is NULL");
+    if (m->d < 1) return fail("dim must be >= 1 (got %d)", m->d);
+    if (m->H < 1 || m->H > kH) return fail("u_hidden_dim %d unsupported (compiled capacity %d)", m->H, kH);
+    if (m->hh < 1 || m->hh > kHH) return fail("u_hidden_hidden_dim %d unsupported (compiled capacity %d)", m->hh, kHH);
+    if (m->nu < 1) return fail("u_layers %d unsupported (need >= 1)", m->nu);
+    if ((m->nu - 1) * kHH > 128) return fail("u_layers %d unsupported (relu-mask stack holds %d layers)", m->nu, 128 / kHH + 1);
+    if (m->Hv < 1 || m->Hv > kHV) return fail("v_hidden_dim %d unsupported (compiled capacity %d)", m->Hv, kHV);
+    if (m->nv < 0 || m->nv > xw::kMaxNv) return fail("v_layers %d unsupported (max %d)", m->nv, xw::kMaxNv);
+    if (m->solver < 0 || m->solver > 2) return fail("solver %d unsupported (0 euler, 1 midpoint, 2 rk4)", m->solver);
+    return 0;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int stages_of(int solver) { return solver == 0 ? 1 : solver == 1 ? 2 : 4; }
+int bwd_block(int solver) { return solver == 2 ? 64 : 128; }
+
+size_t smem_xnode_fwd(int d, int L) {
+    using S = xw::USmem<kH, kHH>;
+    return (size_t)(xw::pad4(S::size(d)) + xw::pad4(L) + 4) * 4 + 32 * 8;
+}
+size_t smem_xnode_bwd(const xw_dims* m, int L, int block) {
+    using S = xw::USmem<kH, kHH>;
+    const int nw = block / 32;
+    const xw::ULayout g(m->d, m->H, m->hh);
+    size_t f = (size_t)xw::pad4(S::size(m->d)) + xw::pad4(L) + 4;
+    f += (size_t)stages_of(m->solver) * m->nu * kHH * block;       // (nsh+1) = nu
+    f += (size_t)nw * 128 * xw::kStgLd;
+    f += (size_t)nw * xw::pad4(g.size);
+    return f * 4 + 32 * 8;
+}
+size_t smem_vnet_fwd(int d) {
+    using S = xw::VSmem<kHV>;
+    return (size_t)(xw::pad4(S::size(d + 1)) + 4) * 4 + 4 * 32 * 8;
+}
+size_t smem_vnet_bwd(const xw_dims* m, int block) {
+    using S = xw::VSmem<kHV>;
+    const int nw = block / 32;
+    const xw::VLayout g(m->d, m->Hv);
+    size_t f = (size_t)xw::pad4(S::size(m->d + 1));
+    f += (size_t)nw * 128 * xw::kStgLd;
+    f += (size_t)nw * xw::pad4(g.size);
+    return f * 4;
+}
+
+int grid_for(long long items, int block, int ctas_per_sm) {
+    const Dev* dv = device();
+    long long want = (items + block - 1) / block;
+    long long cap = (long long)dv->sms * ctas_per_sm;
+    return (int)std::max<long long>(1, std::min(want, cap));
+}
+int ctas_per_sm_for(size_t smem, int cap) {
+    const Dev* dv = device();
+    int k = (int)((dv->smem_optin + 1024) / (smem + 1024));
+    return std::max(1, std::min(k, cap));
+}
+
+template <int MODE>
+int launch_xnode_fwd(const xw_dims* m, const xw::XnodeFwdArgs& a, int grid, size_t smem, void* stream) {
+    using namespace xw;
+#define XW_CASE(SOLV)                                                                       \
+    case SOLV: {                                                                            \
+        if (XW_SET_SMEM((k_xnode_fwd<kH, kHH, SOLV, MODE>), smem)) return 1;                \
+        XW_LAUNCH((k_xnode_fwd<kH, kHH, SOLV, MODE>), grid, kBlkFwd, smem, stream, a);      \
+        break;                                                                              \
+    }
+    switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
+#undef XW_CASE
+    return XW_CHECK_LAUNCH("k_xnode_fwd");
+}
+
+template <int MODE>
+int launch_xnode_bwd(const xw_dims* m, const xw::XnodeBwdArgs& a, int grid, int block, size_t smem, void* stream) {
+    using namespace xw;
+#define XW_CASE(SOLV)                                                                       \
+    case SOLV: {                                                                            \
+        if (XW_SET_SMEM((k_xnode_bwd<kH, kHH, SOLV, MODE>), smem)) return 1;                \
+        XW_LAUNCH((k_xnode_bwd<kH, kHH, SOLV, MODE>), grid, block, smem, stream, a);        \
+        break;                                                                              \
+    }
+    switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
+#undef XW_CASE
+    return XW_CHECK_LAUNCH("k_xnode_bwd");
+}
+
+xw::PointsView view_of(const xw_points* p) {
+    xw::PointsView v;
+    v.t = p->t; v.t_sn = p->t_sn; v.t_sl = p->t_sl;
+    v.x = p->x; v.x_sn = p->x_sn; v.x_sl = p->x_sl;
+    return v;
+}
+
+int reduce_partials(const float* gpart, int nblocks, int P, float* out, int accumulate, void* stream) {
+    XW_LAUNCH(xw::k_reduce_partials, (P + 127) / 128, 128, 0, stream, gpart, nblocks, P, out, accumulate);
+    return XW_CHECK_LAUNCH("k_reduce_partials");
+}
+
+struct XnodeBwdPlan { int block, grid; size_t smem, hist_bytes, part_bytes; };
+int plan_xnode_bwd(const xw_dims* m, int n, int L, XnodeBwdPlan* p) {
+    const Dev* dv = device();
+    p->block = bwd_block(m->solver);
+    p->smem = smem_xnode_bwd(m, L, p->block);
+    if (p->smem > dv->smem_optin)
+        return fail("xnode backward needs %zu B shared memory per CTA (> %zu): u_layers/N_t/dim too large", p->smem, dv->smem_optin);
+    p->grid = grid_for(n, p->block, ctas_per_sm_for(p->smem, 8));
+    p->hist_bytes = align_up((size_t)L * kH * p->grid * p->block * 4, 256);
+    p->part_bytes = align_up((size_t)p->grid * xw::ULayout(m->d, m->H, m->hh).size * 4, 256);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xw_abi_version(void) { return XW_ABI_VERSION; }
+const char* xw_last_error(void) { return g_err; }
+
+int xw_theta_u_size(const xw_dims* m) { return m ? xw::ULayout(m->d, m->H, m->hh).size : -1; }
+int xw_theta_v_size(const xw_dims* m) { return m ? xw::VLayout(m->d, m->Hv).size : -1; }
+
+size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
+    if (check_dims(m) || !device() || n < 1 || L < 1) return 0;
+    // interior forward: du[n*d] + u[n*L] + yhist
+    int gf = grid_for(n, kBlkFwd, 8);
+    size_t fwd = align_up((size_t)n * m->d * 4, 256) + align_up((size_t)n * L * 4, 256) +
+                 align_up((size_t)L * kH * gf * kBlkFwd * 4, 256);
+    XnodeBwdPlan pb;
+    if (plan_xnode_bwd(m, n, L, &pb)) return 0;
+    size_t bwd_u = pb.hist_bytes + pb.part_bytes;
+    const int vb = 128;
+    int gv = grid_for((long long)n * L, vb, ctas_per_sm_for(smem_vnet_bwd(m, vb), 8));
+    size_t bwd_v = align_up((size_t)gv * xw::VLayout(m->d, m->Hv).size * 4, 256);
+    return std::max(fwd, std::max(bwd_u, bwd_v)) + 1024;
+}
+
+int xw_xnode_eval(const xw_dims* m, const float* theta_u, const float* x, long long x_sn, const float* times,
+                  int L, const float* s0, int n, float* u_out, void* stream) {
+    if (check_dims(m)) return 1;
+    if (!device()) return fail("no CUDA device");
+    if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
+    if (!theta_u || !x || !times || !s0 || !u_out) return fail("NULL pointer argument");
+    xw::XnodeFwdArgs a{};
+    a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
+    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0; a.u_out = u_out;
+    return launch_xnode_fwd<0>(m, a, grid_for(n, kBlkFwd, 8), smem_xnode_fwd(m->d, L), stream);
+}
+
+int xw_vnet_eval(const xw_dims* m, const float* theta_v, const xw_points* pts, int n, int L, float* v_out, void* stream) {
+    if (check_dims(m)) return 1;
+    if (!device()) return fail("no CUDA device");
+    if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
+    if (!theta_v || !pts || !pts->t || !pts->x || !v_out) return fail("NULL pointer argument");
+    xw::VnetFwdArgs a{};
+    a.d = m->d; a.Hvr = m->Hv; a.nv = m->nv; a.n = n; a.L = L; a.theta = theta_v; a.p = view_of(pts);
+    a.v_out = v_out;
+    const size_t smem = smem_vnet_fwd(m->d);
+    if (XW_SET_SMEM((xw::k_vnet_points<kHV, 0>), smem)) return 1;
+    XW_LAUNCH((xw::k_vnet_points<kHV, 0>), grid_for((long long)n * L, 128, 8), 128, smem, stream, a);
+    return XW_CHECK_LAUNCH("k_vnet_points<eval>");
+}
+
+int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* coef, const float* theta_u,
+                        const float* theta_v, const float* x, long long x_sn, const float* times, int L,
+                        const xw_points* xv, const float* h, const float* grad_h, const float* f, int n,
+                        double* sums, float* cot_u, float* cot_v, float* u_out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (check_dims(m)) return 1;
+    if (!device()) return fail("no CUDA device");
+    if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
+    if (!dom || !coef || !theta_u || !theta_v || !x || !times || !xv || !xv->t || !xv->x || !h || !grad_h || !f ||
+        !sums || !cot_u || !cot_v || !workspace)
+        return fail("NULL pointer argument");
+    if (dom->kind < 0 || dom->kind > 2) return fail("unknown domain kind %d", dom->kind);
+    const int gf = grid_for(n, kBlkFwd, 8);
+    const size_t du_b = align_up((size_t)n * m->d * 4, 256), u_b = align_up((size_t)n * L * 4, 256);
+    const size_t hist_b = align_up((size_t)L * kH * gf * kBlkFwd * 4, 256);
+    if (workspace_bytes < du_b + u_b + hist_b) return fail("workspace too small: %zu < %zu", workspace_bytes, du_b + u_b + hist_b);
+    char* ws = (char*)workspace;
+    float* du = (float*)ws;
+    float* ubuf = u_out ? u_out : (float*)(ws + du_b);
+    float* yhist = (float*)(ws + du_b + u_b);
+
+    xw::XnodeFwdArgs a{};
+    a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
+    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = h; a.u_out = ubuf;
+    a.grad_h = grad_h; a.du_out = du; a.yhist = yhist; a.sums = sums;
+    if (launch_xnode_fwd<1>(m, a, gf, smem_xnode_fwd(m->d, L), stream)) return 1;
+
+    xw::VnetFwdArgs b{};
+    b.d = m->d; b.Hvr = m->Hv; b.nv = m->nv; b.n = n; b.L = L; b.theta = theta_v; b.p = view_of(xv);
+    b.dom_kind = dom->kind; b.dp0 = dom->p0; b.dp1 = dom->p1; b.dp2 = dom->p2;
+    b.c0 = coef->c0; b.c1 = coef->c1; b.ca = coef->a; b.cb = coef->b;
+    b.u = ubuf; b.du = du; b.h = h; b.f = f; b.sums = sums; b.cot_u = cot_u; b.cot_v = cot_v; b.v_out = nullptr;
+    const size_t smem = smem_vnet_fwd(m->d);
+    if (XW_SET_SMEM((xw::k_vnet_points<kHV, 1>), smem)) return 1;
+    XW_LAUNCH((xw::k_vnet_points<kHV, 1>), grid_for((long long)n * L, 128, 8), 128, smem, stream, b);
+    return XW_CHECK_LAUNCH("k_vnet_points<interior>");
+}
+
+int xw_boundary_u(const xw_dims* m, const float* theta_u, const float* xb, long long xb_sn, const float* times_b,
+                  int Lb, const float* s0b, const float* g, int nb, double gscale, double* sums, float* grad_u,
+                  int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+    if (check_dims(m)) return 1;
+    if (!device()) return fail("no CUDA device");
+    if (nb < 1 || Lb < 1) return fail("empty batch (n=%d, L=%d)", nb, Lb);
+    if (!theta_u || !xb || !times_b || !s0b || !g || !sums || !workspace) return fail("NULL pointer argument");
+    XnodeBwdPlan p;
+    if (plan_xnode_bwd(m, nb, Lb, &p)) return 1;
+    if (workspace_bytes < p.hist_bytes + p.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, p.hist_bytes + p.part_bytes);
+    xw::XnodeBwdArgs a{};
+    a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = Lb; a.n = nb;
+    a.theta = theta_u; a.x = xb; a.x_sn = xb_sn; a.times = times_b; a.s0 = s0b; a.cot = g; a.coefs = nullptr;
+    a.gscale = gscale; a.yhist = (float*)workspace; a.gpart = (float*)((char*)workspace + p.hist_bytes); a.sums = sums;
+    if (launch_xnode_bwd<1>(m, a, p.grid, p.block, p.smem, stream)) return 1;
+    if (grad_u) return reduce_partials(a.gpart, p.grid, xw_theta_u_size(m), grad_u, accumulate, stream);
+    return 0;
+}
+
+int xw_interior_backward_u(const xw_dims* m, const float* theta_u, const float* x, long long x_sn, const float* times,
+                           int L, const float* h, const float* cot_u, int n, const double* coefs_dev, float* grad_u,
+                           int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+    if (check_dims(m)) return 1;
+    if (!device()) return fail("no CUDA device");
+    if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
+    if (!theta_u || !x || !times || !h || !cot_u || !coefs_dev || !grad_u || !workspace) return fail("NULL pointer argument");
+    XnodeBwdPlan p;
+    if (plan_xnode_bwd(m, n, L, &p)) return 1;
+    if (workspace_bytes < p.hist_bytes + p.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, p.hist_bytes + p.part_bytes);
+    xw::XnodeBwdArgs a{};
+    a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
+    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = h; a.cot = cot_u; a.coefs = coefs_dev;
+    a.gscale = 0.0; a.yhist = (float*)workspace; a.gpart = (float*)((char*)workspace + p.hist_bytes); a.sums = nullptr;
+    if (launch_xnode_bwd<0>(m, a, p.grid, p.block, p.smem, stream)) return 1;
+    return reduce_partials(a.gpart, p.grid, xw_theta_u_size(m), grad_u, accumulate, stream);
+}
+
+int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* theta_v, const xw_points* xv,
+                           const float* cot_v, int n, int L, const double* coefs_dev, float* grad_v, int accumulate,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    if (check_dims(m)) return 1;
+    if (!device()) return fail("no CUDA device");
+    if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
+    if (!dom || !theta_v || !xv || !xv->t || !xv->x || !cot_v || !coefs_dev || !grad_v || !workspace)
+        return fail("NULL pointer argument");
+    const int block = 128;
+    const size_t smem = smem_vnet_bwd(m, block);
+    if (smem > device()->smem_optin) return fail("v backward needs %zu B shared memory per CTA (> %zu)", smem, device()->smem_optin);
+    const int grid = grid_for((long long)n * L, block, ctas_per_sm_for(smem, 8));
+    const int P = xw_theta_v_size(m);
+    if (workspace_bytes < (size_t)grid * P * 4) return fail("workspace too small: %zu < %zu", workspace_bytes, (size_t)grid * P * 4);
+    xw::VnetBwdArgs a{};
+    a.d = m->d; a.Hvr = m->Hv; a.nv = m->nv; a.n = n; a.L = L; a.theta = theta_v; a.p = view_of(xv);
+    a.dom_kind = dom->kind; a.dp0 = dom->p0; a.dp1 = dom->p1; a.dp2 = dom->p2;
+    a.cot = cot_v; a.coefs = coefs_dev; a.gpart = (float*)workspace;
+    if (XW_SET_SMEM((xw::k_vnet_bwd<kHV>), smem)) return 1;
+    XW_LAUNCH((xw::k_vnet_bwd<kHV>), grid, block, smem, stream, a);
+    if (XW_CHECK_LAUNCH("k_vnet_bwd")) return 1;
+    return reduce_partials(a.gpart, grid, P, grad_v, accumulate, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// FP32 FMA micro-benchmark (roofline denominator)
+// ---------------------------------------------------------------------------------------------
+#ifndef XW_EMU
+namespace {
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_fma_probe(int iters, float* sink, float seed) {
+    // 16 independent accumulator chains per thread
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i);
+    const float b = 1.0000001f, c = 1e-7f;
+    if (VARIANT == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+        }
+    } else {
+        // packed FFMA2 (fma.rn.f32x2, sm_100+)
+        unsigned long long p[8], pb, pc;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b), "f"(b));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(pc) : "f"(c), "f"(c));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(p[i]) : "f"(a[2 * i]), "f"(a[2 * i + 1]));
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pb), "l"(pc));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(a[2 * i]), "=f"(a[2 * i + 1]) : "l"(p[i]));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;
+}
+}  // namespace
+#endif
+
+extern "C" int xw_fma_probe(int variant, int iters, double* flops_host, void* stream) {
+#ifdef XW_EMU
+    (void)variant; (void)iters; (void)flops_host; (void)stream;
+    return fail("xw_fma_probe needs a CUDA device");
+#else
+    const Dev* dv = device();
+    if (!dv) return fail("no CUDA device");
+    static float* sink = nullptr;
+    if (!sink && cudaMalloc(&sink, 256) != cudaSuccess) return fail("cudaMalloc failed");
+    const int grid = dv->sms * 8, block = 256;
+    if (variant == 0) k_fma_probe<0><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink, 1.f);
+    else k_fma_probe<1><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink, 1.f);
+    if (flops_host) *flops_host = 2.0 * 16 * 8 * (double)iters * (double)grid * block;
+    return check_launch("k_fma_probe");
+#endif
+}

@@ -1,0 +1,718 @@
+// xw_kernels.cuh -- the __global__ kernels of the hot path (generation 1: one thread per path /
+// per point; see DESIGN.md for the roofline of each).  Compiles for sm_100a with nvcc and, for the
+// CPU-side logic tests only, with g++ -DXW_EMU.
+#pragma once
+#include "xw_nets.cuh"
+
+#ifdef XW_EMU
+#define XW_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#else
+#define XW_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+namespace xw {
+
+struct PointsView {
+    const float* t; long long t_sn, t_sl;
+    const float* x; long long x_sn, x_sl;
+};
+
+// block-level sum of NV doubles per thread -> atomicAdd into out[idx[k]]
+template <int NV>
+XW_DEV void block_sum_to_global(double (&v)[NV], double* red /* smem [NV][32] */, double* out, const int (&idx)[NV]) {
+    const int lane = XW_TID & 31, warp = XW_TID >> 5, nw = XW_BDIM >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = warp_sum_d(v[k]);
+        if (lane == 0) red[k * 32 + warp] = s;
+    }
+    XW_SYNCTHREADS();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = lane < nw ? red[k * 32 + lane] : 0.0;
+            s = warp_sum_d(s);
+            if (lane == 0 && out) XW_ATOMIC_ADD_D(out + idx[k], s);
+        }
+    }
+    XW_SYNCTHREADS();
+}
+
+// =============================================================================================
+// XNODE forward (+ the "ones" reverse sweep giving du = grad_x sum_l u)
+// MODE 0: u only (forward evaluation)          MODE 1: interior forward (u, du, init sum)
+// =============================================================================================
+struct XnodeFwdArgs {
+    int d, Hr, HHr, nsh, L, n;
+    const float* theta; const float* x; long long x_sn; const float* times; const float* s0;
+    float* u_out;
+    const float* grad_h; float* du_out; float* yhist; double* sums;
+};
+
+template <int H, int HH>
+XW_DEV void hoist_ax(const float* sw, const float* XW_RESTRICT xp, int d, float (&ax)[HH]) {
+    using S = USmem<H, HH>;
+    load_row<HH>(sw + S::BA, ax);
+    for (int j = 0; j < d; ++j) {
+        float w[HH];
+        load_row<HH>(sw + S::WXT + j * S::HHP, w);
+        const float xj = xp[j];
+#pragma unroll
+        for (int o = 0; o < HH; ++o) ax[o] = fmaf(w[o], xj, ax[o]);
+    }
+}
+
+template <int H, int HH>
+XW_DEV float project_u(const float* sw, const float (&y)[H]) {
+    using S = USmem<H, HH>;
+    float wo[H];
+    load_row<H>(sw + S::WO, wo);
+    float u0 = sw[S::BO], u1 = 0.f;
+#pragma unroll
+    for (int i = 0; i + 1 < H; i += 2) { u0 = fmaf(wo[i], y[i], u0); u1 = fmaf(wo[i + 1], y[i + 1], u1); }
+    if (H & 1) u0 = fmaf(wo[H - 1], y[H - 1], u0);
+    return u0 + u1;
+}
+
+// one explicit RK step y <- y + dt * sum_s b_s k_s, recording stage internals in rec[s] and
+// (optionally) the stage inputs in yin[s]
+template <int H, int HH, int SOLVER, class Rec, bool KEEP_YIN>
+XW_DEV void rk_step(const float* sw, const float (&ax)[HH], float t0, float dt, int nsh, float (&y)[H],
+                    Rec (&rec)[Tableau<SOLVER>::S], float (*yin_keep)[H]) {
+    using T = Tableau<SOLVER>;
+    float k[T::S][H];
+#pragma unroll
+    for (int s = 0; s < T::S; ++s) {
+        float yin[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) yin[i] = y[i];
+#pragma unroll
+        for (int r = 0; r < s; ++r) {
+            const float c = T::a(s, r);
+            if (c != 0.f) {
+                const float cd = c * dt;
+#pragma unroll
+                for (int i = 0; i < H; ++i) yin[i] = fmaf(cd, k[r][i], yin[i]);
+            }
+        }
+        if (KEEP_YIN) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) yin_keep[s][i] = yin[i];
+        }
+        float tau[HH];
+        field_fwd<H, HH>(sw, ax, fmaf(T::c(s), dt, t0), yin, nsh, k[s], tau, rec[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < T::S; ++s) {
+        const float c = T::b(s);
+        if (c != 0.f) {
+            const float cd = c * dt;
+#pragma unroll
+            for (int i = 0; i < H; ++i) y[i] = fmaf(cd, k[s][i], y[i]);
+        }
+    }
+}
+
+template <int H, int HH, int SOLVER, int MODE>
+XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
+    using S = USmem<H, HH>;
+    using T = Tableau<SOLVER>;
+    XW_DYN_SMEM(smem_raw);
+    float* sw = reinterpret_cast<float*>(smem_raw);
+    float* st = sw + pad4(S::size(a.d));
+    double* red = reinterpret_cast<double*>(st + pad4(a.L) + 4);
+    stage_theta_u<H, HH>(sw, a.theta, a.d, a.Hr, a.HHr);
+    for (int i = XW_TID; i < a.L; i += XW_BDIM) st[i] = a.times[i];
+    XW_SYNCTHREADS();
+
+    const long long nthr = (long long)XW_GDIM * XW_BDIM;
+    const long long gtid = (long long)XW_BID * XW_BDIM + XW_TID;
+    const int L = a.L, nsh = a.nsh;
+    double init_acc = 0.0;
+    for (long long n = gtid; n < a.n; n += nthr) {
+        const float* xp = a.x + n * a.x_sn;
+        float ax[HH];
+        hoist_ax<H, HH>(sw, xp, a.d, ax);
+        const float s0 = a.s0[n];
+        float y[H];
+        {
+            float z1[H], z2[H];
+            lift_fwd<H, HH>(sw, s0, z1, z2, y);
+        }
+        float u = project_u<H, HH>(sw, y);
+        if (a.u_out) a.u_out[n * L] = u;
+        if (MODE == 1) {
+            init_acc += (double)((u - s0) * (u - s0));
+#pragma unroll
+            for (int i = 0; i < H; ++i) a.yhist[(long long)i * nthr + gtid] = y[i];
+        }
+        for (int l = 0; l + 1 < L; ++l) {
+            const float t0 = st[l], dt = st[l + 1] - st[l];
+            RecNone<HH> rec[T::S];
+            rk_step<H, HH, SOLVER, RecNone<HH>, false>(sw, ax, t0, dt, nsh, y, rec, nullptr);
+            u = project_u<H, HH>(sw, y);
+            if (a.u_out) a.u_out[n * L + l + 1] = u;
+            if (MODE == 1 && l + 2 < L) {
+#pragma unroll
+                for (int i = 0; i < H; ++i) a.yhist[((long long)(l + 1) * H + i) * nthr + gtid] = y[i];
+            }
+        }
+        if (MODE == 1) {
+            // reverse sweep with cotangent 1 on every u[l]: lam = d sum_l u_l / d y_l
+            float lam[H], a0[HH];
+            load_row<H>(sw + S::WO, lam);
+#pragma unroll
+            for (int i = 0; i < HH; ++i) a0[i] = 0.f;
+            for (int l = L - 2; l >= 0; --l) {
+                const float t0 = st[l], dt = st[l + 1] - st[l];
+                float yl[H];
+#pragma unroll
+                for (int i = 0; i < H; ++i) yl[i] = a.yhist[((long long)l * H + i) * nthr + gtid];
+                RecBits<HH> rec[T::S];
+#pragma unroll
+                for (int s = 0; s < T::S; ++s) rec[s].m.clear();
+                rk_step<H, HH, SOLVER, RecBits<HH>, false>(sw, ax, t0, dt, nsh, yl, rec, nullptr);
+                float kbar[T::S][H], ybar[H];
+#pragma unroll
+                for (int s = 0; s < T::S; ++s)
+#pragma unroll
+                    for (int i = 0; i < H; ++i) kbar[s][i] = (T::b(s) * dt) * lam[i];
+#pragma unroll
+                for (int i = 0; i < H; ++i) ybar[i] = lam[i];
+#pragma unroll
+                for (int s = T::S - 1; s >= 0; --s) {
+                    float gin[H];
+#pragma unroll
+                    for (int i = 0; i < H; ++i) gin[i] = 0.f;
+                    field_rev_bits<H, HH>(sw, rec[s], nsh, kbar[s], gin, a0);
+#pragma unroll
+                    for (int i = 0; i < H; ++i) ybar[i] += gin[i];
+#pragma unroll
+                    for (int r = 0; r < s; ++r) {
+                        const float c = T::a(s, r);
+                        if (c != 0.f) {
+                            const float cd = c * dt;
+#pragma unroll
+                            for (int i = 0; i < H; ++i) kbar[r][i] = fmaf(cd, gin[i], kbar[r][i]);
+                        }
+                    }
+                }
+                float wo[H];
+                load_row<H>(sw + S::WO, wo);
+#pragma unroll
+                for (int i = 0; i < H; ++i) lam[i] = ybar[i] + wo[i];
+            }
+            // lift reverse: d/ds0 (s0 = h(x) depends on x through grad_h)
+            float z1[H], z2[H], y0[H];
+            lift_fwd<H, HH>(sw, s0, z1, z2, y0);
+            float dz2[H], dz1[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) { dz2[i] = 0.f; dz1[i] = 0.f; }
+            matvec_acc<H, H, S::HP>(sw + S::W2, lam, dz2);
+#pragma unroll
+            for (int i = 0; i < H; ++i) dz2[i] = z2[i] > 0.f ? dz2[i] : 0.f;
+            matvec_acc<H, H, S::HP>(sw + S::W1, dz2, dz1);
+            float gs = 0.f;
+#pragma unroll
+            for (int i = 0; i < H; ++i) gs = fmaf(z1[i] > 0.f ? dz1[i] : 0.f, sw[S::W0 + i], gs);
+            for (int j = 0; j < a.d; ++j) {
+                float w[HH];
+                load_row<HH>(sw + S::WXT + j * S::HHP, w);
+                float g = gs * a.grad_h[n * a.d + j];
+#pragma unroll
+                for (int o = 0; o < HH; ++o) g = fmaf(w[o], a0[o], g);
+                a.du_out[n * a.d + j] = g;
+            }
+        }
+    }
+    if (MODE == 1) {
+        double v[1] = {init_acc};
+        const int idx[1] = {4};
+        block_sum_to_global<1>(v, red, a.sums, idx);
+    }
+}
+
+// =============================================================================================
+// v net over all points.  MODE 0: v only.  MODE 1: interior forward sums + cotangent seeds
+// (reference src/loss.py:46-76; time derivative of phi and, on time-row 0, grad_x phi)
+// =============================================================================================
+struct VnetFwdArgs {
+    int d, Hvr, nv, n, L;
+    const float* theta; PointsView p;
+    int dom_kind; float dp0, dp1, dp2;
+    float c0, c1; const float* ca; const float* cb;
+    const float* u; const float* du; const float* h; const float* f;
+    double* sums; float* cot_u; float* cot_v; float* v_out;
+};
+
+template <int HV, int MODE>
+XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
+    using S = VSmem<HV>;
+    XW_DYN_SMEM(smem_raw);
+    float* sv = reinterpret_cast<float*>(smem_raw);
+    double* red = reinterpret_cast<double*>(sv + pad4(S::size(a.d + 1)) + 4);
+    stage_theta_v<HV>(sv, a.theta, a.d, a.Hvr);
+    const long long nthr = (long long)XW_GDIM * XW_BDIM;
+    const long long gtid = (long long)XW_BID * XW_BDIM + XW_TID;
+    const long long npts = (long long)a.n * a.L;
+    const int L = a.L, d = a.d;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long p = gtid; p < npts; p += nthr) {
+        const long long n = p / L;
+        const int l = (int)(p - n * L);
+        const float t = a.p.t[n * a.p.t_sn + l * a.p.t_sl];
+        const float* xp = a.p.x + n * a.p.x_sn + l * a.p.x_sl;
+        unsigned long long masks[kMaxNv];
+        float tau[HV];
+        const float v = vnet_fwd<HV>(sv, t, xp, d, a.nv, masks, tau, StoreNone());
+        if (MODE == 0) { a.v_out[p] = v; continue; }
+        float dl[HV];
+        vnet_rev_bits<HV>(sv, a.nv, masks, tau, 1.f, dl);
+        const float dv_t = vnet_input_grad<HV>(sv, 0, dl);
+        const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, t, xp, d);
+        const float phi = v * W.w;
+        const float dphi0 = fmaf(W.w, dv_t, v * W.dw_t);
+        const float u = a.u[p], fv = a.f[p];
+        const float cu_ = fmaf(a.c1, u, a.c0);
+        const float A = cu_ * u, Ap = fmaf(a.c1, u, cu_);
+        float s1 = 0.f, s3 = (A + fv) * phi;
+        float cu = Ap * phi, cv = W.w * (A + fv);
+        if (l == L - 1) { s1 = fmaf(u, v, s1); cu = fmaf((float)L, v, cu); cv = fmaf((float)L, u, cv); }
+        if (l == 0) {
+            const float hn = a.h[n];
+            s1 = fmaf(-hn, v, s1);
+            cv = fmaf(-(float)L, hn, cv);
+            const float* dun = a.du + n * d;
+            float s31 = 0.f;
+            for (int i = 0; i < d; ++i) {
+                const float dphi_i = fmaf(W.w, vnet_input_grad<HV>(sv, 1 + i, dl), v * domain_dw_x(W, i, xp));
+                float q;
+                if (a.ca) {
+                    q = 0.f;
+                    for (int j = 0; j < d; ++j) q = fmaf(a.ca[i * d + j], dun[j], q);
+                } else {
+                    q = dun[i];
+                }
+                s31 = fmaf(dphi_i, q, s31);
+            }
+            if (a.cb) {
+                float bq = 0.f;
+                for (int j = 0; j < d; ++j) bq = fmaf(a.cb[j], dun[j], bq);
+                s31 = fmaf(phi, bq, s31);
+            }
+            s3 += s31;
+        }
+        a.cot_u[p] = cu;
+        a.cot_v[p] = cv;
+        if (a.v_out) a.v_out[p] = v;
+        acc[0] += (double)s1;
+        acc[1] += (double)(u * dphi0);
+        acc[2] += (double)s3;
+        acc[3] += (double)(v * v);
+    }
+    if (MODE == 1) {
+        const int idx[4] = {0, 1, 2, 3};
+        block_sum_to_global<4>(acc, red, a.sums, idx);
+    }
+}
+
+// =============================================================================================
+// XNODE backward: parameter gradients of sum_l G[n,l] u[n,l]
+// MODE 0 interior: G = k0*cot_u + k2 + [l=0] k1 (u0 - h)      (G_u)
+// MODE 1 boundary: G = 2*gscale*(u - g), and sums[BDRY] += sum (u-g)^2   (src/loss.py:83-85)
+// =============================================================================================
+struct XnodeBwdArgs {
+    int d, Hr, HHr, nsh, L, n;
+    const float* theta; const float* x; long long x_sn; const float* times; const float* s0;
+    const float* cot;            // MODE 0: cot_u[n*L]   MODE 1: g[n*L]
+    const double* coefs;         // MODE 0: device k0,k1,k2
+    double gscale;               // MODE 1
+    float* yhist; float* gpart; double* sums;
+};
+
+template <int O, int I>
+struct OuterShape {
+    static constexpr int NBI = I <= 2 ? I : (I <= 24 ? 6 : 8);
+    static constexpr int BI = (I + NBI - 1) / NBI;
+    static constexpr int NBO = 32 / NBI;
+    static constexpr int BOfull = (O + NBO - 1) / NBO;
+    static constexpr int BOcap = (49 / BI) < 1 ? 1 : (49 / BI);
+    static constexpr int BO = BOfull < BOcap ? BOfull : BOcap;
+    static constexpr int rows_d = ((O + NBO * BO - 1) / (NBO * BO)) * (NBO * BO);
+    static constexpr int rows_r = NBI * BI;
+};
+
+template <int O, int I, class Dst>
+XW_DEV void outer_auto(const float (&dl)[O], const float (&r)[I], float* stg, Dst dst) {
+    using Sh = OuterShape<O, I>;
+    warp_outer<O, I, Sh::BO, Sh::NBO, Sh::BI, Sh::NBI>(dl, r, stg, stg + 64 * kStgLd, dst);
+}
+
+// reverse of one field evaluation with parameter gradients
+template <int H, int HH>
+XW_DEV void field_rev_grads(const float* sw, const float* acts, int stride, int nsh, float tstage,
+                            const float (&yin)[H], const float (&gout)[H], float (&gy)[H], float (&a0)[HH],
+                            float* stg, float* gw, const ULayout& g) {
+    using S = USmem<H, HH>;
+    const int Hr = g.H, HHr = g.hh;
+    float tau1[HH + 1];
+#pragma unroll
+    for (int i = 0; i < HH; ++i) tau1[i] = acts[(nsh * HH + i) * stride];
+    tau1[HH] = 1.f;
+    outer_auto<H, HH + 1>(gout, tau1, stg, [&](int o, int i) -> float* {
+        if (o >= Hr) return nullptr;
+        if (i == HH) return gw + g.bf + o;
+        return i < HHr ? gw + g.Wf + o * HHr + i : nullptr;
+    });
+    float dl[HH];
+#pragma unroll
+    for (int i = 0; i < HH; ++i) dl[i] = 0.f;
+    matvec_acc<H, HH, S::HHP>(sw + S::WF, gout, dl);
+#pragma unroll
+    for (int i = 0; i < HH; ++i) dl[i] *= (1.f - tau1[i] * tau1[i]);
+    for (int j = nsh; j > 0; --j) {
+        float r1[HH + 1];
+#pragma unroll
+        for (int i = 0; i < HH; ++i) r1[i] = acts[((j - 1) * HH + i) * stride];
+        r1[HH] = 1.f;
+        outer_auto<HH, HH + 1>(dl, r1, stg, [&](int o, int i) -> float* {
+            if (o >= HHr) return nullptr;
+            if (i == HH) return gw + g.bs + o;
+            return i < HHr ? gw + g.Ws + o * HHr + i : nullptr;
+        });
+        float dn[HH];
+#pragma unroll
+        for (int i = 0; i < HH; ++i) dn[i] = 0.f;
+        matvec_acc<HH, HH, S::HHP>(sw + S::WS, dl, dn);
+#pragma unroll
+        for (int i = 0; i < HH; ++i) dl[i] = r1[i] > 0.f ? dn[i] : 0.f;
+    }
+    float yt1[H + 2];
+#pragma unroll
+    for (int i = 0; i < H; ++i) yt1[i] = yin[i];
+    yt1[H] = tstage;
+    yt1[H + 1] = 1.f;
+    outer_auto<HH, H + 2>(dl, yt1, stg, [&](int o, int i) -> float* {
+        if (o >= HHr) return nullptr;
+        if (i == H + 1) return gw + g.ba + o;
+        if (i == H) return gw + g.Wa + o * g.lda + g.d;
+        return i < Hr ? gw + g.Wa + o * g.lda + g.d + 1 + i : nullptr;
+    });
+#pragma unroll
+    for (int i = 0; i < HH; ++i) a0[i] += dl[i];
+    matvec_acc<HH, H, S::HP>(sw + S::WY, dl, gy);
+}
+
+template <int H, int HH, int SOLVER, int MODE>
+XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
+    using S = USmem<H, HH>;
+    using T = Tableau<SOLVER>;
+    XW_DYN_SMEM(smem_raw);
+    const int nwarps = XW_BDIM >> 5, warp = XW_TID >> 5, lane = XW_TID & 31;
+    const ULayout g(a.d, a.Hr, a.HHr);
+    const int Pp = pad4(g.size);
+    float* sw = reinterpret_cast<float*>(smem_raw);
+    float* st = sw + pad4(S::size(a.d));
+    float* sacts = st + pad4(a.L) + 4;                                  // [S][(nsh+1)*HH][BDIM]
+    float* sstg = sacts + (size_t)T::S * (a.nsh + 1) * HH * XW_BDIM;    // [nwarps][128][kStgLd]
+    float* sgrad = sstg + (size_t)nwarps * 128 * kStgLd;                // [nwarps][Pp]
+    double* red = reinterpret_cast<double*>(sgrad + (size_t)nwarps * Pp);
+    stage_theta_u<H, HH>(sw, a.theta, a.d, a.Hr, a.HHr);
+    for (int i = XW_TID; i < a.L; i += XW_BDIM) st[i] = a.times[i];
+    for (int i = XW_TID; i < nwarps * Pp; i += XW_BDIM) sgrad[i] = 0.f;
+    XW_SYNCTHREADS();
+    float* stg = sstg + (size_t)warp * 128 * kStgLd;
+    float* gw = sgrad + (size_t)warp * Pp;
+
+    const long long nthr = (long long)XW_GDIM * XW_BDIM;
+    const long long gtid = (long long)XW_BID * XW_BDIM + XW_TID;
+    const int L = a.L, nsh = a.nsh;
+    float k0 = 0.f, k1 = 0.f, k2 = 0.f;
+    if (MODE == 0) { k0 = (float)a.coefs[0]; k1 = (float)a.coefs[1]; k2 = (float)a.coefs[2]; }
+    const float gsc2 = (float)(2.0 * a.gscale);
+    float gwo[H], gbo = 0.f;
+#pragma unroll
+    for (int i = 0; i < H; ++i) gwo[i] = 0.f;
+    double bd_acc = 0.0;
+    const long long iters = (a.n + nthr - 1) / nthr;
+    for (long long it = 0; it < iters; ++it) {
+        const long long nraw = it * nthr + gtid;
+        const bool active = nraw < a.n;
+        const long long n = active ? nraw : (long long)a.n - 1;
+        const float* xp = a.x + n * a.x_sn;
+        float ax[HH];
+        hoist_ax<H, HH>(sw, xp, a.d, ax);
+        const float s0 = a.s0[n];
+        float y[H];
+        {
+            float z1[H], z2[H];
+            lift_fwd<H, HH>(sw, s0, z1, z2, y);
+        }
+        for (int l = 0; l + 1 < L; ++l) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) a.yhist[((long long)l * H + i) * nthr + gtid] = y[i];
+            RecNone<HH> rec[T::S];
+            rk_step<H, HH, SOLVER, RecNone<HH>, false>(sw, ax, st[l], st[l + 1] - st[l], nsh, y, rec, nullptr);
+        }
+        // cotangent of u[n, l]
+        auto cot_at = [&](int l, float u) -> float {
+            if (!active) return 0.f;
+            if (MODE == 0) {
+                float G = fmaf(k0, a.cot[n * L + l], k2);
+                if (l == 0) G = fmaf(k1, u - s0, G);
+                return G;
+            } else {
+                const float r = u - a.cot[n * L + l];
+                bd_acc += (double)(r * r);
+                return gsc2 * r;
+            }
+        };
+        float lam[H], a0[HH];
+#pragma unroll
+        for (int i = 0; i < HH; ++i) a0[i] = 0.f;
+        {
+            const float G = cot_at(L - 1, project_u<H, HH>(sw, y));
+            float wo[H];
+            load_row<H>(sw + S::WO, wo);
+#pragma unroll
+            for (int i = 0; i < H; ++i) { lam[i] = wo[i] * G; gwo[i] = fmaf(G, y[i], gwo[i]); }
+            gbo += G;
+        }
+        for (int l = L - 2; l >= 0; --l) {
+            const float t0 = st[l], dt = st[l + 1] - st[l];
+            float yl[H], ycur[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) { yl[i] = a.yhist[((long long)l * H + i) * nthr + gtid]; ycur[i] = yl[i]; }
+            RecSmem<HH> rec[T::S];
+#pragma unroll
+            for (int s = 0; s < T::S; ++s) {
+                rec[s].base = sacts + (size_t)s * (nsh + 1) * HH * XW_BDIM + XW_TID;
+                rec[s].stride = XW_BDIM;
+                rec[s].nsh = nsh;
+            }
+            float yin[T::S][H];
+            rk_step<H, HH, SOLVER, RecSmem<HH>, true>(sw, ax, t0, dt, nsh, ycur, rec, yin);
+            float kbar[T::S][H], ybar[H];
+#pragma unroll
+            for (int s = 0; s < T::S; ++s)
+#pragma unroll
+                for (int i = 0; i < H; ++i) kbar[s][i] = (T::b(s) * dt) * lam[i];
+#pragma unroll
+            for (int i = 0; i < H; ++i) ybar[i] = lam[i];
+#pragma unroll
+            for (int s = T::S - 1; s >= 0; --s) {
+                float gin[H];
+#pragma unroll
+                for (int i = 0; i < H; ++i) gin[i] = 0.f;
+                field_rev_grads<H, HH>(sw, rec[s].base, XW_BDIM, nsh, fmaf(T::c(s), dt, t0), yin[s], kbar[s], gin, a0,
+                                       stg, gw, g);
+#pragma unroll
+                for (int i = 0; i < H; ++i) ybar[i] += gin[i];
+#pragma unroll
+                for (int r = 0; r < s; ++r) {
+                    const float c = T::a(s, r);
+                    if (c != 0.f) {
+                        const float cd = c * dt;
+#pragma unroll
+                        for (int i = 0; i < H; ++i) kbar[r][i] = fmaf(cd, gin[i], kbar[r][i]);
+                    }
+                }
+            }
+            const float G = cot_at(l, project_u<H, HH>(sw, yl));
+            float wo[H];
+            load_row<H>(sw + S::WO, wo);
+#pragma unroll
+            for (int i = 0; i < H; ++i) { lam[i] = fmaf(wo[i], G, ybar[i]); gwo[i] = fmaf(G, yl[i], gwo[i]); }
+            gbo += G;
+        }
+        // x part of the first field layer: dWa[:, j] += a0 (x) x_j
+        warp_outer_dyn<HH, 3>(a0, a.d, [&](int j) -> float { return xp[j]; }, stg, stg + 64 * kStgLd,
+                              [&](int o, int j) -> float* { return o < a.HHr ? gw + g.Wa + o * g.lda + j : nullptr; });
+        // lift reverse
+        float z1[H], z2[H], y0[H];
+        lift_fwd<H, HH>(sw, s0, z1, z2, y0);
+        {
+            float r1[H + 1];
+#pragma unroll
+            for (int i = 0; i < H; ++i) r1[i] = z2[i];
+            r1[H] = 1.f;
+            outer_auto<H, H + 1>(lam, r1, stg, [&](int o, int i) -> float* {
+                if (o >= a.Hr) return nullptr;
+                if (i == H) return gw + g.b2 + o;
+                return i < a.Hr ? gw + g.W2 + o * a.Hr + i : nullptr;
+            });
+        }
+        float dz2[H], dz1[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) { dz2[i] = 0.f; dz1[i] = 0.f; }
+        matvec_acc<H, H, S::HP>(sw + S::W2, lam, dz2);
+#pragma unroll
+        for (int i = 0; i < H; ++i) dz2[i] = z2[i] > 0.f ? dz2[i] : 0.f;
+        {
+            float r1[H + 1];
+#pragma unroll
+            for (int i = 0; i < H; ++i) r1[i] = z1[i];
+            r1[H] = 1.f;
+            outer_auto<H, H + 1>(dz2, r1, stg, [&](int o, int i) -> float* {
+                if (o >= a.Hr) return nullptr;
+                if (i == H) return gw + g.b1 + o;
+                return i < a.Hr ? gw + g.W1 + o * a.Hr + i : nullptr;
+            });
+        }
+        matvec_acc<H, H, S::HP>(sw + S::W1, dz2, dz1);
+#pragma unroll
+        for (int i = 0; i < H; ++i) dz1[i] = z1[i] > 0.f ? dz1[i] : 0.f;
+        {
+            float r2[2] = {s0, 1.f};
+            outer_auto<H, 2>(dz1, r2, stg, [&](int o, int i) -> float* {
+                if (o >= a.Hr) return nullptr;
+                return i == 0 ? gw + g.W0 + o : gw + g.b0 + o;
+            });
+        }
+    }
+    // final_linear grads: per-lane accumulators -> warp sum -> warp image
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float sgi = warp_sum(gwo[i]);
+        if (lane == 0 && i < a.Hr) gw[g.Wo + i] += sgi;
+    }
+    {
+        const float sgb = warp_sum(gbo);
+        if (lane == 0) gw[g.bo] += sgb;
+    }
+    XW_SYNCTHREADS();
+    for (int e = XW_TID; e < g.size; e += XW_BDIM) {
+        float sgr = 0.f;
+        for (int w = 0; w < nwarps; ++w) sgr += sgrad[(size_t)w * Pp + e];
+        a.gpart[(size_t)XW_BID * g.size + e] = sgr;
+    }
+    if (MODE == 1) {
+        double v[1] = {bd_acc};
+        const int idx[1] = {5};
+        block_sum_to_global<1>(v, red, a.sums, idx);
+    }
+}
+
+// =============================================================================================
+// v net backward: parameter gradients of sum_p G[p] v[p],  G = k0*cot_v + k1*v + k2*w
+// =============================================================================================
+struct VnetBwdArgs {
+    int d, Hvr, nv, n, L;
+    const float* theta; PointsView p;
+    int dom_kind; float dp0, dp1, dp2;
+    const float* cot; const double* coefs;
+    float* gpart;
+};
+
+template <int HV>
+struct StoreLocal {
+    float* acts;   // [nv][HV] per thread (local memory)
+    XW_DEV void operator()(int k, const float (&r)[HV]) const {
+#pragma unroll
+        for (int i = 0; i < HV; ++i) acts[k * HV + i] = r[i];
+    }
+};
+
+template <int HV>
+XW_GLOBAL void k_vnet_bwd(VnetBwdArgs a) {
+    using S = VSmem<HV>;
+    XW_DYN_SMEM(smem_raw);
+    const int nwarps = XW_BDIM >> 5, warp = XW_TID >> 5;
+    const VLayout g(a.d, a.Hvr);
+    const int Pp = pad4(g.size);
+    float* sv = reinterpret_cast<float*>(smem_raw);
+    float* sstg = sv + pad4(S::size(a.d + 1));                       // [nwarps][128][kStgLd]
+    float* sgrad = sstg + (size_t)nwarps * 128 * kStgLd;             // [nwarps][Pp]
+    stage_theta_v<HV>(sv, a.theta, a.d, a.Hvr);
+    for (int i = XW_TID; i < nwarps * Pp; i += XW_BDIM) sgrad[i] = 0.f;
+    XW_SYNCTHREADS();
+    float* stg = sstg + (size_t)warp * 128 * kStgLd;
+    float* gw = sgrad + (size_t)warp * Pp;
+    const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
+
+    const long long nthr = (long long)XW_GDIM * XW_BDIM;
+    const long long gtid = (long long)XW_BID * XW_BDIM + XW_TID;
+    const long long npts = (long long)a.n * a.L;
+    const long long iters = (npts + nthr - 1) / nthr;
+    const int L = a.L, d = a.d, C = a.d + 1, Hvr = a.Hvr;
+    float acts[kMaxNv * HV];
+    for (long long it = 0; it < iters; ++it) {
+        const long long praw = it * nthr + gtid;
+        const bool active = praw < npts;
+        const long long p = active ? praw : npts - 1;
+        const long long n = p / L;
+        const int l = (int)(p - n * L);
+        const float t = a.p.t[n * a.p.t_sn + l * a.p.t_sl];
+        const float* xp = a.p.x + n * a.p.x_sn + l * a.p.x_sl;
+        float tau1[HV + 1];
+        float v;
+        {
+            float tau[HV];
+            v = vnet_fwd<HV>(sv, t, xp, d, a.nv, nullptr, tau, StoreLocal<HV>{acts});
+#pragma unroll
+            for (int i = 0; i < HV; ++i) tau1[i] = tau[i];
+            tau1[HV] = 1.f;
+        }
+        float G = 0.f;
+        if (active) {
+            const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, t, xp, d);
+            G = fmaf(k0, a.cot[p], fmaf(k1, v, k2 * W.w));
+        }
+        {
+            float g1[1] = {G};
+            outer_auto<1, HV + 1>(g1, tau1, stg, [&](int o, int i) -> float* {
+                if (i == HV) return gw + g.bz;
+                return i < Hvr ? gw + g.Wz + i : nullptr;
+            });
+        }
+        float dl[HV];
+        {
+            float wz[HV];
+            load_row<HV>(sv + S::WZ, wz);
+#pragma unroll
+            for (int i = 0; i < HV; ++i) dl[i] = G * wz[i] * (1.f - tau1[i] * tau1[i]);
+        }
+        for (int k = a.nv; k > 0; --k) {
+            float r1[HV + 1];
+#pragma unroll
+            for (int i = 0; i < HV; ++i) r1[i] = acts[(k - 1) * HV + i];
+            r1[HV] = 1.f;
+            outer_auto<HV, HV + 1>(dl, r1, stg, [&](int o, int i) -> float* {
+                if (o >= Hvr) return nullptr;
+                if (i == HV) return gw + g.bh + o;
+                return i < Hvr ? gw + g.Wh + o * Hvr + i : nullptr;
+            });
+            float dn[HV];
+#pragma unroll
+            for (int i = 0; i < HV; ++i) dn[i] = 0.f;
+            matvec_acc<HV, HV, S::HVP>(sv + S::WH, dl, dn);
+#pragma unroll
+            for (int i = 0; i < HV; ++i) dl[i] = r1[i] > 0.f ? dn[i] : 0.f;
+        }
+        // input layer: columns (t, x_0..x_{d-1}, 1)
+        warp_outer_dyn<HV, 7>(dl, C + 1,
+                              [&](int c) -> float { return c == 0 ? t : (c <= d ? xp[c - 1] : 1.f); },
+                              stg, stg + 64 * kStgLd,
+                              [&](int o, int c) -> float* {
+                                  if (o >= Hvr) return nullptr;
+                                  return c < C ? gw + g.Wi + o * C + c : gw + g.bi + o;
+                              });
+    }
+    XW_SYNCTHREADS();
+    for (int e = XW_TID; e < g.size; e += XW_BDIM) {
+        float sgr = 0.f;
+        for (int w = 0; w < nwarps; ++w) sgr += sgrad[(size_t)w * Pp + e];
+        a.gpart[(size_t)XW_BID * g.size + e] = sgr;
+    }
+}
+
+// grad_out[e] = (accumulate ? grad_out[e] : 0) + sum_b gpart[b][e]
+XW_GLOBAL void k_reduce_partials(const float* gpart, int nblocks, int P, float* out, int accumulate) {
+    const long long gtid = (long long)XW_BID * XW_BDIM + XW_TID;
+    if (gtid >= P) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)gpart[(size_t)b * P + gtid];
+    out[gtid] = (float)(s + (accumulate ? (double)out[gtid] : 0.0));
+}
+
+}  // namespace xw

@@ -1,0 +1,108 @@
+// xw_platform.cuh -- the handful of CUDA builtins the kernels use, behind macros.
+//
+// Product build (nvcc, sm_100a): maps 1:1 to the CUDA builtins.
+// Test build (g++ -DXW_EMU, tests/host_emu/): maps to a tiny std::thread-based emulator
+// (tests/host_emu/cuda_emu.h) so that the indexing / staging / reduction logic of every kernel
+// can be checked against the oracle on a CPU-only box.  The emulator is TEST INFRASTRUCTURE: the
+// shipped library never contains it and there is no CPU fallback in the product path.
+#pragma once
+
+#ifdef XW_EMU
+#include "cuda_emu.h"
+#define XW_DEV inline
+#define XW_HD inline
+#define XW_GLOBAL inline
+#define XW_RESTRICT
+#else
+#include <cuda_runtime.h>
+#include <stdint.h>
+#define XW_DEV __device__ __forceinline__
+#define XW_HD __host__ __device__ inline
+#define XW_GLOBAL __global__
+#define XW_RESTRICT __restrict__
+#define XW_SYNCTHREADS() __syncthreads()
+#define XW_SYNCWARP() __syncwarp()
+#define XW_SHFL_XOR(v, m) __shfl_xor_sync(0xffffffffu, (v), (m))
+#define XW_SHFL_IDX(v, l) __shfl_sync(0xffffffffu, (v), (l))
+#define XW_TID ((int)threadIdx.x)
+#define XW_BID ((int)blockIdx.x)
+#define XW_BDIM ((int)blockDim.x)
+#define XW_GDIM ((int)gridDim.x)
+#define XW_ATOMIC_ADD_F(p, v) atomicAdd((p), (v))
+#define XW_ATOMIC_ADD_D(p, v) atomicAdd((p), (v))
+#endif
+
+// compiler-only memory barrier: keeps ptxas/nvcc from hoisting the (loop-invariant) shared-memory
+// weight loads out of the layer / time-step loops, which would need thousands of registers
+#define XW_FENCE() asm volatile("" ::: "memory")
+
+namespace xw {
+
+constexpr int pad4(int x) { return (x + 3) & ~3; }
+
+struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(8) f2 { float x, y; };
+
+XW_DEV f4 ld4(const float* p) { return *reinterpret_cast<const f4*>(p); }
+XW_DEV f2 ld2(const float* p) { return *reinterpret_cast<const f2*>(p); }
+XW_DEV void st4(float* p, f4 v) { *reinterpret_cast<f4*>(p) = v; }
+
+// load N consecutive floats (p 16-byte aligned) into registers with the widest loads
+template <int N>
+XW_DEV void load_row(const float* p, float (&w)[N]) {
+#pragma unroll
+    for (int j = 0; j + 4 <= N; j += 4) {
+        f4 v = ld4(p + j);
+        w[j] = v.x; w[j + 1] = v.y; w[j + 2] = v.z; w[j + 3] = v.w;
+    }
+    constexpr int R = N & ~3;
+    if constexpr ((N & 3) >= 2) {
+        f2 v = ld2(p + R);
+        w[R] = v.x; w[R + 1] = v.y;
+    }
+    if constexpr ((N & 3) == 1) w[R] = p[R];
+    if constexpr ((N & 3) == 3) w[R + 2] = p[R + 2];
+}
+
+// out[j] += sum_i M[i*LD + j] * in[i]        (M "in-major": row i holds the OUT weights of input i)
+template <int IN, int OUT, int LD>
+XW_DEV void matvec_acc(const float* M, const float (&in)[IN], float (&out)[OUT]) {
+    XW_FENCE();
+#pragma unroll
+    for (int i = 0; i < IN; ++i) {
+        float w[OUT];
+        load_row<OUT>(M + i * LD, w);
+        const float xi = in[i];
+#pragma unroll
+        for (int j = 0; j < OUT; ++j) out[j] = fmaf(w[j], xi, out[j]);
+    }
+}
+
+XW_DEV float warp_sum(float v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += XW_SHFL_XOR(v, m);
+    return v;
+}
+XW_DEV double warp_sum_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += XW_SHFL_XOR(v, m);
+    return v;
+}
+
+// 128-bit LIFO of fixed-width bit groups (relu masks of the shared field layers)
+struct BitStack128 {
+    unsigned long long lo, hi;
+    XW_DEV void clear() { lo = 0ull; hi = 0ull; }
+    template <int B> XW_DEV void push(unsigned bits) {
+        hi = (hi << B) | (lo >> (64 - B));
+        lo = (lo << B) | (unsigned long long)bits;
+    }
+    template <int B> XW_DEV unsigned pop() {
+        unsigned bits = (unsigned)(lo & ((1ull << B) - 1ull));
+        lo = (lo >> B) | (hi << (64 - B));
+        hi >>= B;
+        return bits;
+    }
+};
+
+}  // namespace xw
