@@ -1,0 +1,190 @@
+"""CPU: the reference-facing Python API (NODE_WAN_solver / loss / func_eval / Comb_loader /
+autograd.Function) driven end to end with the CPU EMULATION build of the kernels injected, against
+the golden vectors of the unmodified reference.  Checks host logic only (packing, strides,
+normalisers, side-effect terms, state-dict names, sampler RNG order); the real sm_100a library is
+checked by the `-m gpu` tests."""
+import numpy as np
+import pytest
+import torch
+
+import xnode_wan_b200 as xw
+from tests import _golden as G
+from tests.host_emu import build_emu
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    lib = xw._lib.XwLib(build_emu.build())
+    monkeypatch.setattr(xw._lib, "_LIB", lib)
+    monkeypatch.setattr(xw.hotpath, "_TEST_ALLOW_HOST", True)
+    return lib
+
+
+def make_solver(case, device="cpu"):
+    p = dict(case["params"])
+    p["domain"] = "Hypercube"
+    prob = xw.problems.by_name(case["meta"]["funcs"], p["dim"])
+    s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, device,
+                           "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
+    with torch.no_grad():
+        for q, w in zip(s.u_net.parameters(), case["thu_list"]):
+            q.copy_(torch.from_numpy(np.asarray(w)))
+        for q, w in zip(s.v_net.parameters(), case["thv_list"]):
+            q.copy_(torch.from_numpy(np.asarray(w)))
+    return s, prob
+
+
+def eval_phase(s, case, phase, device="cpu"):
+    z = case["z"]
+    X, XV, BX = (torch.from_numpy(z[k]).to(device) for k in ("X", "XV", "BX"))
+    dom = s.new_domain()
+    s.optimizer_u.zero_grad()
+    s.optimizer_v.zero_grad()
+    pv, pu = s.v_net(XV), s.u_net(X)
+    h, f, g, a, b, c = xw.func_eval(X, BX, s.setup, pu, s.func_a, s.func_b, s.func_c, s.func_h, s.func_f, s.func_g)
+    L = xw.loss(s.config["alpha"], a, b, c, h, f, g, s.setup, dom, device)
+    val = L.u(pu, pv, s.u_net, X, XV, BX) if phase == "u" else L.v(pu, pv, X, XV)
+    val.backward()
+    net = s.u_net if phase == "u" else s.v_net
+    return val, [q.grad.detach().cpu().numpy() for q in net.parameters()]
+
+
+@pytest.mark.parametrize("name", ["cube_d5_alpha1_randbias", "cube_d3_small_nets", "cube_d4_ex43", "cube_d3_rk4"])
+def test_reference_api_matches_golden(emu, name):
+    case = G.load(name)
+    s, _ = make_solver(case)
+    z = case["z"]
+    for phase, gold_l, gold_g in (("u", float(z["loss_u"]), case["gu"]), ("v", float(z["loss_v"]), case["gv"])):
+        val, grads = eval_phase(s, case, phase)
+        assert val.dtype == torch.float64
+        assert abs(val.item() - gold_l) <= 1e-4 * abs(gold_l) + 1e-6
+        comp = val.components
+        assert abs(comp["I"].item() - float(z["I"])) <= 1e-4 * abs(float(z["I"]))
+        for a, b in zip(grads, gold_g):
+            assert a.dtype == np.float64 and G.rel(a, b) < 1e-3
+
+
+def test_state_dict_names_match_reference_layout(emu):
+    case = G.load("cube_d5_shipped_small")
+    s, _ = make_solver(case)
+    ku = list(s.u_net.state_dict().keys())
+    assert ku[:6] == ["module.initial_layers.0.weight", "module.initial_layers.0.bias", "module.initial_layers.2.weight",
+                      "module.initial_layers.2.bias", "module.initial_layers.4.weight", "module.initial_layers.4.bias"]
+    assert "module.ODE_rhs.net.16.weight" in ku and "module.final_linear.bias" in ku
+    assert [n for n, _ in s.u_net.named_parameters()][6:10] == [
+        "module.ODE_rhs.net.0.weight", "module.ODE_rhs.net.0.bias", "module.ODE_rhs.net.2.weight", "module.ODE_rhs.net.2.bias"]
+    kv = list(s.v_net.state_dict().keys())
+    assert "module.hidden.weight" in kv and "module.net.2.weight" in kv and "module.net.20.weight" in kv
+    assert [tuple(q.shape) for q in s.v_net.parameters()] == [(50, 6), (50,), (50, 50), (50,), (1, 50), (1,)]
+    assert all(q.dtype == torch.float64 for q in s.u_net.parameters())
+
+
+def test_hypercube_sampler_reproduces_reference_stream():
+    """same seeds -> the golden samples of the unmodified reference, bit for bit"""
+    case = G.load("cube_d5_shipped_small")
+    p, z = case["params"], case["z"]
+    torch.manual_seed(case["meta"]["seed"])
+    np.random.seed(case["meta"]["seed"])
+    # the reference solver constructor builds one throw-away domain and initialises both nets first
+    s, _ = make_solver_for_rng(case)
+    dom = s.new_domain()
+    pts = xw.Comb_loader(p["N_r"], p["N_b"], dom, "cpu")
+    X, XV, BX = pts[0]
+    assert torch.equal(X, torch.from_numpy(z["X"]))
+    assert torch.equal(XV, torch.from_numpy(z["XV"]))
+    assert torch.equal(BX, torch.from_numpy(z["BX"]))
+    # and the xavier initialisation consumed the RNG identically: weights equal the golden ones
+    for q, w in zip(s.u_net.parameters(), case["thu_list"]):
+        assert torch.equal(q.detach(), torch.from_numpy(np.asarray(w)))
+    for q, w in zip(s.v_net.parameters(), case["thv_list"]):
+        assert torch.equal(q.detach(), torch.from_numpy(np.asarray(w)))
+
+
+def make_solver_for_rng(case):
+    p = dict(case["params"])
+    p["domain"] = "Hypercube"
+    prob = xw.problems.by_name(case["meta"]["funcs"], p["dim"])
+    s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, "cpu",
+                           "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
+    return s, prob
+
+
+def test_problem_callables_match_reference_values():
+    case = G.load("cube_d4_ex43")
+    z = case["z"]
+    prob = xw.problems.ex4_3(4)
+    X, BX = torch.from_numpy(z["X"]), torch.from_numpy(z["BX"])
+    assert np.allclose(prob.func_h(X[:, 0, :]).numpy(), z["h"], rtol=2e-6, atol=1e-6)
+    assert np.allclose(prob.func_f(X).numpy(), z["f"], rtol=2e-5, atol=2e-5)
+    assert np.allclose(prob.func_g(BX).numpy(), z["g"], rtol=2e-6, atol=1e-6)
+
+
+def test_unsupported_inputs_raise(emu):
+    case = G.load("cube_d3_small_nets")
+    s, prob = make_solver(case)
+    z = case["z"]
+    X = torch.from_numpy(z["X"])
+    with pytest.raises(NotImplementedError):
+        xw.training.classify_coefficients(X, s.setup, prob.func_a, prob.func_b, lambda X_, u: -u * u)
+    with pytest.raises(NotImplementedError):
+        xw.training.classify_coefficients(X, s.setup, lambda X_, i, j: X_[:, :, 1] * (i == j), prob.func_b, prob.func_c)
+    with pytest.raises(RuntimeError):
+        xw.NeuralODE(20, 1, prob.func_h, prob.func_g, s.setup, 10, 8, s.new_domain(), solver="dopri5")
+    with pytest.raises(RuntimeError):
+        xw.NeuralODE(20, 1, prob.func_h, prob.func_g, s.setup, 10, 8, s.new_domain(), adjoint=True)
+    with pytest.raises(TypeError):
+        xw.loss(1.0, torch.zeros(3, 3, 4, 7), xw.CoefB(), xw.CoefC(), None, None, None, s.setup, s.new_domain(), "cpu")
+
+
+def test_product_path_refuses_cpu_tensors():
+    """without the test injection the product path must fail loudly on CPU tensors / missing GPU"""
+    case = G.load("cube_d3_small_nets")
+    s, _ = make_solver(case)
+    with pytest.raises(RuntimeError):
+        eval_phase(s, case, "u")
+
+
+def test_collapsed_layout_equals_dense_layout(emu):
+    """CollapsedPaths(times, x) through the public API == the reference's repeated [N, L, C] tensors"""
+    case = G.load("cube_d5_alpha1_randbias")
+    s, _ = make_solver(case)
+    z = case["z"]
+    dense = {k: torch.from_numpy(z[k]) for k in ("X", "XV", "BX")}
+    col = {k: xw.CollapsedPaths(v[0, :, 0].clone(), v[:, 0, 1:].clone()) for k, v in dense.items()}
+    assert torch.equal(col["X"].dense(), dense["X"])
+    assert torch.equal(col["X"][:, :, 2], dense["X"][:, :, 2]) and torch.equal(col["X"][:, 0, :], dense["X"][:, 0, :])
+    outs = []
+    for data in (dense, col):
+        res = []
+        for phase in ("u", "v"):
+            dom = s.new_domain()
+            s.optimizer_u.zero_grad(); s.optimizer_v.zero_grad()
+            pv, pu = s.v_net(data["XV"]), s.u_net(data["X"])
+            h, f, g, a, b, c = xw.func_eval(data["X"], data["BX"], s.setup, pu, s.func_a, s.func_b, s.func_c, s.func_h,
+                                            s.func_f, s.func_g)
+            L = xw.loss(s.config["alpha"], a, b, c, h, f, g, s.setup, dom, "cpu")
+            val = L.u(pu, pv, s.u_net, data["X"], data["XV"], data["BX"]) if phase == "u" else L.v(pu, pv, data["X"], data["XV"])
+            val.backward()
+            net = s.u_net if phase == "u" else s.v_net
+            res.append((val.item(), [q.grad.clone() for q in net.parameters()]))
+        outs.append(res)
+    for (l0, g0), (l1, g1) in zip(*outs):
+        assert abs(l0 - l1) <= 1e-9 * abs(l0)
+        for a_, b_ in zip(g0, g1):
+            assert torch.allclose(a_, b_, rtol=1e-6, atol=1e-9)
+    # forward-only evaluation agrees too
+    with torch.no_grad():
+        assert torch.allclose(s.u_net(dense["X"]), s.u_net(col["X"]), atol=1e-6)
+
+
+def test_train_iteration_runs_and_updates_both_nets(emu):
+    case = G.load("cube_d3_small_nets")
+    s, _ = make_solver(case)
+    torch.manual_seed(0)
+    dom = s.new_domain()
+    pts = xw.Comb_loader(16, 12, dom, "cpu")
+    before = [q.detach().clone() for q in list(s.u_net.parameters()) + list(s.v_net.parameters())]
+    lu, lv = s.train_iteration(dom, pts)
+    assert torch.isfinite(lu) and torch.isfinite(lv)
+    after = list(s.u_net.parameters()) + list(s.v_net.parameters())
+    assert all(not torch.equal(a, b) for a, b in zip(before, after))

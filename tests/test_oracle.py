@@ -128,3 +128,29 @@ def test_domain_w_gradients_fd():
             Pm = P.copy(); Pm[..., c] -= 1e-7
             fd = (cf.domain_w(dom, Pp)[0] - cf.domain_w(dom, Pm)[0]) / 2e-7
             assert np.abs(fd - dw[..., c]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["cube_d5_alpha1_randbias", "cube_d4_ex43", "cube_d3_rk4", "cube_d2_L2"])
+def test_torch_port_matches_reference_golden(name):
+    """the PyTorch/CPU port used as cpu_baseline and `--impl reference` stand-in reproduces the
+    unmodified reference's loss values and parameter gradients (same ops, float64)"""
+    import torch
+    import xnode_wan_b200 as xw
+    from oracle import torch_port as tp
+    c = G.load(name)
+    z, p = c["z"], c["params"]
+    prob = xw.problems.by_name(c["meta"]["funcs"], p["dim"])
+    pu = [torch.tensor(np.asarray(w), dtype=torch.float64, requires_grad=True) for w in c["thu_list"]]
+    pv = [torch.tensor(np.asarray(w), dtype=torch.float64, requires_grad=True) for w in c["thv_list"]]
+    cfg = dict(nu=p["u_layers"], nv=p["v_layers"], solver=p["solver"], alpha=p["alpha"], bot=c["meta"]["domain"][1],
+               top=c["meta"]["domain"][2], V=c["meta"]["V"])
+    X, XV, BX = (torch.from_numpy(z[k]) for k in ("X", "XV", "BX"))
+    lu, comps = tp.step("u", pu, pv, X, XV, BX, prob, cfg)
+    assert abs(lu - float(z["loss_u"])) <= 1e-6 * abs(float(z["loss_u"])) + 1e-6
+    assert abs(comps["I"] - float(z["I"])) <= 1e-5 * abs(float(z["I"]))
+    for q, gref in zip(pu, c["gu"]):
+        assert G.rel(q.grad.numpy(), gref) < 1e-5
+    lv, _ = tp.step("v", pu, pv, X, XV, BX, prob, cfg)
+    assert abs(lv - float(z["loss_v"])) <= 1e-5 * abs(float(z["loss_v"])) + 1e-6
+    for q, gref in zip(pv, c["gv"]):
+        assert G.rel(q.grad.numpy(), gref) < 1e-5

@@ -1,0 +1,119 @@
+"""Domain samplers with the reference's protocol (/root/reference/src/dataset.py:34-45):
+`interior(N_r)`, `boundary(N_b)`, `func_w(x)`, `V()` and the `Comb_loader(N_r, N_b, shape, device)`
+iterable of (datau, datav, bdata) triples in the [N, L, C] layout with time in channel 0.
+
+`Hypercube` draws the SAME random numbers in the same order as the reference when sampling on the
+CPU (so a seeded run yields bit-identical samples: times -> interior x -> second interior x for the
+test function -> boundary x -> one unused draw -> permutation, src/dataset.py:248-276,306-310), and
+can alternatively sample directly on the GPU (`sample_device=`) for the large configurations where
+host sampling + H2D of the repeated [N, L, C] tensors would dominate.
+"""
+import math
+
+import torch
+
+from .paths import CollapsedPaths
+
+
+class Hypercube:
+    """cube (bot..top)^dim x [T0, T]; time grid = sorted uniforms with pinned end points"""
+
+    def __init__(self, top_bot, dim: int, T0: float, T: float, N_t: int, sample_device=None, times=None,
+                 collapsed=False):
+        assert top_bot[1] > top_bot[0], "The hypercube needs to have volume"
+        self.bot, self.top = top_bot[0], top_bot[1]
+        self.dim, self.T0, self.T, self.N_t = dim, T0, T, N_t
+        self.sample_device = sample_device
+        self.collapsed = collapsed      # yield CollapsedPaths(times, x) instead of dense [N, L, C]
+        if times is None:
+            times = torch.empty(N_t).uniform_(T0, T).sort(0).values
+            times[0], times[-1] = T0, T
+        self.times = times
+
+    # -- raw draws -------------------------------------------------------------------------
+    def _uniform_x(self, n):
+        if self.sample_device is None:
+            return torch.empty(n, 1, self.dim).uniform_(self.bot, self.top)
+        return torch.empty(n, 1, self.dim, device=self.sample_device).uniform_(self.bot, self.top)
+
+    def _with_time(self, x):
+        n = x.shape[0]
+        if self.collapsed:
+            return CollapsedPaths(self.times.to(x.device), x[:, 0, :].contiguous())
+        t = self.times.to(x.device).reshape(1, self.N_t, 1).expand(n, self.N_t, 1)
+        return torch.cat((t, x.expand(n, self.N_t, self.dim)), dim=2)
+
+    def interior(self, N_r: int):
+        return self._with_time(self._uniform_x(N_r))
+
+    def boundary_x(self, N_b: int):
+        """[N_b, dim] spatial coordinates on the faces: consecutive blocks of int(N_b/dim/2) paths get
+        coordinate k pinned to top / bot, the remainder goes to the last face; then a permutation"""
+        x = self._uniform_x(N_b)[:, 0, :].clone()
+        self._uniform_x(N_b)                                   # the reference draws (and drops) one more
+        n = int(N_b / self.dim / 2)
+        edges = [n * i for i in range(2 * self.dim)] + [N_b]
+        for k in range(self.dim):
+            x[edges[2 * k]:edges[2 * k + 1], k] = self.top
+            x[edges[2 * k + 1]:edges[2 * k + 2], k] = self.bot
+        perm = torch.randperm(N_b) if self.sample_device is None else torch.randperm(N_b, device=self.sample_device)
+        return x[perm]
+
+    def boundary(self, N_b: int):
+        return self._with_time(self.boundary_x(N_b).unsqueeze(1))
+
+    def func_w(self, x: torch.Tensor):
+        s = x[:, :, 1:]
+        return torch.minimum((self.top - s).abs().amin(dim=2), (self.bot - s).abs().amin(dim=2))
+
+    def bound_pad(self, x):
+        raise NotImplementedError("bound_pad / fillt (evaluation from inside the domain) is not supported yet")
+
+    def V(self):
+        return (self.top - self.bot) ** self.dim * (self.T - self.T0)
+
+
+class Comb_loader:
+    """(datau, datav, bdata) batches of equally long paths (reference src/dataset.py:293-322).
+    For a tensor-valued domain (the cube) there is one batch; the test-function points are an
+    independent second interior sample (src/dataset.py:308)."""
+
+    def __init__(self, N_r: int, N_b: int, shape, device):
+        self.N_r, self.N_b, self.shape, self.device = N_r, N_b, shape, device
+        interior = shape.interior(N_r)
+        if isinstance(interior, list):
+            self.interioru = interior
+            self.interiorv = [g.clone().detach() for g in interior]
+            self.boundary = shape.boundary(N_b)
+        else:
+            self.interioru = interior
+            self.interiorv = shape.interior(N_r)
+            self.boundary = shape.boundary(N_b)
+        self._cache = {}
+
+    def __len__(self):
+        return len(self.interioru) if isinstance(self.interioru, list) else 1
+
+    def _dev(self, t, start):
+        out = t.to(self.device, non_blocking=True)
+        out._xw_start = start
+        return out
+
+    def __getitem__(self, idx):
+        is_list = isinstance(self.interioru, list)
+        if not is_list and idx != 0:
+            raise IndexError
+        if idx not in self._cache:      # one H2D per sample (the reference re-copies on every access)
+            if is_list:
+                if idx >= min(len(self.interioru), len(self.boundary)):
+                    raise IndexError
+                trip = (self.interioru[idx], self.interiorv[idx], self.boundary[idx])
+                self._cache[idx] = tuple(self._dev(t, None) for t in trip)
+            else:
+                self._cache[idx] = (self._dev(self.interioru, "h"), self._dev(self.interiorv, "h"),
+                                    self._dev(self.boundary, "h"))
+        return self._cache[idx]
+
+
+def domain_volume_sphere(dim, r, timecomp):
+    return math.pi ** (dim / 2) / math.gamma(dim / 2 + 1) * r ** dim * timecomp

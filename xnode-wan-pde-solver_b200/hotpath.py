@@ -1,0 +1,334 @@
+"""Host side of the fused hot path: one `torch.autograd.Function` per phase that replaces
+/root/reference/src/training.py:129-137 (u-phase) and :153-161 (v-phase).
+
+forward  : xw_interior_forward (+ xw_boundary_u in the u-phase) -> Monte-Carlo partial sums
+           -> [one small all-reduce when sharded] -> loss scalar (fp64, on device, no host sync)
+backward : xw_interior_backward_u / xw_interior_backward_v -> flat fp32 gradient
+           -> [one small all-reduce] -> per-parameter .grad in the parameters' dtype
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); all arithmetic of the path
+runs in the sm_100a kernels behind the C ABI (include/xnode_wan_b200.h).  No CPU fallback: CPU
+tensors or a missing library raise.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_TEST_ALLOW_HOST = False      # set ONLY by tests that inject the CPU emulation build
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    if dev.type != "cuda":
+        return None
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _check_dev(t, what):
+    if not t.is_cuda and not _TEST_ALLOW_HOST:
+        raise RuntimeError("%s must be a CUDA tensor: the XNODE-WAN hot path has no CPU fallback" % what)
+
+
+@dataclass
+class NetSpec:
+    """network sizes (configs/cube_pde.yaml keys) -> xw_dims"""
+    d: int
+    H: int
+    hh: int
+    nu: int
+    Hv: int
+    nv: int
+    solver: str = "midpoint"
+
+    def c(self):
+        if self.solver not in _lib.SOLVERS:
+            raise RuntimeError("unsupported solver %r (supported: euler, midpoint, rk4)" % (self.solver,))
+        return _lib.Dims(self.d, self.H, self.hh, self.nu, self.Hv, self.nv, _lib.SOLVERS[self.solver])
+
+
+@dataclass
+class DomainSpec:
+    kind: str                      # cube | cone | hourglass
+    p: tuple = (0.0, 0.0, 0.0)
+    V: float = 1.0
+
+    def c(self):
+        p = tuple(float(x) for x in self.p) + (0.0, 0.0, 0.0)
+        return _lib.Domain(_lib.DOMAINS[self.kind], p[0], p[1], p[2])
+
+
+@dataclass
+class CoefSpec:
+    """structured PDE coefficients: c(X,u) = c0 + c1*u; a None=identity or constant [d,d];
+    b None=0 or constant [d]"""
+    c0: float = 0.0
+    c1: float = 0.0
+    a: Optional[torch.Tensor] = None
+    b: Optional[torch.Tensor] = None
+
+    def c(self):
+        return _lib.Coef(float(self.c0), float(self.c1), self.a.data_ptr() if self.a is not None else None,
+                         self.b.data_ptr() if self.b is not None else None)
+
+
+def as_f32(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+@dataclass
+class Batch:
+    """one (datau, datav, bdata) triple of Comb_loader plus the coefficient values on it.
+    X/XV/BX keep the reference layout [N, L, C] (time in channel 0) or the collapsed layout
+    (x[N,d] + times[L]); everything is fp32 on the device."""
+    N: int
+    L: int
+    d: int
+    times: torch.Tensor            # [L]   path 0's time grid (src/model.py:92)
+    x: torch.Tensor                # base tensor holding X
+    x_off: int
+    x_sn: int
+    xv: torch.Tensor               # base tensor holding XV
+    tv_off: int
+    tv_sn: int
+    tv_sl: int
+    xv_off: int
+    xv_sn: int
+    xv_sl: int
+    tv: Optional[torch.Tensor] = None   # separate tensor for XV times (collapsed layout)
+    h: Optional[torch.Tensor] = None        # [N]
+    grad_h: Optional[torch.Tensor] = None   # [N, d]
+    f: Optional[torch.Tensor] = None        # [N, L]
+    # boundary
+    Nb: int = 0
+    Lb: int = 0
+    times_b: Optional[torch.Tensor] = None
+    xb: Optional[torch.Tensor] = None
+    xb_off: int = 0
+    xb_sn: int = 0
+    sb: Optional[torch.Tensor] = None       # [Nb]
+    g: Optional[torch.Tensor] = None        # [Nb, Lb]
+    # global (all-rank) counts used in the normalisers
+    N_glob: int = 0
+    Nb_glob: int = 0
+    keep: list = field(default_factory=list)
+
+    def points(self):
+        tbase = self.tv if self.tv is not None else self.xv
+        return _lib.Points(tbase.data_ptr() + 4 * self.tv_off, self.tv_sn, self.tv_sl,
+                           self.xv.data_ptr() + 4 * self.xv_off, self.xv_sn, self.xv_sl)
+
+
+def batch_from_reference_layout(X, XV, BX=None):
+    """X, XV [N,L,C], BX [Nb,Lb,C] (any float dtype) -> Batch (fp32 views, no repack when already fp32)"""
+    Xf, XVf = as_f32(X), as_f32(XV)
+    N, L, Cc = Xf.shape
+    b = Batch(N=N, L=L, d=Cc - 1, times=Xf[0, :, 0].contiguous(), x=Xf, x_off=1, x_sn=L * Cc,
+              xv=XVf, tv_off=0, tv_sn=L * Cc, tv_sl=Cc, xv_off=1, xv_sn=L * Cc, xv_sl=Cc, N_glob=N)
+    if BX is not None:
+        BXf = as_f32(BX)
+        Nb, Lb, _ = BXf.shape
+        b.Nb, b.Lb, b.times_b, b.xb, b.xb_off, b.xb_sn, b.Nb_glob = Nb, Lb, BXf[0, :, 0].contiguous(), BXf, 1, Lb * Cc, Nb
+    return b
+
+
+def batch_from_collapsed(times, x, xv, xb=None, times_b=None):
+    """collapsed layout: x, xv [N,d], xb [Nb,d], shared times[L] (the cube's repeated [N,L,C]
+    tensors carry no more information, src/dataset.py:252-254)"""
+    times, x, xv = as_f32(times), as_f32(x), as_f32(xv)
+    N, d = x.shape
+    L = times.numel()
+    b = Batch(N=N, L=L, d=d, times=times, x=x, x_off=0, x_sn=d, xv=xv, tv=times, tv_off=0, tv_sn=0, tv_sl=1,
+              xv_off=0, xv_sn=d, xv_sl=0, N_glob=N)
+    if xb is not None:
+        xb = as_f32(xb)
+        tb = as_f32(times_b) if times_b is not None else times
+        b.Nb, b.Lb, b.times_b, b.xb, b.xb_off, b.xb_sn, b.Nb_glob = xb.shape[0], tb.numel(), tb, xb, 0, d, xb.shape[0]
+    return b
+
+
+class _Workspace:
+    """per-device scratch reused across calls (grown on demand; allocated by torch's caching allocator)"""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, dev, nbytes):
+        b = self.buf.get(dev)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            self.buf[dev] = b
+        return b
+
+
+_WS = _Workspace()
+
+
+def flatten_params(params):
+    return torch.cat([p.detach().reshape(-1) for p in params]).float()
+
+
+def unflatten_like(flat, meta):
+    """meta: list of (shape, dtype)"""
+    out, o = [], 0
+    for shape, dtype in meta:
+        n = 1
+        for s_ in shape:
+            n *= s_
+        out.append(flat[o:o + n].reshape(shape).to(dtype))
+        o += n
+    return out
+
+
+def _allreduce(t, group):
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                             and torch.distributed.get_world_size() > 1):
+        torch.distributed.all_reduce(t, group=group)
+
+
+def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, alpha, boundary_grad=None):
+    """launches the forward kernels; returns (sums[8] fp64 device tensor, cot_u, cot_v)"""
+    dev = theta_u.device
+    dims = spec.c()
+    st = _stream(dev)
+    N, L = batch.N, batch.L
+    wsb = lib.workspace_bytes(dims, max(N, batch.Nb if with_boundary else 1), max(L, batch.Lb if with_boundary else 1))
+    ws = _WS.get(dev, wsb)
+    sums = torch.zeros(_lib.NSUMS, dtype=torch.float64, device=dev)
+    cot_u = torch.empty(N * L, dtype=torch.float32, device=dev)
+    cot_v = torch.empty(N * L, dtype=torch.float32, device=dev)
+    cdom, ccoef, pts = dom.c(), coef.c(), batch.points()
+    lib.call("xw_interior_forward", C.byref(dims), C.byref(cdom), C.byref(ccoef), _ptr(theta_u), _ptr(theta_v),
+             C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), L, C.byref(pts),
+             _ptr(batch.h), _ptr(batch.grad_h), _ptr(batch.f), N, _ptr(sums), _ptr(cot_u), _ptr(cot_v), None,
+             _ptr(ws), ws.numel(), st)
+    if with_boundary:
+        gscale = float(alpha) / (batch.Nb_glob * batch.Lb)
+        lib.call("xw_boundary_u", C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
+                 batch.xb_sn, _ptr(batch.times_b), batch.Lb, _ptr(batch.sb), _ptr(batch.g), batch.Nb, gscale,
+                 _ptr(sums), _ptr(boundary_grad), 0, _ptr(ws), ws.numel(), st)
+    return sums, cot_u, cot_v
+
+
+def loss_from_sums(sums, batch, V, alpha):
+    """device-side fp64 scalars (no host sync): I, S, init, bdry, int (src/loss.py:64-96)"""
+    N, L = batch.N_glob, batch.L
+    I = (V / N) * sums[_lib.SUM_S1] - (V / (N * L)) * (sums[_lib.SUM_S2] - sums[_lib.SUM_S3])
+    S = V * sums[_lib.SUM_VV] / (N * L)
+    init = sums[_lib.SUM_INIT] / N
+    bdry = sums[_lib.SUM_BDRY] / (batch.Nb_glob * batch.Lb) if batch.Nb_glob else torch.zeros_like(I)
+    integ = torch.log(I * I) - torch.log(S)
+    return I, S, init, bdry, integ
+
+
+class WeakLoss(torch.autograd.Function):
+    """loss_u (phase 'u') or loss_v (phase 'v') as a differentiable function of the phase's own
+    parameters.  Reproduces the reference's EFFECTIVE gradients, including the
+    side effects of the two helper backward calls at src/loss.py:55,60 (`side_effect=True`)."""
+
+    @staticmethod
+    def forward(ctx, phase, lib, spec, dom, coef, alpha, batch, group, side_effect, nu_params, *params):
+        pu, pv = params[:nu_params], params[nu_params:]
+        theta_u, theta_v = flatten_params(pu), flatten_params(pv)
+        _check_dev(theta_u, "parameters")
+        dev = theta_u.device
+        gb = torch.zeros(theta_u.numel(), dtype=torch.float32, device=dev) if phase == "u" else None
+        sums, cot_u, cot_v = forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, phase == "u", alpha, gb)
+        _allreduce(sums, group)
+        I, S, init, bdry, integ = loss_from_sums(sums, batch, dom.V, alpha)
+        ctx.phase, ctx.lib, ctx.spec, ctx.dom, ctx.batch, ctx.group = phase, lib, spec, dom, batch, group
+        ctx.nu_params, ctx.side = nu_params, 1.0 if side_effect else 0.0
+        ctx.meta = [(tuple(p.shape), p.dtype) for p in params]
+        N, L = batch.N_glob, batch.L
+        if phase == "u":
+            k = torch.stack([(2.0 / I) * (dom.V / (N * L)), torch.full_like(I, 2.0 * alpha / N), torch.full_like(I, ctx.side)])
+            ctx.save_for_backward(theta_u, cot_u, k, gb)
+            out = integ + alpha * (init + bdry)
+        else:
+            k = torch.stack([-(2.0 / I) * (dom.V / (N * L)), 2.0 / sums[_lib.SUM_VV], torch.full_like(I, ctx.side)])
+            ctx.save_for_backward(theta_v, cot_v, k)
+            out = -integ
+        ctx.components = dict(I=I, S=S, init=init, bdry=bdry)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        lib, spec, batch = ctx.lib, ctx.spec, ctx.batch
+        dims = spec.c()
+        nup = ctx.nu_params
+        none = (None,) * 10
+        if ctx.phase == "u":
+            theta_u, cot_u, k, gb = ctx.saved_tensors
+            dev = theta_u.device
+            st = _stream(dev)
+            ws = _WS.get(dev, lib.workspace_bytes(dims, batch.N, batch.L))
+            ks = k.clone()
+            ks[0:2] *= go.to(ks.dtype)
+            grad = (gb * go.to(gb.dtype)).contiguous()
+            lib.call("xw_interior_backward_u", C.byref(dims), _ptr(theta_u),
+                     C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), batch.L,
+                     _ptr(batch.h), _ptr(cot_u), batch.N, _ptr(ks), _ptr(grad), 1, _ptr(ws), ws.numel(), st)
+            _allreduce(grad, ctx.group)
+            gl = unflatten_like(grad, ctx.meta[:nup])
+            return none + tuple(gl) + (None,) * (len(ctx.meta) - nup)
+        theta_v, cot_v, k = ctx.saved_tensors
+        dev = theta_v.device
+        st = _stream(dev)
+        ws = _WS.get(dev, lib.workspace_bytes(dims, batch.N, batch.L))
+        ks = k.clone()
+        ks[0:2] *= go.to(ks.dtype)
+        grad = torch.empty(theta_v.numel(), dtype=torch.float32, device=dev)
+        cdom, pts = ctx.dom.c(), batch.points()
+        lib.call("xw_interior_backward_v", C.byref(dims), C.byref(cdom), _ptr(theta_v), C.byref(pts), _ptr(cot_v),
+                 batch.N, batch.L, _ptr(ks), _ptr(grad), 0, _ptr(ws), ws.numel(), st)
+        _allreduce(grad, ctx.group)
+        gl = unflatten_like(grad, ctx.meta[nup:])
+        return none + (None,) * nup + tuple(gl)
+
+
+def weak_loss(phase, spec, dom, coef, alpha, batch, u_params, v_params, group=None, side_effect=True, lib=None):
+    """public functional entry: returns the scalar loss tensor (fp64) with autograd wired to the
+    phase's own parameters.  `loss.components` is attached for logging (I, S, init, bdry)."""
+    assert phase in ("u", "v")
+    lib = lib or _lib.get()
+    u_params, v_params = list(u_params), list(v_params)
+    out = WeakLoss.apply(phase, lib, spec, dom, coef, alpha, batch, group, side_effect, len(u_params),
+                         *(u_params + v_params))
+    out.components = getattr(out.grad_fn, "components", None)
+    return out
+
+
+def xnode_eval(spec, u_params, x_base, x_off, x_sn, times, s0, n, lib=None):
+    """u[n, L] forward only (fp32)"""
+    lib = lib or _lib.get()
+    theta_u = flatten_params(u_params)
+    _check_dev(theta_u, "parameters")
+    dims = spec.c()
+    L = times.numel()
+    out = torch.empty(n, L, dtype=torch.float32, device=theta_u.device)
+    lib.call("xw_xnode_eval", C.byref(dims), _ptr(theta_u), C.c_void_p(x_base.data_ptr() + 4 * x_off), x_sn,
+             _ptr(times), L, _ptr(s0), n, _ptr(out), _stream(theta_u.device))
+    return out
+
+
+def vnet_eval(spec, v_params, XV, lib=None):
+    """v[N, L] forward only (fp32) for XV [N, L, C]"""
+    lib = lib or _lib.get()
+    theta_v = flatten_params(v_params)
+    _check_dev(theta_v, "parameters")
+    XVf = as_f32(XV)
+    N, L, Cc = XVf.shape
+    dims = spec.c()
+    pts = _lib.Points(XVf.data_ptr(), L * Cc, Cc, XVf.data_ptr() + 4, L * Cc, Cc)
+    out = torch.empty(N, L, dtype=torch.float32, device=theta_v.device)
+    lib.call("xw_vnet_eval", C.byref(dims), _ptr(theta_v), C.byref(pts), N, L, _ptr(out), _stream(theta_v.device))
+    return out

@@ -1,0 +1,169 @@
+"""Drop-in `loss` class (reference /root/reference/src/loss.py:12-96).
+
+Same constructor and method signatures; `u()` / `v()` return a float64 scalar tensor whose
+`.backward()` fills `.grad` of u_net's (resp. v_net's) parameters with exactly what the reference's
+optimisers see.  The work is done by the fused sm_100a kernels; the
+arguments `a, b, c` are the structured coefficients produced by training.func_eval (CoefA / CoefB /
+CoefC) instead of the reference's dense [d,d,N,L] tensors.
+"""
+import torch
+
+from . import hotpath
+from .model import LazyPrediction, unwrap
+from .paths import CollapsedPaths
+
+
+class CoefA:
+    """a_ij: identity (matrix=None) or a constant [d,d] matrix"""
+    def __init__(self, matrix=None):
+        self.matrix = matrix
+
+
+class CoefB:
+    """b_i: zero (vector=None) or a constant [d] vector"""
+    def __init__(self, vector=None):
+        self.vector = vector
+
+
+class CoefC:
+    """c(X,u) = c0 + c1*u"""
+    def __init__(self, c0=0.0, c1=0.0):
+        self.c0, self.c1 = float(c0), float(c1)
+
+
+def domain_spec(domain):
+    """reference domain object (src/dataset.py) -> DomainSpec for the kernels"""
+    name = type(domain).__name__
+    V = float(domain.V())
+    if name == "Hypercube":
+        return hotpath.DomainSpec("cube", (domain.bot, domain.top, 0.0), V)
+    if name == "NSphere_TCone":
+        return hotpath.DomainSpec("cone", (domain.r, 0.0, 0.0), V)
+    if name == "NSphere_THourglass":
+        return hotpath.DomainSpec("hourglass", (domain.r, domain.T0, domain.T), V)
+    raise NotImplementedError("domain %s: only Hypercube, NSphere_TCone and NSphere_THourglass have an in-kernel "
+                              "func_w / grad func_w" % name)
+
+
+class loss:
+    def __init__(self, alpha: float, a, b, c, h: torch.Tensor, f: torch.Tensor, g: torch.Tensor, setup: dict,
+                 domain, device):
+        self.T, self.T0 = setup['T'], setup['T0']
+        self.alpha = alpha
+        self.a, self.b, self.c = a, b, c
+        self.h, self.f, self.g = h, f, g
+        self.setup = setup
+        self.domain = domain
+        self.func_w = domain.func_w
+        self.V = domain.V()
+        self.device = device
+        self.group = None            # torch.distributed process group (None = default group if initialised)
+        self.N_glob = None           # global path counts when the batch is one rank's shard
+        self.Nb_glob = None
+        self.side_effect = True      # reproduce the reference's helper-backward side effects
+        for nm, obj, cls in (("a", a, CoefA), ("b", b, CoefB), ("c", c, CoefC)):
+            if not isinstance(obj, cls):
+                raise TypeError("coefficient %s must be a %s produced by func_eval (dense tensors of the reference "
+                                "layout are not accepted: d=100 would need 3.4 TB)" % (nm, cls.__name__))
+
+    # -------------------------------------------------------------------------------- internals
+    def _nets(self, y_output_u, y_output_v):
+        if not isinstance(y_output_u, LazyPrediction) or not isinstance(y_output_v, LazyPrediction):
+            raise TypeError("loss.u / loss.v need the objects returned by u_net(X) and v_net(XV) of this package "
+                            "(lazy predictions); got plain tensors")
+        return y_output_u.net, y_output_v.net
+
+    def _batch(self, u_net, X, XV, border):
+        dev = X.device
+        if isinstance(X, CollapsedPaths):
+            b = hotpath.batch_from_collapsed(X.times, X.x, XV.x, border.x if border is not None else None,
+                                             border.times if border is not None else None)
+        else:
+            b = hotpath.batch_from_reference_layout(X, XV, border)
+        kind = u_net.start_kind(X)
+        if kind == "pad":
+            raise NotImplementedError("interior batch must start at T0 or on the boundary")
+        if b.L == 1 and kind == "h":
+            raise NotImplementedError("single-time-point interior groups (rank-2 shortcut, src/model.py:89-91)")
+        b.h = hotpath.as_f32(self.h)
+        x0 = X[:, 0, :].detach().clone().requires_grad_(True)        # [N, C]
+        with torch.enable_grad():
+            hv = u_net.h(x0) if kind == "h" else u_net.g(x0.unsqueeze(1)).reshape(-1)
+            gh, = torch.autograd.grad(hv.sum(), x0, allow_unused=True)
+        b.grad_h = hotpath.as_f32(gh[:, 1:]) if gh is not None else torch.zeros(b.N, b.d, device=dev)
+        if kind == "g":
+            b.h = hotpath.as_f32(hv)
+        b.f = hotpath.as_f32(self.f)
+        if border is not None:
+            kb = u_net.start_kind(border)
+            if kb == "pad":
+                raise NotImplementedError("boundary batch must start at T0 or on the boundary")
+            b.sb = hotpath.as_f32(u_net.initial_scalar(border.detach(), kb))
+            b.g = hotpath.as_f32(self.g)
+        if self.N_glob:
+            b.N_glob = self.N_glob
+        if self.Nb_glob and border is not None:
+            b.Nb_glob = self.Nb_glob
+        return b
+
+    def _coef(self, dev):
+        a = self.a.matrix
+        bb = self.b.vector
+        return hotpath.CoefSpec(self.c.c0, self.c.c1,
+                                hotpath.as_f32(a).to(dev) if a is not None else None,
+                                hotpath.as_f32(bb).to(dev) if bb is not None else None)
+
+    def _eval(self, phase, y_output_u, y_output_v, X, XV, border):
+        u_mod, v_mod = self._nets(y_output_u, y_output_v)
+        batch = self._batch(u_mod, X, XV, border)
+        spec = u_mod.spec(v_mod)
+        dom = domain_spec(self.domain)
+        return hotpath.weak_loss(phase, spec, dom, self._coef(X.device), float(self.alpha), batch,
+                                 u_mod.kernel_parameters(), v_mod.flat_parameters(), group=self.group,
+                                 side_effect=self.side_effect)
+
+    # ------------------------------------------------------------------------------ reference API
+    def u(self, y_output_u, y_output_v, u_net, X, XV, border):
+        """loss_u = int + alpha*(init + bdry)   (reference src/loss.py:92-93)"""
+        return self._eval("u", y_output_u, y_output_v, X, XV, border)
+
+    def v(self, y_output_u, y_output_v, X, XV):
+        """loss_v = -int   (reference src/loss.py:95-96)"""
+        return self._eval("v", y_output_u, y_output_v, X, XV, None)
+
+    def _components(self, y_output_u, y_output_v, X, XV, border=None):
+        with torch.no_grad():
+            out = self._eval("u" if border is not None else "v", y_output_u, y_output_v, X, XV, border)
+        return out.components if out.components is not None else {}
+
+    def I(self, y_output_u, y_output_v, X, XV):
+        """value of <A[u], phi> (reference src/loss.py:46-76); value only"""
+        return self._value("I", y_output_u, y_output_v, X, XV)
+
+    def int(self, y_output_u, y_output_v, X, XV):
+        I = self._value("I", y_output_u, y_output_v, X, XV)
+        S = self._value("S", y_output_u, y_output_v, X, XV)
+        return torch.log(I ** 2) - torch.log(S)
+
+    def init(self, y_output_u):
+        u = y_output_u.materialize() if isinstance(y_output_u, LazyPrediction) else y_output_u
+        return torch.mean((u[:, 0] - self.h.unsqueeze(1).to(u.dtype)) ** 2)
+
+    def bdry(self, u_net, border_data):
+        net = unwrap(u_net)
+        with torch.no_grad():
+            ub = net.evaluate(border_data)
+        return torch.mean((ub - self.g.unsqueeze(2).to(ub.dtype)) ** 2)
+
+    def _value(self, key, y_output_u, y_output_v, X, XV):
+        u_mod, v_mod = self._nets(y_output_u, y_output_v)
+        batch = self._batch(u_mod, X, XV, None)
+        spec, dom = u_mod.spec(v_mod), domain_spec(self.domain)
+        lib = hotpath._lib.get()
+        with torch.no_grad():
+            thu = hotpath.flatten_params(u_mod.kernel_parameters())
+            thv = hotpath.flatten_params(v_mod.flat_parameters())
+            sums, _, _ = hotpath.forward_sums(lib, spec, dom, self._coef(X.device), thu, thv, batch, False, 0.0)
+            hotpath._allreduce(sums, self.group)
+            I, S, init, bdry, integ = hotpath.loss_from_sums(sums, batch, dom.V, 0.0)
+        return {"I": I, "S": S}[key]

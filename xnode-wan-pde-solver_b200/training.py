@@ -1,0 +1,190 @@
+"""`func_eval` and `NODE_WAN_solver` with the reference's signatures
+(/root/reference/src/training.py:13-43, :54-187).  The min-max loop, Adam x2, init, logging and the
+stop criterion stay plain Python/PyTorch (they are the CALLER of the hot path); the
+per-batch work (net forwards, coefficient evaluation, weak-form loss, backward) goes through the
+fused sm_100a kernels."""
+import itertools
+import json
+import os
+import time
+
+import torch
+
+from . import dataset as _dataset
+from .aux import L_norm
+from .dataset import Comb_loader
+from .loss import CoefA, CoefB, CoefC, loss
+from .model import NeuralODE, discriminator, init_weights
+
+_COEF_CACHE = {}
+
+
+def _probe_constant(vals, what):
+    """vals: tensor over probe points -> python float if constant, else raises"""
+    v0 = vals.reshape(-1)[0]
+    if not bool(torch.all(vals == v0)):
+        raise NotImplementedError("%s varies over the sample: only constant coefficients are supported by the "
+                                  "fused kernels (no dense-tensor fallback)" % what)
+    return float(v0)
+
+
+def classify_coefficients(X, setup, func_a, func_b, func_c):
+    """turn the user callables a_ij(X), b_i(X), c(X,u) into structure (SURVEY.md 7 'User callables').
+    Probed on a few sample paths once per (callables, dim) and cached."""
+    d = setup['dim']
+    key = (id(func_a), id(func_b), id(func_c), d)
+    if key in _COEF_CACHE:
+        return _COEF_CACHE[key]
+    Xs = X[:min(4, X.shape[0])].detach()
+    A = torch.empty(d, d, dtype=torch.float64)
+    for i, j in itertools.product(range(d), repeat=2):
+        A[i, j] = _probe_constant(func_a(Xs, i, j), "a[%d,%d]" % (i, j))
+    a = CoefA(None if bool(torch.equal(A, torch.eye(d, dtype=torch.float64))) else A.float())
+    B = torch.tensor([_probe_constant(func_b(Xs, i), "b[%d]" % i) for i in range(d)], dtype=torch.float64)
+    b = CoefB(None if bool(torch.all(B == 0)) else B.float())
+    shape = (Xs.shape[0], Xs.shape[1], 1)
+    u0 = torch.zeros(shape, dtype=torch.float64, device=Xs.device)
+    c_at0, c_at1, c_at2 = (func_c(Xs, u0 + k) for k in (0.0, 1.0, 2.0))
+    c0 = _probe_constant(c_at0, "c(X, 0)")
+    c1 = _probe_constant(c_at1 - c_at0, "c(X, 1) - c(X, 0)")
+    if not bool(torch.allclose(c_at2, c_at0 + 2.0 * (c_at1 - c_at0), rtol=1e-12, atol=1e-12)):
+        raise NotImplementedError("c(X, u) is not affine in u: unsupported coefficient form")
+    out = (a, b, CoefC(c0, c1))
+    _COEF_CACHE[key] = out
+    return out
+
+
+def func_eval(X: torch.Tensor, BX: torch.Tensor, setup: dict, y_output_u, func_a, func_b, func_c, func_h, func_f,
+              func_g):
+    """h, f, g evaluated on the sample by the user's callables (as the reference does); a, b, c as
+    structure instead of the reference's dense [d,d,N,L] / [d,N,L] tensors (src/training.py:32-41).
+    `y_output_u` is accepted for signature parity and not evaluated."""
+    h = func_h(X[:, 0, :])
+    f = func_f(X)
+    g = func_g(BX)
+    a, b, c = classify_coefficients(X, setup, func_a, func_b, func_c)
+    return h.to(X.device), f.to(X.device), g.to(X.device), a, b, c
+
+
+class NODE_WAN_solver:
+    """weak adversarial training loop; constructor arguments as the reference (src/training.py:65-66)"""
+
+    def __init__(self, params: dict, func_a, func_b, func_c, func_h, func_f, func_g, device, path, stop=None,
+                 func_u_sol=None, p: float = 1, log_json: bool = True):
+        self.params = params
+        self.func_a, self.func_b, self.func_c = func_a, func_b, func_c
+        self.func_h, self.func_f, self.func_g = func_h, func_f, func_g
+        self.device, self.path, self.stop, self.func_u_sol, self.p = device, path, stop, func_u_sol, p
+        self.log_json = log_json
+        it = iter(params.items())                       # positional split, as the reference
+        self.config = dict(itertools.islice(it, 13))
+        self.setup = dict(itertools.islice(it, 7))
+        self.iterations = dict(itertools.islice(it, 1))['iterations']
+        dom = params['domain']
+        self.domain = getattr(_dataset, dom) if isinstance(dom, str) else dom
+        self.n1, self.n2 = self.config['n1'], self.config['n2']
+        domain = self.new_domain()
+        dev = torch.device(device)
+        ids = [dev.index if dev.index is not None else torch.cuda.current_device()] if dev.type == "cuda" else None
+        self.u_net = torch.nn.DataParallel(
+            NeuralODE(self.config['u_hidden_dim'], 1, func_h, func_g, self.setup, self.config['u_hidden_hidden_dim'],
+                      self.config['u_layers'], domain, self.config['solver'], self.config['min_steps'],
+                      self.config['adjoint']), device_ids=ids).to(device)
+        self.v_net = torch.nn.DataParallel(discriminator(self.config, self.setup), device_ids=ids).to(device)
+        self.u_net.apply(init_weights)
+        self.v_net.apply(init_weights)
+        self.optimizer_u = torch.optim.Adam(self.u_net.parameters(), lr=self.config['u_rate'])
+        self.optimizer_v = torch.optim.Adam(self.v_net.parameters(), lr=self.config['v_rate'])
+        self.best_l = float('inf')
+        self.av_l = 0
+        self.history = {"loss_u": [], "loss_v": [], "L2": [], "time": []}
+
+    def new_domain(self):
+        s = self.setup
+        return self.domain(s['shape_param'], s['dim'], s['T0'], s['T'], s['N_t'])
+
+    def _step(self, phase, domain, batch):
+        datau, datav, bdata = batch
+        prediction_v = self.v_net(datav)
+        prediction_u = self.u_net(datau)
+        h, f, g, a, b, c = func_eval(datau.detach(), bdata.detach(), self.setup, prediction_u, self.func_a,
+                                     self.func_b, self.func_c, self.func_h, self.func_f, self.func_g)
+        Loss = loss(self.config['alpha'], a, b, c, h, f, g, self.setup, domain, self.device)
+        if phase == "u":
+            val = Loss.u(prediction_u, prediction_v, self.u_net, datau, datav, bdata)
+            val.backward()
+            self.optimizer_u.step()
+        else:
+            val = Loss.v(prediction_u, prediction_v, datau, datav)
+            val.backward()
+            self.optimizer_v.step()
+        return val
+
+    def train_iteration(self, domain, points):
+        """the hot part of one outer iteration: n1 u-steps then n2 v-steps on the same sample
+        (reference src/training.py:125-162 without logging / stop / checkpoint).  Returns the last
+        (loss_u, loss_v) tensors; nothing here synchronises the host."""
+        loss_u = loss_v = None
+        for _ in range(self.n1):
+            self.optimizer_u.zero_grad()
+            for batch in points:
+                loss_u = self._step("u", domain, batch)
+        for _ in range(self.n2):
+            self.optimizer_v.zero_grad()
+            for batch in points:
+                loss_v = self._step("v", domain, batch)
+        return loss_u, loss_v
+
+    def train(self, report: bool = False, report_it: int = 10, show_plt: bool = False, max_seconds=None):
+        past_losses = []
+        t_start = time.time()
+        times = [t_start]
+        loss_u = loss_v = None
+        for k in range(self.iterations):
+            domain = self.new_domain()
+            points = Comb_loader(self.setup['N_r'], self.setup['N_b'], domain, self.device)
+            for i in range(self.n1):
+                self.av_l = 0
+                self.optimizer_u.zero_grad()
+                for batch in points:
+                    loss_u = self._step("u", domain, batch)
+                    self.av_l += loss_u.item()
+                past_losses.append(self.av_l)
+                if self.log_json:
+                    with open('losses_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
+                        json.dump(past_losses, fh)
+                if self.stop is not None and self.stop(self, points.interioru, domain):
+                    torch.save(self.u_net.state_dict(), os.path.join(self.path, 'best_model_weights_NODE.pth'))
+                    print('Stopping Criterion Reached')
+                    self.history["stopped_at_subiter"] = len(past_losses)
+                    return self.history
+                if self.av_l < self.best_l:
+                    if self.log_json:
+                        torch.save(self.u_net.state_dict(), 'best_model_weights_NODE.pth')
+                    self.best_l = self.av_l
+            for j in range(self.n2):
+                self.optimizer_v.zero_grad()
+                for batch in points:
+                    loss_v = self._step("v", domain, batch)
+            L2 = None
+            if self.func_u_sol is not None:
+                fresh = Comb_loader(self.setup['N_r'], self.setup['N_b'], domain, self.device)
+                L2 = L_norm(fresh.interioru, self.u_net, self.p, self.func_u_sol, domain.V(), self.setup['N_r']).item()
+                if self.log_json:
+                    with open('L2_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
+                        json.dump([L2], fh)
+            times.append(time.time())
+            if self.log_json:
+                with open('Time_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
+                    json.dump(times, fh)
+            self.history["loss_u"].append(self.av_l)
+            self.history["loss_v"].append(loss_v.item() if loss_v is not None else None)
+            self.history["L2"].append(L2)
+            self.history["time"].append(times[-1] - t_start)
+            if report and k % report_it == 0:
+                print('iteration: ' + str(k), 'Loss u: ' + str(self.av_l), 'Loss v: ' + str(self.history["loss_v"][-1]))
+                if L2 is not None:
+                    print('L^2 norm error: ' + str(L2))
+            if max_seconds is not None and times[-1] - t_start > max_seconds:
+                break
+        return self.history
