@@ -1,0 +1,126 @@
+"""GPU (-m gpu): the reference-facing Python API on cuda:0 against the golden vectors of the
+unmodified reference, plus size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+import torch
+
+import xnode_wan_b200 as xw
+from oracle import closed_form as cf
+from tests import _golden as G
+from tests.test_host_api_emu import eval_phase, make_solver
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_reference_api_matches_golden_on_gpu(name):
+    case = G.load(name)
+    s, _ = make_solver(case, DEV)
+    z = case["z"]
+    for phase, gold_l, gold_g in (("u", float(z["loss_u"]), case["gu"]), ("v", float(z["loss_v"]), case["gv"])):
+        val, grads = eval_phase(s, case, phase, DEV)
+        assert abs(val.item() - gold_l) <= 1e-4 * abs(gold_l) + 1e-6
+        for k in ("I", "S"):
+            assert abs(val.components[k].item() - float(z[k])) <= 1e-4 * abs(float(z[k]))
+        for a, b in zip(grads, gold_g):
+            assert G.rel(a, b) < 1e-3
+
+
+def test_forward_only_modules_match_golden_on_gpu():
+    case = G.load("cube_d5_shipped_small")
+    s, _ = make_solver(case, DEV)
+    z = case["z"]
+    with torch.no_grad():
+        u = s.u_net(torch.from_numpy(z["X"]).to(DEV))
+        v = s.v_net(torch.from_numpy(z["XV"]).to(DEV))
+    assert u.shape == (z["X"].shape[0], z["X"].shape[1], 1) and u.dtype == torch.float64
+    assert np.abs(u.cpu().numpy()[..., 0] - z["u"]).max() < 2e-5
+    assert np.abs(v.cpu().numpy()[..., 0] - z["v"]).max() < 2e-5
+
+
+def _rand_case(d, N, Nb, seed):
+    torch.manual_seed(seed)
+    p = xw.problems.cube_params(dim=d, N_r=N, N_b=Nb, alpha=10.0, shape_param=[-1.0, 1.0])
+    prob = xw.problems.ex4_1()
+    s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, DEV,
+                           "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
+    with torch.no_grad():
+        for q in list(s.u_net.parameters()) + list(s.v_net.parameters()):
+            q.add_(0.05 * torch.randn_like(q))
+    return s, prob
+
+
+def _loss_and_grads(s, dom, X, XV, BX, phase):
+    s.optimizer_u.zero_grad(); s.optimizer_v.zero_grad()
+    pv, pu = s.v_net(XV), s.u_net(X)
+    h, f, g, a, b, c = xw.func_eval(X, BX, s.setup, pu, s.func_a, s.func_b, s.func_c, s.func_h, s.func_f, s.func_g)
+    L = xw.loss(s.config["alpha"], a, b, c, h, f, g, s.setup, dom, DEV)
+    val = L.u(pu, pv, s.u_net, X, XV, BX) if phase == "u" else L.v(pu, pv, X, XV)
+    val.backward()
+    net = s.u_net if phase == "u" else s.v_net
+    return val, [q.grad.detach().clone() for q in net.parameters()]
+
+
+def test_mid_size_against_oracle_d20():
+    """d=20, N=2048 (more than one CTA per kernel, tail warps) vs the fp64 closed-form oracle"""
+    s, prob = _rand_case(20, 2048 + 37, 1024 + 5, 3)
+    dom = s.new_domain()
+    pts = xw.Comb_loader(2048 + 37, 1024 + 5, dom, DEV)
+    X, XV, BX = pts[0]
+    thu, thv = cf.theta_from_state([q.detach().cpu().numpy() for q in s.u_net.parameters()],
+                                   [q.detach().cpu().numpy() for q in s.v_net.parameters()])
+    Xc, XVc, BXc = (t.cpu() for t in (X, XV, BX))
+    x0 = Xc[:, 0, :].double().requires_grad_(True)
+    prob.func_h(x0).sum().backward()
+    coef = dict(h=prob.func_h(Xc[:, 0, :]).double().numpy(), f=prob.func_f(Xc).double().numpy(),
+                g=prob.func_g(BXc).double().numpy(), grad_h=x0.grad[:, 1:].numpy(),
+                sb=prob.func_h(BXc[:, 0, :]).double().numpy(), c0=0.0, c1=-1.0)
+    cfg = dict(nu=8, nv=9, solver="midpoint", alpha=10.0, V=dom.V(), domain=("cube", -1.0, 1.0))
+    for phase in ("u", "v"):
+        o = cf.weak_form(thu, thv, Xc.numpy(), XVc.numpy(), BXc.numpy(), coef, cfg, phase)
+        val, grads = _loss_and_grads(s, dom, X, XV, BX, phase)
+        assert abs(val.item() - o["loss_" + phase]) <= 1e-4 * abs(o["loss_" + phase])
+        assert abs(val.components["I"].item() - o["I"]) <= 1e-4 * abs(o["I"])
+        for a, b in zip(grads, o["grads"]):
+            assert G.rel(a.cpu().numpy(), b) < 1e-3
+
+
+def test_large_size_properties():
+    """N = 2^16 paths: sharding invariance (sum of two half-batches == whole batch: the property the
+    multi-GPU path relies on), layout invariance (collapsed == dense), determinism"""
+    N = 1 << 16
+    s, prob = _rand_case(20, N, N, 4)
+    dom = s.new_domain(sample_device=DEV)
+    pts = xw.Comb_loader(N, N, dom, DEV)
+    X, XV, BX = pts[0]
+    lu, gu = _loss_and_grads(s, dom, X, XV, BX, "u")
+    lu2, gu2 = _loss_and_grads(s, dom, X, XV, BX, "u")
+    assert abs(lu.item() - lu2.item()) <= 1e-9 * abs(lu.item())
+    col = [xw.CollapsedPaths(t[0, :, 0].contiguous(), t[:, 0, 1:].contiguous()) for t in (X, XV, BX)]
+    lc, gc = _loss_and_grads(s, dom, col[0], col[1], col[2], "u")
+    assert abs(lu.item() - lc.item()) <= 1e-7 * abs(lu.item())
+    for a, b in zip(gu, gc):
+        assert G.rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+    # sharding: raw sums of two halves add up to the sums of the whole
+    hp = xw.hotpath
+    u_mod, v_mod = xw.model.unwrap(s.u_net), xw.model.unwrap(s.v_net)
+    spec = u_mod.spec(v_mod)
+    thu, thv = hp.flatten_params(u_mod.kernel_parameters()), hp.flatten_params(v_mod.flat_parameters())
+    from importlib import import_module
+    lossm = import_module("xnode-wan-pde-solver_b200.loss")
+    domspec = lossm.domain_spec(dom)
+
+    def sums_of(Xs, XVs, BXs):
+        pv, pu = s.v_net(XVs), s.u_net(Xs)
+        h, f, g, a, b, c = xw.func_eval(Xs, BXs, s.setup, pu, s.func_a, s.func_b, s.func_c, s.func_h, s.func_f, s.func_g)
+        L = xw.loss(s.config["alpha"], a, b, c, h, f, g, s.setup, dom, DEV)
+        bt = L._batch(u_mod, Xs, XVs, BXs)
+        sm, _, _ = hp.forward_sums(xw._lib.get(), spec, domspec, L._coef(DEV), thu, thv, bt, True, 10.0,
+                                   torch.zeros_like(thu))
+        return sm.cpu().numpy()
+    whole = sums_of(X, XV, BX)
+    h1 = sums_of(X[:N // 2], XV[:N // 2], BX[:N // 2])
+    h2 = sums_of(X[N // 2:], XV[N // 2:], BX[N // 2:])
+    # path 0's time grid is shared, so the halves see the same grid
+    assert np.allclose(h1 + h2, whole, rtol=1e-9, atol=1e-9 * np.abs(whole).max())

@@ -91,6 +91,17 @@ class Comb_loader:
             self.boundary = shape.boundary(N_b)
         self._cache = {}
 
+    @classmethod
+    def from_tensors(cls, interioru, interiorv, boundary, device):
+        """wrap an existing sample (e.g. pinned host tensors / CollapsedPaths); the host->device copy
+        happens on first access, as in the reference's __getitem__ (src/dataset.py:321)"""
+        self = cls.__new__(cls)
+        self.N_r, self.N_b = interioru.shape[0], boundary.shape[0]
+        self.shape, self.device = None, device
+        self.interioru, self.interiorv, self.boundary = interioru, interiorv, boundary
+        self._cache = {}
+        return self
+
     def __len__(self):
         return len(self.interioru) if isinstance(self.interioru, list) else 1
 

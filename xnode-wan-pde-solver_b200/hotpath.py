@@ -20,6 +20,25 @@ from . import _lib
 
 _TEST_ALLOW_HOST = False      # set ONLY by tests that inject the CPU emulation build
 
+# optional per-call CUDA-event timing (bench.py's roofline): PROFILE = {} to switch on;
+# maps C-ABI entry name -> list of (start_event, end_event) recorded on the launching stream
+PROFILE = None
+CALLS = {}                    # C-ABI entry name -> number of calls (always counted)
+KERNELS_PER_CALL = {"xw_interior_forward": 2, "xw_boundary_u": 2, "xw_interior_backward_u": 2,
+                    "xw_interior_backward_v": 2, "xw_xnode_eval": 1, "xw_vnet_eval": 1}
+
+
+def _call(lib, name, dev, *args):
+    CALLS[name] = CALLS.get(name, 0) + 1
+    if PROFILE is not None and dev.type == "cuda":
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(dev))
+        lib.call(name, *args)
+        e1.record(torch.cuda.current_stream(dev))
+        PROFILE.setdefault(name, []).append((e0, e1))
+    else:
+        lib.call(name, *args)
+
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
@@ -207,13 +226,13 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
     cot_u = torch.empty(N * L, dtype=torch.float32, device=dev)
     cot_v = torch.empty(N * L, dtype=torch.float32, device=dev)
     cdom, ccoef, pts = dom.c(), coef.c(), batch.points()
-    lib.call("xw_interior_forward", C.byref(dims), C.byref(cdom), C.byref(ccoef), _ptr(theta_u), _ptr(theta_v),
+    _call(lib, "xw_interior_forward", dev, C.byref(dims), C.byref(cdom), C.byref(ccoef), _ptr(theta_u), _ptr(theta_v),
              C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), L, C.byref(pts),
              _ptr(batch.h), _ptr(batch.grad_h), _ptr(batch.f), N, _ptr(sums), _ptr(cot_u), _ptr(cot_v), None,
              _ptr(ws), ws.numel(), st)
     if with_boundary:
         gscale = float(alpha) / (batch.Nb_glob * batch.Lb)
-        lib.call("xw_boundary_u", C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
+        _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
                  batch.xb_sn, _ptr(batch.times_b), batch.Lb, _ptr(batch.sb), _ptr(batch.g), batch.Nb, gscale,
                  _ptr(sums), _ptr(boundary_grad), 0, _ptr(ws), ws.numel(), st)
     return sums, cot_u, cot_v
@@ -274,7 +293,7 @@ class WeakLoss(torch.autograd.Function):
             ks = k.clone()
             ks[0:2] *= go.to(ks.dtype)
             grad = (gb * go.to(gb.dtype)).contiguous()
-            lib.call("xw_interior_backward_u", C.byref(dims), _ptr(theta_u),
+            _call(lib, "xw_interior_backward_u", dev, C.byref(dims), _ptr(theta_u),
                      C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), batch.L,
                      _ptr(batch.h), _ptr(cot_u), batch.N, _ptr(ks), _ptr(grad), 1, _ptr(ws), ws.numel(), st)
             _allreduce(grad, ctx.group)
@@ -288,7 +307,7 @@ class WeakLoss(torch.autograd.Function):
         ks[0:2] *= go.to(ks.dtype)
         grad = torch.empty(theta_v.numel(), dtype=torch.float32, device=dev)
         cdom, pts = ctx.dom.c(), batch.points()
-        lib.call("xw_interior_backward_v", C.byref(dims), C.byref(cdom), _ptr(theta_v), C.byref(pts), _ptr(cot_v),
+        _call(lib, "xw_interior_backward_v", dev, C.byref(dims), C.byref(cdom), _ptr(theta_v), C.byref(pts), _ptr(cot_v),
                  batch.N, batch.L, _ptr(ks), _ptr(grad), 0, _ptr(ws), ws.numel(), st)
         _allreduce(grad, ctx.group)
         gl = unflatten_like(grad, ctx.meta[nup:])
@@ -315,7 +334,7 @@ def xnode_eval(spec, u_params, x_base, x_off, x_sn, times, s0, n, lib=None):
     dims = spec.c()
     L = times.numel()
     out = torch.empty(n, L, dtype=torch.float32, device=theta_u.device)
-    lib.call("xw_xnode_eval", C.byref(dims), _ptr(theta_u), C.c_void_p(x_base.data_ptr() + 4 * x_off), x_sn,
+    _call(lib, "xw_xnode_eval", theta_u.device, C.byref(dims), _ptr(theta_u), C.c_void_p(x_base.data_ptr() + 4 * x_off), x_sn,
              _ptr(times), L, _ptr(s0), n, _ptr(out), _stream(theta_u.device))
     return out
 
@@ -330,5 +349,5 @@ def vnet_eval(spec, v_params, XV, lib=None):
     dims = spec.c()
     pts = _lib.Points(XVf.data_ptr(), L * Cc, Cc, XVf.data_ptr() + 4, L * Cc, Cc)
     out = torch.empty(N, L, dtype=torch.float32, device=theta_v.device)
-    lib.call("xw_vnet_eval", C.byref(dims), _ptr(theta_v), C.byref(pts), N, L, _ptr(out), _stream(theta_v.device))
+    _call(lib, "xw_vnet_eval", theta_v.device, C.byref(dims), _ptr(theta_v), C.byref(pts), N, L, _ptr(out), _stream(theta_v.device))
     return out

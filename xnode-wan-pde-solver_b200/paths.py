@@ -58,6 +58,9 @@ class CollapsedPaths:
     def nbytes(self):
         return self.times.numel() * self.times.element_size() + self.x.numel() * self.x.element_size()
 
+    def head(self, k):
+        return CollapsedPaths(self.times, self.x[:k], self._xw_start)
+
     def dense(self):
         N, L, C = self.shape
         t = self.times.reshape(1, L, 1).expand(N, L, 1)

@@ -35,7 +35,7 @@ def classify_coefficients(X, setup, func_a, func_b, func_c):
     key = (id(func_a), id(func_b), id(func_c), d)
     if key in _COEF_CACHE:
         return _COEF_CACHE[key]
-    Xs = X[:min(4, X.shape[0])].detach()
+    Xs = X.head(4).dense() if hasattr(X, "head") else X[:min(4, X.shape[0])].detach()
     A = torch.empty(d, d, dtype=torch.float64)
     for i, j in itertools.product(range(d), repeat=2):
         A[i, j] = _probe_constant(func_a(Xs, i, j), "a[%d,%d]" % (i, j))
@@ -95,13 +95,29 @@ class NODE_WAN_solver:
         self.v_net.apply(init_weights)
         self.optimizer_u = torch.optim.Adam(self.u_net.parameters(), lr=self.config['u_rate'])
         self.optimizer_v = torch.optim.Adam(self.v_net.parameters(), lr=self.config['v_rate'])
+        # one process per GPU: N_r / N_b are GLOBAL counts, every rank samples its own shard; identical
+        # seeds give identical initial weights, all-reduced sums/gradients keep the replicas identical
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.best_l = float('inf')
         self.av_l = 0
         self.history = {"loss_u": [], "loss_v": [], "L2": [], "time": []}
 
-    def new_domain(self):
+    def new_domain(self, **kw):
         s = self.setup
-        return self.domain(s['shape_param'], s['dim'], s['T0'], s['T'], s['N_t'])
+        dom = self.domain(s['shape_param'], s['dim'], s['T0'], s['T'], s['N_t'], **kw)
+        if getattr(self, "world", 1) > 1:          # the time grid must be the same on every rank
+            t = dom.times.to(self.device)
+            torch.distributed.broadcast(t, src=0)
+            dom.times = t.to(dom.times.device)
+        return dom
+
+    def local_counts(self):
+        """(N_r, N_b) of this rank's shard"""
+        w = getattr(self, "world", 1)
+        if self.setup['N_r'] % w or self.setup['N_b'] % w:
+            raise RuntimeError("N_r and N_b must be divisible by the number of ranks")
+        return self.setup['N_r'] // w, self.setup['N_b'] // w
 
     def _step(self, phase, domain, batch):
         datau, datav, bdata = batch
@@ -110,6 +126,8 @@ class NODE_WAN_solver:
         h, f, g, a, b, c = func_eval(datau.detach(), bdata.detach(), self.setup, prediction_u, self.func_a,
                                      self.func_b, self.func_c, self.func_h, self.func_f, self.func_g)
         Loss = loss(self.config['alpha'], a, b, c, h, f, g, self.setup, domain, self.device)
+        if self.world > 1:
+            Loss.N_glob, Loss.Nb_glob = datau.shape[0] * self.world, bdata.shape[0] * self.world
         if phase == "u":
             val = Loss.u(prediction_u, prediction_v, self.u_net, datau, datav, bdata)
             val.backward()
@@ -142,7 +160,8 @@ class NODE_WAN_solver:
         loss_u = loss_v = None
         for k in range(self.iterations):
             domain = self.new_domain()
-            points = Comb_loader(self.setup['N_r'], self.setup['N_b'], domain, self.device)
+            n_r, n_b = self.local_counts()
+            points = Comb_loader(n_r, n_b, domain, self.device)
             for i in range(self.n1):
                 self.av_l = 0
                 self.optimizer_u.zero_grad()
@@ -168,8 +187,8 @@ class NODE_WAN_solver:
                     loss_v = self._step("v", domain, batch)
             L2 = None
             if self.func_u_sol is not None:
-                fresh = Comb_loader(self.setup['N_r'], self.setup['N_b'], domain, self.device)
-                L2 = L_norm(fresh.interioru, self.u_net, self.p, self.func_u_sol, domain.V(), self.setup['N_r']).item()
+                fresh = Comb_loader(n_r, n_b, domain, self.device)
+                L2 = L_norm(fresh.interioru, self.u_net, self.p, self.func_u_sol, domain.V(), n_r).item()
                 if self.log_json:
                     with open('L2_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
                         json.dump([L2], fh)
