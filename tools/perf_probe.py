@@ -32,7 +32,7 @@ def ev_time(fn, reps=3, warm=1):
 def main():
     log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 17
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    lib = L_.get()
+    lib = L_.XwLib(os.environ.get("XW_LIB", L_.LIB_PATH))
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     N = Nb = 1 << log2n

@@ -7,8 +7,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "xw_capi.cu")
 OUT = os.path.join(HERE, "libxnode_wan_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("xw_capi.cu", "xw_kernels.cuh", "xw_nets.cuh", "xw_platform.cuh")] + \
-       [os.path.join(os.path.dirname(HERE), "include", "xnode_wan_b200.h")]
+def _deps():
+    c = os.path.join(HERE, "csrc")
+    return [os.path.join(c, f) for f in os.listdir(c) if f.endswith((".cu", ".cuh"))] + \
+           [os.path.join(os.path.dirname(HERE), "include", "xnode_wan_b200.h"), os.path.abspath(__file__)]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -18,7 +20,7 @@ def up_to_date():
     if not os.path.exists(OUT):
         return False
     t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(p) <= t for p in DEPS)
+    return all(os.path.getmtime(p) <= t for p in _deps())
 
 
 def build(force=False, verbose=False):

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -68,6 +69,9 @@ int set_smem(K kern, size_t bytes, const char* name) {
 // compiled capacities (exact for configs/cube_pde.yaml: H=20, hh=10, Hv=50); smaller nets are
 // zero-padded into them, larger ones are rejected (no silent fallback).
 constexpr int kH = 20, kHH = 10, kHV = 50;
+#ifndef XW_TILE_QR
+#define XW_TILE_QR 4
+#endif
 constexpr int kBlkFwd = 128;
 
 int check_dims(const xw_dims* m) {
@@ -84,6 +88,8 @@ int check_dims(const xw_dims* m) {
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+int grid_for(long long items, int block, int ctas_per_sm);
+int ctas_per_sm_for(size_t smem, int cap);
 
 int stages_of(int solver) { return solver == 0 ? 1 : solver == 1 ? 2 : 4; }
 int bwd_block(int solver) { return solver == 2 ? 64 : 128; }
@@ -105,6 +111,37 @@ size_t smem_xnode_bwd(const xw_dims* m, int L, int block) {
 size_t smem_vnet_fwd(int d) {
     using S = xw::VSmem<kHV>;
     return (size_t)(xw::pad4(S::size(d + 1)) + 4) * 4 + 4 * 32 * 8;
+}
+constexpr int kQR = XW_TILE_QR;
+size_t smem_vtile_fwd(int d) {
+    using VT = xw::VTile<kHV, kQR>;
+    const int C = d + 1;
+    size_t f = (size_t)xw::pad4(VT::WIT + VT::wit_size(C)) + (size_t)VT::ROWS * VT::RS + (size_t)VT::ROWS * VT::xin_ld(C) +
+               (size_t)VT::NG * VT::ROWS * 2;
+    return f * 4 + 4 * 32 * 8 + 2 * VT::ROWS * 4;
+}
+constexpr int kQRB = 2;      // pair rows per lane in the tiled backward (2 x 64 rows = 128 points per tile)
+size_t smem_vtile_bwd(int d) {
+    using VT = xw::VTile<kHV, kQRB>;
+    const int C = d + 1, NPT = 2 * VT::ROWS;
+    size_t f = (size_t)xw::pad4(VT::WIT + VT::wit_size(C)) + (size_t)kHV * VT::WLD + 2 * (size_t)VT::ROWS * VT::RS +
+               (size_t)xw::pad4(NPT * VT::xin_ld(C)) + (size_t)VT::NG * NPT + NPT + (size_t)xw::pad4(kHV * (C + 1)) + 2 * NPT;
+    return f * 4 + 64;
+}
+struct VtileBwdPlan { int grid; size_t smem, scratch_bytes, part_bytes; };
+int plan_vtile_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
+    using VT = xw::VTile<kHV, kQRB>;
+    p->smem = smem_vtile_bwd(m->d);
+    if (p->smem > device()->smem_optin) return fail("tiled v-net backward needs %zu B shared memory (> %zu): dim too large", p->smem, device()->smem_optin);
+    const long long ntiles = ((long long)n * L + 2 * VT::ROWS - 1) / (2 * VT::ROWS);
+    p->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms * ctas_per_sm_for(p->smem, 2)));
+    p->scratch_bytes = align_up((size_t)p->grid * std::max(m->nv, 1) * VT::ROWS * VT::RS * 4, 256);
+    p->part_bytes = align_up((size_t)p->grid * xw::VLayout(m->d, m->Hv).size * 4, 256);
+    return 0;
+}
+bool use_point_kernels() {
+    const char* e = getenv("XW_VNET_IMPL");
+    return e && strcmp(e, "points") == 0;
 }
 size_t smem_vnet_bwd(const xw_dims* m, int block) {
     using S = xw::VSmem<kHV>;
@@ -203,6 +240,9 @@ size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
     const int vb = 128;
     int gv = grid_for((long long)n * L, vb, ctas_per_sm_for(smem_vnet_bwd(m, vb), 8));
     size_t bwd_v = align_up((size_t)gv * xw::VLayout(m->d, m->Hv).size * 4, 256);
+    VtileBwdPlan pv;
+    if (plan_vtile_bwd(m, n, L, &pv)) return 0;
+    bwd_v = std::max(bwd_v, pv.scratch_bytes + pv.part_bytes);
     return std::max(fwd, std::max(bwd_u, bwd_v)) + 1024;
 }
 
@@ -265,9 +305,27 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     b.c0 = coef->c0; b.c1 = coef->c1; b.ca = coef->a; b.cb = coef->b;
     b.u = ubuf; b.du = du; b.h = h; b.f = f; b.sums = sums; b.cot_u = cot_u; b.cot_v = cot_v; b.v_out = nullptr;
     const size_t smem = smem_vnet_fwd(m->d);
-    if (XW_SET_SMEM((xw::k_vnet_points<kHV, 1>), smem)) return 1;
-    XW_LAUNCH((xw::k_vnet_points<kHV, 1>), grid_for((long long)n * L, 128, 8), 128, smem, stream, b);
-    return XW_CHECK_LAUNCH("k_vnet_points<interior>");
+    if (use_point_kernels()) {
+        if (XW_SET_SMEM((xw::k_vnet_points<kHV, 1>), smem)) return 1;
+        XW_LAUNCH((xw::k_vnet_points<kHV, 1>), grid_for((long long)n * L, 128, 8), 128, smem, stream, b);
+        return XW_CHECK_LAUNCH("k_vnet_points<interior>");
+    }
+    // generation 2: time-row-0 gradient term (one thread per path) + CTA-tiled pass over all points
+    if (XW_SET_SMEM((xw::k_vnet_points<kHV, 2>), smem)) return 1;
+    XW_LAUNCH((xw::k_vnet_points<kHV, 2>), grid_for(n, 128, 8), 128, smem, stream, b);
+    if (XW_CHECK_LAUNCH("k_vnet_points<row0>")) return 1;
+    xw::VtileFwdArgs t{};
+    t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
+    t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
+    t.c0 = coef->c0; t.c1 = coef->c1; t.u = ubuf; t.h = h; t.f = f; t.sums = sums; t.cot_u = cot_u; t.cot_v = cot_v;
+    using VT = xw::VTile<kHV, kQR>;
+    const size_t tsmem = smem_vtile_fwd(m->d);
+    if (tsmem > device()->smem_optin) return fail("tiled v-net forward needs %zu B shared memory (> %zu): dim too large", tsmem, device()->smem_optin);
+    if (XW_SET_SMEM((xw::k_vnet_tile_fwd<kHV, kQR>), tsmem)) return 1;
+    const long long ntiles = ((long long)n * L + VT::ROWS - 1) / VT::ROWS;
+    const int tgrid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms * ctas_per_sm_for(tsmem, 6)));
+    XW_LAUNCH((xw::k_vnet_tile_fwd<kHV, kQR>), tgrid, VT::THREADS, tsmem, stream, t);
+    return XW_CHECK_LAUNCH("k_vnet_tile_fwd");
 }
 
 int xw_boundary_u(const xw_dims* m, const float* theta_u, const float* xb, long long xb_sn, const float* times_b,
@@ -315,6 +373,20 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
     if (!dom || !theta_v || !xv || !xv->t || !xv->x || !cot_v || !coefs_dev || !grad_v || !workspace)
         return fail("NULL pointer argument");
+    if (!use_point_kernels()) {
+        VtileBwdPlan pl;
+        if (plan_vtile_bwd(m, n, L, &pl)) return 1;
+        if (workspace_bytes < pl.scratch_bytes + pl.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, pl.scratch_bytes + pl.part_bytes);
+        xw::VtileBwdArgs t{};
+        t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
+        t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
+        t.cot = cot_v; t.coefs = coefs_dev; t.scratch = (float*)workspace; t.gpart = (float*)((char*)workspace + pl.scratch_bytes);
+        using VT = xw::VTile<kHV, kQRB>;
+        if (XW_SET_SMEM((xw::k_vnet_tile_bwd<kHV, kQRB>), pl.smem)) return 1;
+        XW_LAUNCH((xw::k_vnet_tile_bwd<kHV, kQRB>), pl.grid, VT::THREADS, pl.smem, stream, t);
+        if (XW_CHECK_LAUNCH("k_vnet_tile_bwd")) return 1;
+        return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
+    }
     const int block = 128;
     const size_t smem = smem_vnet_bwd(m, block);
     if (smem > device()->smem_optin) return fail("v backward needs %zu B shared memory per CTA (> %zu)", smem, device()->smem_optin);

@@ -254,10 +254,12 @@ XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
     stage_theta_v<HV>(sv, a.theta, a.d, a.Hvr);
     const long long nthr = (long long)XW_GDIM * XW_BDIM;
     const long long gtid = (long long)XW_BID * XW_BDIM + XW_TID;
-    const long long npts = (long long)a.n * a.L;
+    // MODE 2 visits time-row 0 of every path only (the grad_x phi . du term of src/loss.py:66-69)
+    const long long npts = MODE == 2 ? (long long)a.n : (long long)a.n * a.L;
     const int L = a.L, d = a.d;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (long long p = gtid; p < npts; p += nthr) {
+    for (long long it = gtid; it < npts; it += nthr) {
+        const long long p = MODE == 2 ? it * L : it;
         const long long n = p / L;
         const int l = (int)(p - n * L);
         const float t = a.p.t[n * a.p.t_sn + l * a.p.t_sl];
@@ -271,6 +273,28 @@ XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
         const float dv_t = vnet_input_grad<HV>(sv, 0, dl);
         const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, t, xp, d);
         const float phi = v * W.w;
+        if (MODE == 2) {
+            const float* dun = a.du + n * d;
+            float s31 = 0.f;
+            for (int i = 0; i < d; ++i) {
+                const float dphi_i = fmaf(W.w, vnet_input_grad<HV>(sv, 1 + i, dl), v * domain_dw_x(W, i, xp));
+                float q;
+                if (a.ca) {
+                    q = 0.f;
+                    for (int j = 0; j < d; ++j) q = fmaf(a.ca[i * d + j], dun[j], q);
+                } else {
+                    q = dun[i];
+                }
+                s31 = fmaf(dphi_i, q, s31);
+            }
+            if (a.cb) {
+                float bq = 0.f;
+                for (int j = 0; j < d; ++j) bq = fmaf(a.cb[j], dun[j], bq);
+                s31 = fmaf(phi, bq, s31);
+            }
+            acc[2] += (double)s31;
+            continue;
+        }
         const float dphi0 = fmaf(W.w, dv_t, v * W.dw_t);
         const float u = a.u[p], fv = a.f[p];
         const float cu_ = fmaf(a.c1, u, a.c0);
@@ -310,7 +334,7 @@ XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
         acc[2] += (double)s3;
         acc[3] += (double)(v * v);
     }
-    if (MODE == 1) {
+    if (MODE != 0) {
         const int idx[4] = {0, 1, 2, 3};
         block_sum_to_global<4>(acc, red, a.sums, idx);
     }
@@ -716,3 +740,5 @@ XW_GLOBAL void k_reduce_partials(const float* gpart, int nblocks, int P, float* 
 }
 
 }  // namespace xw
+
+#include "xw_vnet_tile.cuh"

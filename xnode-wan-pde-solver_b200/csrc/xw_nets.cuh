@@ -262,7 +262,7 @@ XW_DEV void field_fwd(const float* s, const float (&ax)[HH], float t, const floa
         for (int i = 0; i < HH; ++i) a[i] = b[i];
     }
 #pragma unroll
-    for (int i = 0; i < HH; ++i) tau[i] = tanhf(a[i]);
+    for (int i = 0; i < HH; ++i) tau[i] = tanh_fast(a[i]);
     rec.tanh_out(tau);
     load_row<H>(s + S::BF, out);
     matvec_acc<HH, H, S::HP>(s + S::WFT, tau, out);
@@ -454,7 +454,7 @@ XW_DEV float vnet_fwd(const float* s, float t, const float* XW_RESTRICT x, int d
     load_row<HV>(s + S::WZ, wz);
 #pragma unroll
     for (int i = 0; i < HV; ++i) {
-        tau[i] = tanhf(a[i]);
+        tau[i] = tanh_fast(a[i]);
         v = fmaf(wz[i], tau[i], v);
     }
     return v;

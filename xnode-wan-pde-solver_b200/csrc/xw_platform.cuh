@@ -32,6 +32,16 @@
 #define XW_ATOMIC_ADD_D(p, v) atomicAdd((p), (v))
 #endif
 
+// 16-byte asynchronous global->shared copy (LDGSTS) and its completion wait
+#ifdef XW_EMU
+#define XW_CP_ASYNC16(dst, src) memcpy((dst), (src), 16)
+#define XW_CP_ASYNC_WAIT_ALL() ((void)0)
+#else
+#define XW_CP_ASYNC16(dst, src)                                                                   \
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define XW_CP_ASYNC_WAIT_ALL() asm volatile("cp.async.wait_all;" ::: "memory")
+#endif
+
 // compiler-only memory barrier: keeps ptxas/nvcc from hoisting the (loop-invariant) shared-memory
 // weight loads out of the layer / time-step loops, which would need thousands of registers
 #define XW_FENCE() asm volatile("" ::: "memory")
@@ -78,6 +88,17 @@ XW_DEV void matvec_acc(const float* M, const float (&in)[IN], float (&out)[OUT])
     }
 }
 
+// tanh as 1 - 2/(1 + e^{2x}) on the SFU (ex2 + rcp approximations): absolute error ~1e-7, i.e. the
+// fp32 rounding level of the surrounding FMAs, at ~6 instructions instead of ~30 for tanhf()
+XW_DEV float tanh_fast(float x) {
+#ifdef XW_EMU
+    return tanhf(x);
+#else
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, 1.f + e);
+#endif
+}
+
 XW_DEV float warp_sum(float v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v += XW_SHFL_XOR(v, m);
@@ -88,6 +109,20 @@ XW_DEV double warp_sum_d(double v) {
     for (int m = 16; m > 0; m >>= 1) v += XW_SHFL_XOR(v, m);
     return v;
 }
+
+// packed pair of floats for the Blackwell FFMA2 path (fma.rn.f32x2, sm_100+): two IEEE fmas per
+// instruction, i.e. the same results as two fmaf() at half the issue slots
+#ifdef XW_EMU
+struct fpair { float lo, hi; };
+XW_DEV fpair pack2(float lo, float hi) { return fpair{lo, hi}; }
+XW_DEV void unpack2(fpair v, float& lo, float& hi) { lo = v.lo; hi = v.hi; }
+XW_DEV fpair fma2(fpair a, fpair b, fpair c) { return fpair{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+#else
+typedef unsigned long long fpair;
+XW_DEV fpair pack2(float lo, float hi) { fpair r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+XW_DEV void unpack2(fpair v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+XW_DEV fpair fma2(fpair a, fpair b, fpair c) { fpair d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+#endif
 
 // 128-bit LIFO of fixed-width bit groups (relu masks of the shared field layers)
 struct BitStack128 {
