@@ -170,8 +170,8 @@ def test_collapsed_layout_equals_dense_layout(emu):
         outs.append(res)
     for (l0, g0), (l1, g1) in zip(*outs):
         assert abs(l0 - l1) <= 1e-9 * abs(l0)
-        for a_, b_ in zip(g0, g1):
-            assert torch.allclose(a_, b_, rtol=1e-6, atol=1e-9)
+        for a_, b_ in zip(g0, g1):      # cross-warp fp32 atomics in the tiled backward: order-dependent rounding
+            assert G.rel(a_.numpy(), b_.numpy()) < 1e-5
     # forward-only evaluation agrees too
     with torch.no_grad():
         assert torch.allclose(s.u_net(dense["X"]), s.u_net(col["X"]), atol=1e-6)
