@@ -93,13 +93,15 @@ int xw_vnet_eval(const xw_dims* dims, const float* theta_v, const xw_points* pts
  *   cot_u[i,l] = A'(u) phi + L v[i,L-1] [l=L-1]                 A(u) = (c0 + c1 u) u
  *   cot_v[i,l] = w (A(u) + f) + L u[i,L-1] [l=L-1] - L h[i] [l=0]
  * and optionally u_out[n*L] (NULL to skip).
- * h[n], grad_h[n*d] (dh/dx at X[:,0,1:]), f[n*L] are the user's callables evaluated by the host. */
+ * h[n] = func_h(X[:,0,:]) (src/training.py:25), f[n*L] = func_f(X): the user's callables evaluated
+ * by the host.  s0[n]: initial scalar of each path (src/model.py:95-96: h(x) when the batch starts
+ * at T0, g at the entry point otherwise; NULL = use h); grad_s0[n*d] = d s0 / d x. */
 int xw_interior_forward(const xw_dims* dims, const xw_domain* dom, const xw_coef* coef,
                         const float* theta_u, const float* theta_v,
                         const float* x, long long x_sn, const float* times, int L,
-                        const xw_points* xv, const float* h, const float* grad_h, const float* f,
+                        const xw_points* xv, const float* h, const float* grad_s0, const float* f,
                         int n, double* sums, float* cot_u, float* cot_v, float* u_out,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        void* workspace, size_t workspace_bytes, void* stream, const float* s0);
 
 /* Boundary term (replaces loss.bdry = mean((u_net(BX) - g)^2), src/loss.py:83-85, and its
  * backward): adds sum (u_b - g)^2 to sums[BDRY]; if grad_u != NULL also accumulates
@@ -116,7 +118,7 @@ int xw_boundary_u(const xw_dims* dims, const float* theta_u, const float* xb, lo
 int xw_interior_backward_u(const xw_dims* dims, const float* theta_u, const float* x, long long x_sn,
                            const float* times, int L, const float* h, const float* cot_u, int n,
                            const double* coefs_dev, float* grad_u, int accumulate,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           void* workspace, size_t workspace_bytes, void* stream, const float* s0);
 
 /* theta_v gradient of loss_v (replaces loss_v.backward() for v_net, src/training.py:160,
  * including the side effect of src/loss.py:60):

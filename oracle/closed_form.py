@@ -281,9 +281,9 @@ def weak_form(thu, thv, X, XV, BX, coef, cfg, phase=None):
     """Everything src/training.py:129-137 / :153-161 produces for one batch.
 
     X, XV [N,L,C], BX [Nb,Lb,C] (time in channel 0)
-    coef : dict(h[N], grad_h[N,d] (dh/dx at X[:,0,1:]), f[N,L], g[Nb,Lb], sb[Nb] initial scalar
-                of the boundary paths, a (None=identity | [d,d] constant), b (None | [d] constant),
-                c0, c1 (c(X,u) = c0 + c1*u))
+    coef : dict(h[N], grad_h[N,d] (d s0/dx at X[:,0,1:]), f[N,L], g[Nb,Lb], sb[Nb] initial scalar
+                of the boundary paths, optional s0[N] initial scalar of the interior paths (default h),
+                a (None=identity | [d,d] constant), b (None | [d] constant), c0, c1 (c(X,u) = c0 + c1*u))
     cfg  : dict(nu, nv, solver, alpha, V, domain)
     returns dict with u, v, ub, w, du[N,d], dphi[N,L,C], I, S, init, bdry, loss_u, loss_v and,
     for phase in ('u','v'), `grads` = list in the reference's parameter order.
@@ -298,7 +298,8 @@ def weak_form(thu, thv, X, XV, BX, coef, cfg, phase=None):
     h, f, g_b = coef["h"], coef["f"], coef["g"]
     c0, c1 = float(coef.get("c0", 0.0)), float(coef.get("c1", 0.0))
 
-    u, cu = xnode_forward(thu, X[:, 0, 1:], X[0, :, 0], h, nu, solver)
+    s0 = coef.get("s0", h)      # initial scalar of the interior paths: h(x) at T0, else g at the entry point (src/model.py:95-96)
+    u, cu = xnode_forward(thu, X[:, 0, 1:], X[0, :, 0], s0, nu, solver)
     v, cv = vnet_forward(thv, XV, nv)
     w, dw = domain_w(cfg["domain"], XV)
     phi = v * w

@@ -26,6 +26,8 @@ def load(name):
     coef = dict(h=z["h"].astype(np.float64), f=z["f"].astype(np.float64), g=z["g"].astype(np.float64),
                 grad_h=z["grad_h"].astype(np.float64), sb=z["sb"].astype(np.float64),
                 c0=meta["c0"], c1=meta["c1"])
+    if "s0" in z.files:
+        coef["s0"] = z["s0"].astype(np.float64)
     gu = [z["gu_%02d" % i] for i in range(14)]
     gv = [z["gv_%02d" % i] for i in range(6)]
     return dict(z=z, meta=meta, params=p, thu=thu, thv=thv, thu_list=thu_list, thv_list=thv_list,

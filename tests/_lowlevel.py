@@ -103,6 +103,7 @@ def run_case(lib, be, case, coef_a=None, coef_b=None):
     Pu, Pv = lib.theta_sizes(dims)
     assert Pu == thu.shape[0] and Pv == thv.shape[0]
     h, gh, f = be.arr(z["h"]), be.arr(z["grad_h"]), be.arr(z["f"])
+    s0 = be.arr(z["s0"]) if "s0" in z.files else None
     g, sb = be.arr(z["g"]), be.arr(z["sb"])
     a_dev = be.arr(coef_a) if coef_a is not None else None
     b_dev = be.arr(coef_b) if coef_b is not None else None
@@ -115,7 +116,7 @@ def run_case(lib, be, case, coef_a=None, coef_b=None):
     cot_u, cot_v, u_out = be.zeros(N * L), be.zeros(N * L), be.zeros(N * L)
     lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), be.ptr(thu), be.ptr(thv),
              be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L, C.byref(pts), be.ptr(h), be.ptr(gh), be.ptr(f), N,
-             be.ptr(sums), be.ptr(cot_u), be.ptr(cot_v), be.ptr(u_out), be.ptr(ws), wsb, be.stream)
+             be.ptr(sums), be.ptr(cot_u), be.ptr(cot_v), be.ptr(u_out), be.ptr(ws), wsb, be.stream, be.ptr(s0))
     gu = be.zeros(Pu)
     lib.call("xw_boundary_u", C.byref(dims), be.ptr(thu), be.ptr_off(BXd, 1), Lb * Cc, be.ptr(times_b), Lb,
              be.ptr(sb), be.ptr(g), Nb, alpha / (Nb * Lb), be.ptr(sums), be.ptr(gu), 0, be.ptr(ws), wsb, be.stream)
@@ -129,7 +130,7 @@ def run_case(lib, be, case, coef_a=None, coef_b=None):
                u=be.host(u_out).reshape(N, L).copy())
     ku = be.arr(np.array([(2.0 / I) * V / (N * L), 2.0 * alpha / N, 1.0]), np.float64)
     lib.call("xw_interior_backward_u", C.byref(dims), be.ptr(thu), be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L,
-             be.ptr(h), be.ptr(cot_u), N, be.ptr(ku), be.ptr(gu), 1, be.ptr(ws), wsb, be.stream)
+             be.ptr(h), be.ptr(cot_u), N, be.ptr(ku), be.ptr(gu), 1, be.ptr(ws), wsb, be.stream, be.ptr(s0))
     kv = be.arr(np.array([-(2.0 / I) * V / (N * L), 2.0 / s[3], 1.0]), np.float64)
     gv = be.zeros(Pv)
     lib.call("xw_interior_backward_v", C.byref(dims), C.byref(dom), be.ptr(thv), C.byref(pts), be.ptr(cot_v), N, L,

@@ -34,6 +34,59 @@ CASES = {
 }
 
 
+SPHERE_CASES = {
+    # name: (domain, group index, seed)
+    "cone_d5_g2": ("NSphere_TCone", 2, 3),
+    "cone_d5_g4": ("NSphere_TCone", 4, 3),
+    "hourglass_d5_g2_reentry": ("NSphere_THourglass", 2, 3),
+    "hourglass_d5_g4_reentry": ("NSphere_THourglass", 4, 3),
+    "hourglass_d5_g18": ("NSphere_THourglass", 18, 3),
+}
+
+
+def run_sphere_case(name, dom, group, seed):
+    """variable-length float64 groups of the time-varying domains (src/dataset.py:48-229); group 0
+    (single time point, rank-2 shortcut of src/model.py:89-91) is not a supported batch"""
+    over = {'N_r': 300, 'N_b': 300, 'dim': 5, 'domain': dom, 'shape_param': 1.0, 'alpha': 10}
+    solver, funcs, params = rr.build(over, "Ex4_3_funcs", seed)
+    g_ = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for p in list(solver.u_net.parameters()) + list(solver.v_net.parameters()):
+            p.add_(0.1 * torch.randn(p.shape, generator=g_, dtype=p.dtype))
+    domain, batches = rr.sample(solver)
+    b = batches[group]
+    ou = rr.evaluate(solver, domain, b, 'u')
+    ov = rr.evaluate(solver, domain, b, 'v')
+    c = rr.components(solver, domain, b)
+    X, XV, BX = b
+    T0 = params['T0']
+
+    def scalar0(P):          # src/model.py:95-96
+        x0 = P[:, 0, :].clone().detach().double().requires_grad_(True)
+        val = funcs.func_h(x0) if float(P[0, 0, 0]) == T0 else funcs.func_g(x0.unsqueeze(1)).reshape(-1)
+        gr, = torch.autograd.grad(val.sum(), x0)
+        return val.detach().numpy(), gr[:, 1:].numpy()
+    s0, gs0 = scalar0(X)
+    sb, _ = scalar0(BX)
+    domspec = ["cone", 1.0] if dom == "NSphere_TCone" else ["hourglass", 1.0, float(params['T0']), float(params['T'])]
+    meta = dict(params={k: v for k, v in params.items() if k != 'domain'}, funcs="Ex4_3_funcs", seed=seed,
+                domain=domspec, V=c['V'], c0=0.0, c1=-1.0, group=group, domain_class=dom)
+    arrays = dict(X=X.numpy(), XV=XV.numpy(), BX=BX.numpy(), h=ou['h'], f=ou['f'], g=ou['g'], sb=sb, s0=s0, grad_h=gs0,
+                  loss_u=np.float64(ou['loss']), loss_v=np.float64(ov['loss']), I=np.float64(c['I']), S=np.float64(c['S']),
+                  init=np.float64(c['init']), bdry=np.float64(c['bdry']), u=ou['u'][..., 0], v=ou['v'][..., 0],
+                  du=c['du'], dphi=c['dphi'], w=c['w'][..., 0], meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+    for i, p in enumerate(solver.u_net.parameters()):
+        arrays["thu_%02d" % i] = p.detach().numpy()
+        arrays["gu_%02d" % i] = ou['grads'][i]
+    for i, p in enumerate(solver.v_net.parameters()):
+        arrays["thv_%02d" % i] = p.detach().numpy()
+        arrays["gv_%02d" % i] = ov['grads'][i]
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("%-28s loss_u=%.10e loss_v=%.10e I=%.6e shapes %s %s (%d KB)" % (
+        name, ou['loss'], ov['loss'], c['I'], tuple(X.shape), tuple(BX.shape), os.path.getsize(path) // 1024))
+
+
 def grad_h(func_h, X0):
     x = X0.clone().detach().double().requires_grad_(True)
     func_h(x).sum().backward()
@@ -86,3 +139,7 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_case(name, *spec)
+    for name, spec in SPHERE_CASES.items():
+        if only and name not in only:
+            continue
+        run_sphere_case(name, *spec)

@@ -22,7 +22,7 @@ def emu(monkeypatch):
 
 def make_solver(case, device="cpu"):
     p = dict(case["params"])
-    p["domain"] = "Hypercube"
+    p["domain"] = case["meta"].get("domain_class", "Hypercube")
     prob = xw.problems.by_name(case["meta"]["funcs"], p["dim"])
     s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, device,
                            "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
@@ -49,7 +49,8 @@ def eval_phase(s, case, phase, device="cpu"):
     return val, [q.grad.detach().cpu().numpy() for q in net.parameters()]
 
 
-@pytest.mark.parametrize("name", ["cube_d5_alpha1_randbias", "cube_d3_small_nets", "cube_d4_ex43", "cube_d3_rk4"])
+@pytest.mark.parametrize("name", ["cube_d5_alpha1_randbias", "cube_d3_small_nets", "cube_d4_ex43", "cube_d3_rk4",
+                                  "cone_d5_g2", "hourglass_d5_g2_reentry", "hourglass_d5_g18"])
 def test_reference_api_matches_golden(emu, name):
     case = G.load(name)
     s, _ = make_solver(case)

@@ -77,6 +77,7 @@ def main():
         return fl.value / (t * 1e-3) / 1e12
     res["fma_tflops_ffma"] = fma(0)
     res["fma_tflops_ffma2"] = fma(1)
+    res["mma_sync_tf32_tflops"] = fma(2)
 
     def xeval():
         lib.call("xw_xnode_eval", C.byref(dims), p(thu), p(x), d, p(times), L, p(h), N, p(u_out), st)
@@ -84,13 +85,13 @@ def main():
         lib.call("xw_vnet_eval", C.byref(dims), p(thv), C.byref(pts), N, L, p(v_out), st)
     def ifwd():
         lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), p(thu), p(thv), p(x), d, p(times), L,
-                 C.byref(pts), p(h), p(gh), p(f), N, p(sums), p(cot_u), p(cot_v), p(u_out), p(ws), wsb, st)
+                 C.byref(pts), p(h), p(gh), p(f), N, p(sums), p(cot_u), p(cot_v), p(u_out), p(ws), wsb, st, None)
     def bdry():
         lib.call("xw_boundary_u", C.byref(dims), p(thu), p(xb), d, p(times), L, p(sb), p(g), Nb, 1e-3, p(sums), p(gu), 0,
                  p(ws), wsb, st)
     def bwdu():
         lib.call("xw_interior_backward_u", C.byref(dims), p(thu), p(x), d, p(times), L, p(h), p(cot_u), N, p(ku), p(gu), 1,
-                 p(ws), wsb, st)
+                 p(ws), wsb, st, None)
     def bwdv():
         lib.call("xw_interior_backward_v", C.byref(dims), C.byref(dom), p(thv), C.byref(pts), p(cot_v), N, L, p(ku), p(gv),
                  0, p(ws), wsb, st)

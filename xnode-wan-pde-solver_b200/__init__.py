@@ -7,7 +7,7 @@ The directory name carries a hyphen (it mirrors the upstream repository name); i
 """
 from . import _lib, hotpath, problems  # noqa: F401
 from .aux import L_norm, rel_err  # noqa: F401
-from .dataset import Comb_loader, Hypercube  # noqa: F401
+from .dataset import Comb_loader, Hypercube, NSphere_TCone, NSphere_THourglass  # noqa: F401
 from .loss import CoefA, CoefB, CoefC, loss  # noqa: F401
 from .paths import CollapsedPaths  # noqa: F401
 from .model import LazyPrediction, NeuralODE, discriminator, init_weights  # noqa: F401

@@ -92,7 +92,7 @@ int grid_for(long long items, int block, int ctas_per_sm);
 int ctas_per_sm_for(size_t smem, int cap);
 
 int stages_of(int solver) { return solver == 0 ? 1 : solver == 1 ? 2 : 4; }
-int bwd_block(int solver) { return solver == 2 ? 64 : 128; }
+int bwd_block(int solver) { (void)solver; return 128; }
 
 size_t smem_xnode_fwd(int d, int L) {
     using S = xw::USmem<kH, kHH>;
@@ -103,8 +103,8 @@ size_t smem_xnode_bwd(const xw_dims* m, int L, int block) {
     const int nw = block / 32;
     const xw::ULayout g(m->d, m->H, m->hh);
     size_t f = (size_t)xw::pad4(S::size(m->d)) + xw::pad4(L) + 4;
-    f += (size_t)stages_of(m->solver) * m->nu * kHH * block;       // (nsh+1) = nu
-    f += (size_t)nw * 128 * xw::kStgLd;
+    f += (size_t)m->nu * kHH * block;                              // (nsh+1) = nu, one stage at a time
+    f += (size_t)nw * xw::kStgRowsU * xw::kStgLd;
     f += (size_t)nw * xw::pad4(g.size);
     return f * 4 + 32 * 8;
 }
@@ -276,7 +276,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
                         const float* theta_v, const float* x, long long x_sn, const float* times, int L,
                         const xw_points* xv, const float* h, const float* grad_h, const float* f, int n,
                         double* sums, float* cot_u, float* cot_v, float* u_out, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+                        size_t workspace_bytes, void* stream, const float* s0) {
     if (check_dims(m)) return 1;
     if (!device()) return fail("no CUDA device");
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
@@ -295,8 +295,8 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
 
     xw::XnodeFwdArgs a{};
     a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
-    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = h; a.u_out = ubuf;
-    a.grad_h = grad_h; a.du_out = du; a.yhist = yhist; a.sums = sums;
+    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0 ? s0 : h; a.u_out = ubuf;
+    a.grad_h = grad_h; a.du_out = du; a.yhist = yhist; a.sums = sums; a.hloss = h;
     if (launch_xnode_fwd<1>(m, a, gf, smem_xnode_fwd(m->d, L), stream)) return 1;
 
     xw::VnetFwdArgs b{};
@@ -349,7 +349,7 @@ int xw_boundary_u(const xw_dims* m, const float* theta_u, const float* xb, long 
 
 int xw_interior_backward_u(const xw_dims* m, const float* theta_u, const float* x, long long x_sn, const float* times,
                            int L, const float* h, const float* cot_u, int n, const double* coefs_dev, float* grad_u,
-                           int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+                           int accumulate, void* workspace, size_t workspace_bytes, void* stream, const float* s0) {
     if (check_dims(m)) return 1;
     if (!device()) return fail("no CUDA device");
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
@@ -359,7 +359,7 @@ int xw_interior_backward_u(const xw_dims* m, const float* theta_u, const float* 
     if (workspace_bytes < p.hist_bytes + p.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, p.hist_bytes + p.part_bytes);
     xw::XnodeBwdArgs a{};
     a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
-    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = h; a.cot = cot_u; a.coefs = coefs_dev;
+    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0 ? s0 : h; a.hloss = h; a.cot = cot_u; a.coefs = coefs_dev;
     a.gscale = 0.0; a.yhist = (float*)workspace; a.gpart = (float*)((char*)workspace + p.hist_bytes); a.sums = nullptr;
     if (launch_xnode_bwd<0>(m, a, p.grid, p.block, p.smem, stream)) return 1;
     return reduce_partials(a.gpart, p.grid, xw_theta_u_size(m), grad_u, accumulate, stream);
@@ -445,6 +445,26 @@ __global__ void __launch_bounds__(256) k_fma_probe(int iters, float* sink, float
     for (int i = 0; i < 16; ++i) s += a[i];
     if (s == 123.456f) sink[0] = s;
 }
+// legacy warp-level tensor-core path (mma.sync m16n8k8 TF32): 8 independent accumulator tiles per warp
+__global__ void __launch_bounds__(256) k_mma_probe_tf32(int iters, float* sink) {
+    float c[8][4];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[t][i] = 0.f;
+    unsigned a0 = 0x3f800000u + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = 0x3f000000u + threadIdx.x, b1 = b0 + 7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[t][0]), "+f"(c[t][1]), "+f"(c[t][2]), "+f"(c[t][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += c[t][0] + c[t][1] + c[t][2] + c[t][3];
+    if (s == 123.456f) sink[0] = s;
+}
 }  // namespace
 #endif
 
@@ -458,6 +478,11 @@ extern "C" int xw_fma_probe(int variant, int iters, double* flops_host, void* st
     static float* sink = nullptr;
     if (!sink && cudaMalloc(&sink, 256) != cudaSuccess) return fail("cudaMalloc failed");
     const int grid = dv->sms * 8, block = 256;
+    if (variant == 2) {
+        k_mma_probe_tf32<<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink);
+        if (flops_host) *flops_host = 2.0 * 16 * 8 * 8 * 8 * (double)iters * (double)grid * (block / 32);
+        return check_launch("k_mma_probe_tf32");
+    }
     if (variant == 0) k_fma_probe<0><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink, 1.f);
     else k_fma_probe<1><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink, 1.f);
     if (flops_host) *flops_host = 2.0 * 16 * 8 * (double)iters * (double)grid * block;

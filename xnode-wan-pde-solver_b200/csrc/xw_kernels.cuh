@@ -47,6 +47,7 @@ struct XnodeFwdArgs {
     const float* theta; const float* x; long long x_sn; const float* times; const float* s0;
     float* u_out;
     const float* grad_h; float* du_out; float* yhist; double* sums;
+    const float* hloss;          // func_h values used by loss.init (== s0 when the batch starts at T0)
 };
 
 template <int H, int HH>
@@ -142,7 +143,7 @@ XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
         float u = project_u<H, HH>(sw, y);
         if (a.u_out) a.u_out[n * L] = u;
         if (MODE == 1) {
-            init_acc += (double)((u - s0) * (u - s0));
+            { const float hd = u - a.hloss[n]; init_acc += (double)(hd * hd); }
 #pragma unroll
             for (int i = 0; i < H; ++i) a.yhist[(long long)i * nthr + gtid] = y[i];
         }
@@ -350,6 +351,7 @@ struct XnodeBwdArgs {
     const float* theta; const float* x; long long x_sn; const float* times; const float* s0;
     const float* cot;            // MODE 0: cot_u[n*L]   MODE 1: g[n*L]
     const double* coefs;         // MODE 0: device k0,k1,k2
+    const float* hloss;          // MODE 0: func_h values of loss.init
     double gscale;               // MODE 1
     float* yhist; float* gpart; double* sums;
 };
@@ -366,11 +368,15 @@ struct OuterShape {
     static constexpr int rows_r = NBI * BI;
 };
 
-template <int O, int I, class Dst>
+// staging buffer of one warp: d-side rows [0, ROFF), r-side rows [ROFF, ...)
+template <int O, int I, int ROFF, class Dst>
 XW_DEV void outer_auto(const float (&dl)[O], const float (&r)[I], float* stg, Dst dst) {
     using Sh = OuterShape<O, I>;
-    warp_outer<O, I, Sh::BO, Sh::NBO, Sh::BI, Sh::NBI>(dl, r, stg, stg + 64 * kStgLd, dst);
+    static_assert(Sh::rows_d <= ROFF, "d-side staging rows");
+    warp_outer<O, I, Sh::BO, Sh::NBO, Sh::BI, Sh::NBI>(dl, r, stg, stg + ROFF * kStgLd, dst);
 }
+constexpr int kStgRowsU = 32 + 24;     // XNODE: d-side <= 32 rows, r-side <= 24 rows (warp_outer_dyn chunks of 16)
+constexpr int kStgRowsV = 64 + 64;     // per-point v-net kernel
 
 // reverse of one field evaluation with parameter gradients
 template <int H, int HH>
@@ -383,7 +389,7 @@ XW_DEV void field_rev_grads(const float* sw, const float* acts, int stride, int 
 #pragma unroll
     for (int i = 0; i < HH; ++i) tau1[i] = acts[(nsh * HH + i) * stride];
     tau1[HH] = 1.f;
-    outer_auto<H, HH + 1>(gout, tau1, stg, [&](int o, int i) -> float* {
+    outer_auto<H, HH + 1, 32>(gout, tau1, stg, [&](int o, int i) -> float* {
         if (o >= Hr) return nullptr;
         if (i == HH) return gw + g.bf + o;
         return i < HHr ? gw + g.Wf + o * HHr + i : nullptr;
@@ -399,7 +405,7 @@ XW_DEV void field_rev_grads(const float* sw, const float* acts, int stride, int 
 #pragma unroll
         for (int i = 0; i < HH; ++i) r1[i] = acts[((j - 1) * HH + i) * stride];
         r1[HH] = 1.f;
-        outer_auto<HH, HH + 1>(dl, r1, stg, [&](int o, int i) -> float* {
+        outer_auto<HH, HH + 1, 32>(dl, r1, stg, [&](int o, int i) -> float* {
             if (o >= HHr) return nullptr;
             if (i == HH) return gw + g.bs + o;
             return i < HHr ? gw + g.Ws + o * HHr + i : nullptr;
@@ -416,7 +422,7 @@ XW_DEV void field_rev_grads(const float* sw, const float* acts, int stride, int 
     for (int i = 0; i < H; ++i) yt1[i] = yin[i];
     yt1[H] = tstage;
     yt1[H + 1] = 1.f;
-    outer_auto<HH, H + 2>(dl, yt1, stg, [&](int o, int i) -> float* {
+    outer_auto<HH, H + 2, 32>(dl, yt1, stg, [&](int o, int i) -> float* {
         if (o >= HHr) return nullptr;
         if (i == H + 1) return gw + g.ba + o;
         if (i == H) return gw + g.Wa + o * g.lda + g.d;
@@ -437,15 +443,15 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
     const int Pp = pad4(g.size);
     float* sw = reinterpret_cast<float*>(smem_raw);
     float* st = sw + pad4(S::size(a.d));
-    float* sacts = st + pad4(a.L) + 4;                                  // [S][(nsh+1)*HH][BDIM]
-    float* sstg = sacts + (size_t)T::S * (a.nsh + 1) * HH * XW_BDIM;    // [nwarps][128][kStgLd]
-    float* sgrad = sstg + (size_t)nwarps * 128 * kStgLd;                // [nwarps][Pp]
+    float* sacts = st + pad4(a.L) + 4;                                  // [(nsh+1)*HH][BDIM]  ONE stage at a time
+    float* sstg = sacts + (size_t)(a.nsh + 1) * HH * XW_BDIM;    // [nwarps][kStgRowsU][kStgLd]
+    float* sgrad = sstg + (size_t)nwarps * kStgRowsU * kStgLd;                // [nwarps][Pp]
     double* red = reinterpret_cast<double*>(sgrad + (size_t)nwarps * Pp);
     stage_theta_u<H, HH>(sw, a.theta, a.d, a.Hr, a.HHr);
     for (int i = XW_TID; i < a.L; i += XW_BDIM) st[i] = a.times[i];
     for (int i = XW_TID; i < nwarps * Pp; i += XW_BDIM) sgrad[i] = 0.f;
     XW_SYNCTHREADS();
-    float* stg = sstg + (size_t)warp * 128 * kStgLd;
+    float* stg = sstg + (size_t)warp * kStgRowsU * kStgLd;
     float* gw = sgrad + (size_t)warp * Pp;
 
     const long long nthr = (long long)XW_GDIM * XW_BDIM;
@@ -483,7 +489,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
             if (!active) return 0.f;
             if (MODE == 0) {
                 float G = fmaf(k0, a.cot[n * L + l], k2);
-                if (l == 0) G = fmaf(k1, u - s0, G);
+                if (l == 0) G = fmaf(k1, u - a.hloss[n], G);
                 return G;
             } else {
                 const float r = u - a.cot[n * L + l];
@@ -507,15 +513,38 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
             float yl[H], ycur[H];
 #pragma unroll
             for (int i = 0; i < H; ++i) { yl[i] = a.yhist[((long long)l * H + i) * nthr + gtid]; ycur[i] = yl[i]; }
-            RecSmem<HH> rec[T::S];
-#pragma unroll
-            for (int s = 0; s < T::S; ++s) {
-                rec[s].base = sacts + (size_t)s * (nsh + 1) * HH * XW_BDIM + XW_TID;
-                rec[s].stride = XW_BDIM;
-                rec[s].nsh = nsh;
-            }
+            // stage inputs yin[s] (forward through the stages; only the LAST stage records its
+            // internals: the shared-memory activation buffer holds one stage at a time, earlier
+            // stages are re-evaluated right before their own reverse -> 2S-1 field evaluations)
+            RecSmem<HH> rec;
+            rec.base = sacts + XW_TID;
+            rec.stride = XW_BDIM;
+            rec.nsh = nsh;
             float yin[T::S][H];
-            rk_step<H, HH, SOLVER, RecSmem<HH>, true>(sw, ax, t0, dt, nsh, ycur, rec, yin);
+            {
+                float kst[T::S][H];
+#pragma unroll
+                for (int s = 0; s < T::S; ++s) {
+#pragma unroll
+                    for (int i = 0; i < H; ++i) yin[s][i] = ycur[i];
+#pragma unroll
+                    for (int r = 0; r < s; ++r) {
+                        const float c = T::a(s, r);
+                        if (c != 0.f) {
+                            const float cd = c * dt;
+#pragma unroll
+                            for (int i = 0; i < H; ++i) yin[s][i] = fmaf(cd, kst[r][i], yin[s][i]);
+                        }
+                    }
+                    float tau[HH];
+                    if (s + 1 < T::S) {
+                        RecNone<HH> none;
+                        field_fwd<H, HH>(sw, ax, fmaf(T::c(s), dt, t0), yin[s], nsh, kst[s], tau, none);
+                    } else {
+                        field_fwd<H, HH>(sw, ax, fmaf(T::c(s), dt, t0), yin[s], nsh, kst[s], tau, rec);
+                    }
+                }
+            }
             float kbar[T::S][H], ybar[H];
 #pragma unroll
             for (int s = 0; s < T::S; ++s)
@@ -525,10 +554,14 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
             for (int i = 0; i < H; ++i) ybar[i] = lam[i];
 #pragma unroll
             for (int s = T::S - 1; s >= 0; --s) {
+                if (s + 1 < T::S) {      // re-evaluate this stage, recording its internals
+                    float kdummy[H], tau[HH];
+                    field_fwd<H, HH>(sw, ax, fmaf(T::c(s), dt, t0), yin[s], nsh, kdummy, tau, rec);
+                }
                 float gin[H];
 #pragma unroll
                 for (int i = 0; i < H; ++i) gin[i] = 0.f;
-                field_rev_grads<H, HH>(sw, rec[s].base, XW_BDIM, nsh, fmaf(T::c(s), dt, t0), yin[s], kbar[s], gin, a0,
+                field_rev_grads<H, HH>(sw, rec.base, XW_BDIM, nsh, fmaf(T::c(s), dt, t0), yin[s], kbar[s], gin, a0,
                                        stg, gw, g);
 #pragma unroll
                 for (int i = 0; i < H; ++i) ybar[i] += gin[i];
@@ -550,7 +583,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
             gbo += G;
         }
         // x part of the first field layer: dWa[:, j] += a0 (x) x_j
-        warp_outer_dyn<HH, 3>(a0, a.d, [&](int j) -> float { return xp[j]; }, stg, stg + 64 * kStgLd,
+        warp_outer_dyn<HH, 3, 2>(a0, a.d, [&](int j) -> float { return xp[j]; }, stg, stg + 32 * kStgLd,
                               [&](int o, int j) -> float* { return o < a.HHr ? gw + g.Wa + o * g.lda + j : nullptr; });
         // lift reverse
         float z1[H], z2[H], y0[H];
@@ -560,7 +593,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
 #pragma unroll
             for (int i = 0; i < H; ++i) r1[i] = z2[i];
             r1[H] = 1.f;
-            outer_auto<H, H + 1>(lam, r1, stg, [&](int o, int i) -> float* {
+            outer_auto<H, H + 1, 32>(lam, r1, stg, [&](int o, int i) -> float* {
                 if (o >= a.Hr) return nullptr;
                 if (i == H) return gw + g.b2 + o;
                 return i < a.Hr ? gw + g.W2 + o * a.Hr + i : nullptr;
@@ -577,7 +610,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
 #pragma unroll
             for (int i = 0; i < H; ++i) r1[i] = z1[i];
             r1[H] = 1.f;
-            outer_auto<H, H + 1>(dz2, r1, stg, [&](int o, int i) -> float* {
+            outer_auto<H, H + 1, 32>(dz2, r1, stg, [&](int o, int i) -> float* {
                 if (o >= a.Hr) return nullptr;
                 if (i == H) return gw + g.b1 + o;
                 return i < a.Hr ? gw + g.W1 + o * a.Hr + i : nullptr;
@@ -588,7 +621,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
         for (int i = 0; i < H; ++i) dz1[i] = z1[i] > 0.f ? dz1[i] : 0.f;
         {
             float r2[2] = {s0, 1.f};
-            outer_auto<H, 2>(dz1, r2, stg, [&](int o, int i) -> float* {
+            outer_auto<H, 2, 32>(dz1, r2, stg, [&](int o, int i) -> float* {
                 if (o >= a.Hr) return nullptr;
                 return i == 0 ? gw + g.W0 + o : gw + g.b0 + o;
             });
@@ -684,7 +717,7 @@ XW_GLOBAL void k_vnet_bwd(VnetBwdArgs a) {
         }
         {
             float g1[1] = {G};
-            outer_auto<1, HV + 1>(g1, tau1, stg, [&](int o, int i) -> float* {
+            outer_auto<1, HV + 1, 64>(g1, tau1, stg, [&](int o, int i) -> float* {
                 if (i == HV) return gw + g.bz;
                 return i < Hvr ? gw + g.Wz + i : nullptr;
             });
@@ -701,7 +734,7 @@ XW_GLOBAL void k_vnet_bwd(VnetBwdArgs a) {
 #pragma unroll
             for (int i = 0; i < HV; ++i) r1[i] = acts[(k - 1) * HV + i];
             r1[HV] = 1.f;
-            outer_auto<HV, HV + 1>(dl, r1, stg, [&](int o, int i) -> float* {
+            outer_auto<HV, HV + 1, 64>(dl, r1, stg, [&](int o, int i) -> float* {
                 if (o >= Hvr) return nullptr;
                 if (i == HV) return gw + g.bh + o;
                 return i < Hvr ? gw + g.Wh + o * Hvr + i : nullptr;
@@ -714,7 +747,7 @@ XW_GLOBAL void k_vnet_bwd(VnetBwdArgs a) {
             for (int i = 0; i < HV; ++i) dl[i] = r1[i] > 0.f ? dn[i] : 0.f;
         }
         // input layer: columns (t, x_0..x_{d-1}, 1)
-        warp_outer_dyn<HV, 7>(dl, C + 1,
+        warp_outer_dyn<HV, 7, 4>(dl, C + 1,
                               [&](int c) -> float { return c == 0 ? t : (c <= d ? xp[c - 1] : 1.f); },
                               stg, stg + 64 * kStgLd,
                               [&](int o, int c) -> float* {

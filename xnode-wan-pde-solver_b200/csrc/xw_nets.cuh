@@ -355,10 +355,10 @@ XW_DEV void warp_outer(const float (&dl)[O], const float (&r)[I], float* stg_d, 
 }
 
 // same for a RUNTIME number of columns (e.g. the d spatial inputs): colval(i) returns this lane's
-// i-th column value; columns are processed in chunks of 32 (BI=4 x NBI=8), rows in passes of 4*BO.
-template <int O, int BO, class ColVal, class Dst>
+// i-th column value; columns are processed in chunks of 8*BI (r-side staging rows), rows in passes of 4*BO.
+template <int O, int BO, int BI, class ColVal, class Dst>
 XW_DEV void warp_outer_dyn(const float (&dl)[O], int ncols, ColVal colval, float* stg_d, float* stg_r, Dst dst) {
-    constexpr int NBO = 4, BI = 4, NBI = 8;
+    constexpr int NBO = 4, NBI = 8;
     const int lane = XW_TID & 31;
 #pragma unroll
     for (int o = 0; o < O; ++o) stg_d[o * kStgLd + lane] = dl[o];

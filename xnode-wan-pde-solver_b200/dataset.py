@@ -126,5 +126,54 @@ class Comb_loader:
         return self._cache[idx]
 
 
-def domain_volume_sphere(dim, r, timecomp):
-    return math.pi ** (dim / 2) / math.gamma(dim / 2 + 1) * r ** dim * timecomp
+def _ball_volume(dim, r):
+    return math.pi ** (dim / 2) / math.gamma(dim / 2 + 1) * r ** dim
+
+
+class _SphereDomain:
+    """time-varying ball domains of the reference (src/dataset.py:48-229): the weight func_w, its
+    in-kernel counterpart (loss.domain_spec) and the Monte-Carlo volume V are provided; the
+    variable-length group SAMPLERS (`interior`, `boundary`) are a later row of the scope table
+     -- batches sampled by the reference's own classes run through loss.u / loss.v."""
+
+    def __init__(self, r: float, dim: int, T0: float, T: float, N_t: int, times=None):
+        self.r, self.dim, self.T0, self.T, self.N_t = r, dim, T0, T, N_t
+        if times is None:
+            times = torch.empty(N_t).uniform_(T0, T).sort(0).values
+            times[0], times[-1] = T0, T
+        self.times = times
+
+    def interior(self, N_r: int):
+        raise NotImplementedError("%s.interior: sphere-domain samplers are not part of this round" % type(self).__name__)
+
+    def boundary(self, N_b: int):
+        raise NotImplementedError("%s.boundary: sphere-domain samplers are not part of this round" % type(self).__name__)
+
+    def bound_pad(self, x):
+        raise NotImplementedError("bound_pad / fillt (evaluation from inside the domain) is not supported yet")
+
+
+class NSphere_TCone(_SphereDomain):
+    """ball of radius r (1 - t)   (reference src/dataset.py:162-229)"""
+
+    def func_w(self, x: torch.Tensor):
+        return self.r * (1 - x[:, :, 0]) - x[:, :, 1:].pow(2).sum(2).sqrt()
+
+    def V(self):
+        tc = (1 - self.T0) ** (self.dim + 1) / (self.dim + 1) - (1 - self.T) ** (self.dim + 1) / (self.dim + 1)
+        return _ball_volume(self.dim, self.r) * tc
+
+
+class NSphere_THourglass(_SphereDomain):
+    """ball of radius r ((T-T0) - t) for t <= (T-T0)/2 and r t afterwards (reference src/dataset.py:48-159)"""
+
+    def func_w(self, x: torch.Tensor):
+        t = x[:, :, 0]
+        dist = x[:, :, 1:].pow(2).sum(2).sqrt()
+        span = self.T - self.T0
+        return torch.where(t <= span / 2, self.r * (span - t) - dist, self.r * t - dist)
+
+    def V(self):
+        tc = 2 * ((1 - self.T0) ** (self.dim + 1) / (self.dim + 1) -
+                  (1 - (self.T - self.T0) / 2) ** (self.dim + 1) / (self.dim + 1))
+        return _ball_volume(self.dim, self.r) * tc

@@ -124,7 +124,8 @@ class Batch:
     xv_sn: int
     xv_sl: int
     tv: Optional[torch.Tensor] = None   # separate tensor for XV times (collapsed layout)
-    h: Optional[torch.Tensor] = None        # [N]
+    h: Optional[torch.Tensor] = None        # [N]   func_h(X[:,0,:])
+    s0: Optional[torch.Tensor] = None       # [N]   initial scalar when it is not h (batch not starting at T0)
     grad_h: Optional[torch.Tensor] = None   # [N, d]
     f: Optional[torch.Tensor] = None        # [N, L]
     # boundary
@@ -229,7 +230,7 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
     _call(lib, "xw_interior_forward", dev, C.byref(dims), C.byref(cdom), C.byref(ccoef), _ptr(theta_u), _ptr(theta_v),
              C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), L, C.byref(pts),
              _ptr(batch.h), _ptr(batch.grad_h), _ptr(batch.f), N, _ptr(sums), _ptr(cot_u), _ptr(cot_v), None,
-             _ptr(ws), ws.numel(), st)
+             _ptr(ws), ws.numel(), st, _ptr(batch.s0))
     if with_boundary:
         gscale = float(alpha) / (batch.Nb_glob * batch.Lb)
         _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
@@ -295,7 +296,8 @@ class WeakLoss(torch.autograd.Function):
             grad = (gb * go.to(gb.dtype)).contiguous()
             _call(lib, "xw_interior_backward_u", dev, C.byref(dims), _ptr(theta_u),
                      C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), batch.L,
-                     _ptr(batch.h), _ptr(cot_u), batch.N, _ptr(ks), _ptr(grad), 1, _ptr(ws), ws.numel(), st)
+                     _ptr(batch.h), _ptr(cot_u), batch.N, _ptr(ks), _ptr(grad), 1, _ptr(ws), ws.numel(), st,
+                     _ptr(batch.s0))
             _allreduce(grad, ctx.group)
             gl = unflatten_like(grad, ctx.meta[:nup])
             return none + tuple(gl) + (None,) * (len(ctx.meta) - nup)

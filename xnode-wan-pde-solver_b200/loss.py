@@ -92,7 +92,7 @@ class loss:
             gh, = torch.autograd.grad(hv.sum(), x0, allow_unused=True)
         b.grad_h = hotpath.as_f32(gh[:, 1:]) if gh is not None else torch.zeros(b.N, b.d, device=dev)
         if kind == "g":
-            b.h = hotpath.as_f32(hv)
+            b.s0 = hotpath.as_f32(hv)
         b.f = hotpath.as_f32(self.f)
         if border is not None:
             kb = u_net.start_kind(border)
