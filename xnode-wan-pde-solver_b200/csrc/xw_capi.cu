@@ -72,6 +72,9 @@ constexpr int kH = 20, kHH = 10, kHV = 50;
 #ifndef XW_TILE_QR
 #define XW_TILE_QR 4
 #endif
+#ifndef XW_TILE_NH
+#define XW_TILE_NH 1
+#endif
 constexpr int kBlkFwd = 128;
 
 int check_dims(const xw_dims* m) {
@@ -112,9 +115,9 @@ size_t smem_vnet_fwd(int d) {
     using S = xw::VSmem<kHV>;
     return (size_t)(xw::pad4(S::size(d + 1)) + 4) * 4 + 4 * 32 * 8;
 }
-constexpr int kQR = XW_TILE_QR;
+constexpr int kQR = XW_TILE_QR, kNH = XW_TILE_NH;
 size_t smem_vtile_fwd(int d) {
-    using VT = xw::VTile<kHV, kQR>;
+    using VT = xw::VTile<kHV, kQR, kNH>;
     const int C = d + 1;
     size_t f = (size_t)xw::pad4(VT::WIT + VT::wit_size(C)) + (size_t)VT::ROWS * VT::RS + (size_t)VT::ROWS * VT::xin_ld(C) +
                (size_t)VT::NG * VT::ROWS * 2;
@@ -318,13 +321,13 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
     t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
     t.c0 = coef->c0; t.c1 = coef->c1; t.u = ubuf; t.h = h; t.f = f; t.sums = sums; t.cot_u = cot_u; t.cot_v = cot_v;
-    using VT = xw::VTile<kHV, kQR>;
+    using VT = xw::VTile<kHV, kQR, kNH>;
     const size_t tsmem = smem_vtile_fwd(m->d);
     if (tsmem > device()->smem_optin) return fail("tiled v-net forward needs %zu B shared memory (> %zu): dim too large", tsmem, device()->smem_optin);
-    if (XW_SET_SMEM((xw::k_vnet_tile_fwd<kHV, kQR>), tsmem)) return 1;
+    if (XW_SET_SMEM((xw::k_vnet_tile_fwd<kHV, kQR, kNH>), tsmem)) return 1;
     const long long ntiles = ((long long)n * L + VT::ROWS - 1) / VT::ROWS;
     const int tgrid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms * ctas_per_sm_for(tsmem, 6)));
-    XW_LAUNCH((xw::k_vnet_tile_fwd<kHV, kQR>), tgrid, VT::THREADS, tsmem, stream, t);
+    XW_LAUNCH((xw::k_vnet_tile_fwd<kHV, kQR, kNH>), tgrid, VT::THREADS, tsmem, stream, t);
     return XW_CHECK_LAUNCH("k_vnet_tile_fwd");
 }
 

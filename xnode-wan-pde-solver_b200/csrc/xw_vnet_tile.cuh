@@ -19,7 +19,7 @@
 
 namespace xw {
 
-template <int HV, int QR_ = 3>
+template <int HV, int QR_ = 3, int NH_ = 1>
 struct VTile {
     static constexpr int NG = 4;                         // warps per CTA = output groups (one per SMSP)
     static constexpr int TN = (HV + NG - 1) / NG;        // hidden units per group (13)
@@ -27,10 +27,12 @@ struct VTile {
     static constexpr int TNP = pad4(TN);                 // padded group width in the weight image (16)
     static constexpr int WLD = NG * TNP;                 // weight row stride (64)
     static constexpr int QR = QR_;                       // pair rows per lane
-    static constexpr int ROWS = 32 * QR;                 // pair rows per tile
+    static constexpr int NH = NH_;                       // row blocks per CTA (each handled by its own NG warps)
+    static constexpr int WROWS = 32 * QR;                // pair rows per warp
+    static constexpr int ROWS = WROWS * NH;              // pair rows per tile
     static constexpr int RS0 = 2 * NG * GP + 4;
     static constexpr int RS = RS0 + ((RS0 / 4) % 2 == 0 ? 4 : 0);    // 116 for HV=50
-    static constexpr int THREADS = NG * 32;
+    static constexpr int THREADS = NG * NH * 32;
     static_assert(TN * NG >= HV, "groups cover the hidden units");
     static_assert((RS / 4) % 2 == 1, "row stride must be an odd multiple of 16 bytes (bank-conflict free)");
     static constexpr int valid_in_group(int g) { return HV - TN * g >= TN ? TN : (HV - TN * g > 0 ? HV - TN * g : 0); }
@@ -84,6 +86,48 @@ XW_DEV void tile_fma_unit(const float* wk, const fpair (&a)[QR], fpair (&acc)[QR
     }
 }
 
+// contraction over the NU input units of one group (tile positions tg.., weight rows wg..): fully
+// unrolled straight-line code so that the activation / weight loads of later units are scheduled
+// under the FFMA2 stream of earlier ones (no exposed LDS latency at loop boundaries)
+template <int HV, int QR, int NU>
+XW_DEV void tile_group_fma(const float* tg, const float* wg, fpair (&acc)[QR][VTile<HV, QR>::TN]) {
+    using VT = VTile<HV, QR>;
+#pragma unroll
+    for (int jp = 0; jp < NU / 2; ++jp) {
+        fpair a[QR], b[QR];
+#pragma unroll
+        for (int q = 0; q < QR; ++q) {
+            const f4 v = ld4(tg + q * 32 * VT::RS + 4 * jp);
+            a[q] = pack2(v.x, v.y); b[q] = pack2(v.z, v.w);
+        }
+        tile_fma_unit<HV, QR>(wg + (2 * jp) * VT::WLD, a, acc);
+        tile_fma_unit<HV, QR>(wg + (2 * jp + 1) * VT::WLD, b, acc);
+    }
+    if (NU & 1) {
+        fpair a[QR];
+#pragma unroll
+        for (int q = 0; q < QR; ++q) {
+            const f2 v = ld2(tg + q * 32 * VT::RS + 2 * (NU - 1));
+            a[q] = pack2(v.x, v.y);
+        }
+        tile_fma_unit<HV, QR>(wg + (NU - 1) * VT::WLD, a, acc);
+    }
+}
+
+// acc[q][o] += sum_k W[k-row][o] * T[row_q][k][:]  over all HV input units; `wimg` is the weight image
+// (row = input unit, columns = this warp's outputs), `trow` the lane's first pair row
+template <int HV, int QR>
+XW_DEV void tile_contract(const float* wimg, const float* trow, fpair (&acc)[QR][VTile<HV, QR>::TN]) {
+    using VT = VTile<HV, QR>;
+    constexpr int NFULL = HV / VT::TN;                 // groups with all TN units
+    constexpr int NLAST = HV - NFULL * VT::TN;         // units of the trailing partial group
+#pragma unroll 1
+    for (int gk = 0; gk < NFULL; ++gk)
+        tile_group_fma<HV, QR, VT::TN>(trow + 2 * VT::GP * gk, wimg + gk * VT::TN * VT::WLD, acc);
+    if (NLAST > 0)
+        tile_group_fma<HV, QR, (NLAST > 0 ? NLAST : 1)>(trow + 2 * VT::GP * NFULL, wimg + NFULL * VT::TN * VT::WLD, acc);
+}
+
 // one hidden layer on the pair-row tile:  acc[q][o] = (bias[o], BIAS1 ? bias[o] : 0) + sum_k W[o][k] * T[row_q][k][:]
 // BIAS1: add the bias to the second vector of the pair too (false for tangents)
 template <int HV, int QR, bool BIAS1>
@@ -98,37 +142,10 @@ XW_DEV void tile_hidden_layer(const float* sw, const float* tile, int grp, int l
         for (int o = 0; o < VT::TN; ++o) {
             const fpair bb = pack2(b[o], BIAS1 ? b[o] : 0.f);
 #pragma unroll
-            for (int q = 0; q < VT::QR; ++q) acc[q][o] = bb;
+            for (int q = 0; q < QR; ++q) acc[q][o] = bb;
         }
     }
-    const float* trow = tile + lane * VT::RS;
-    const float* wrow = sw + VT::WT + grp * VT::TNP;
-#pragma unroll 1
-    for (int gk = 0; gk < VT::NG; ++gk) {
-        const int nvalid = (HV - gk * VT::TN) < VT::TN ? (HV - gk * VT::TN) : VT::TN;
-        const float* tg = trow + 2 * VT::GP * gk;                    // group's position in the pair row
-        const float* wg = wrow + gk * VT::TN * VT::WLD;              // weight rows of its input units
-#pragma unroll 2
-        for (int jp = 0; jp < nvalid / 2; ++jp) {
-            fpair a[VT::QR], b[VT::QR];
-#pragma unroll
-            for (int q = 0; q < VT::QR; ++q) {
-                const f4 v = ld4(tg + q * 32 * VT::RS + 4 * jp);
-                a[q] = pack2(v.x, v.y); b[q] = pack2(v.z, v.w);
-            }
-            tile_fma_unit<HV, QR>(wg + (2 * jp) * VT::WLD, a, acc);
-            tile_fma_unit<HV, QR>(wg + (2 * jp + 1) * VT::WLD, b, acc);
-        }
-        if (nvalid & 1) {
-            fpair a[VT::QR];
-#pragma unroll
-            for (int q = 0; q < VT::QR; ++q) {
-                const f2 v = ld2(tg + q * 32 * VT::RS + 2 * (nvalid - 1));
-                a[q] = pack2(v.x, v.y);
-            }
-            tile_fma_unit<HV, QR>(wg + (nvalid - 1) * VT::WLD, a, acc);
-        }
-    }
+    tile_contract<HV, QR>(sw + VT::WT + grp * VT::TNP, tile + lane * VT::RS, acc);
 }
 
 // store relu(value) and the masked tangent of a layer's pre-activations back into the tile
@@ -171,9 +188,13 @@ struct VtileFwdArgs {
     double* sums; float* cot_u; float* cot_v;
 };
 
-template <int HV, int QR>
-XW_GLOBAL void k_vnet_tile_fwd(VtileFwdArgs a) {
-    using VT = VTile<HV, QR>;
+template <int HV, int QR, int NH>
+XW_GLOBAL void
+#ifndef XW_EMU
+__launch_bounds__(VTile<HV, QR, NH>::THREADS, (NH > 1 ? 2 : 1))
+#endif
+k_vnet_tile_fwd(VtileFwdArgs a) {
+    using VT = VTile<HV, QR, NH>;
     XW_DYN_SMEM(smem_raw);
     const int C = a.d + 1, XLD = VT::xin_ld(C);
     float* sw = reinterpret_cast<float*>(smem_raw);
@@ -182,13 +203,22 @@ XW_GLOBAL void k_vnet_tile_fwd(VtileFwdArgs a) {
     float* redv = xin + VT::ROWS * XLD;                           // [NG][ROWS][2]
     double* red = reinterpret_cast<double*>(redv + VT::NG * VT::ROWS * 2);
     stage_theta_v_tile<HV, QR>(sw, a.theta, a.d, a.Hvr);
-    const int lane = XW_TID & 31, grp = XW_TID >> 5;
+    const int lane = XW_TID & 31, grp = (XW_TID >> 5) % VT::NG, rbase = ((XW_TID >> 5) / VT::NG) * VT::WROWS;
+    float* tile_w = tile + rbase * VT::RS;                      // this warp's block of pair rows
     const long long npts = (long long)a.n * a.L;
     const long long ntiles = (npts + VT::ROWS - 1) / VT::ROWS;
     const int L = a.L;
     int* rown = reinterpret_cast<int*>(red + 4 * 32);            // [ROWS] path index of each row (-1: past the end)
     int* rowl = rown + VT::ROWS;                                  // [ROWS] time index
     double accs[4] = {0.0, 0.0, 0.0, 0.0};
+#if !defined(XW_EMU) && defined(XW_PHASE_SKEW)
+    // co-resident CTAs run identical phases (FMA-heavy layer, then store/barrier): skew the second
+    // resident set by about half a layer so that one CTA's epilogue overlaps the other's FMA phase
+    if (XW_BID >= (XW_GDIM >> 1)) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < XW_PHASE_SKEW) {}
+    }
+#endif
     float wz[VT::TN], wi0[VT::TN];
     load_row<VT::TN>(sw + VT::WZ + grp * VT::TNP, wz);
     load_row<VT::TN>(sw + VT::WIT + grp * VT::TNP, wi0);          // dh_0/dt = Wi[:, 0]
@@ -229,7 +259,7 @@ XW_GLOBAL void k_vnet_tile_fwd(VtileFwdArgs a) {
                 load_row<VT::TN>(wrow + c * VT::WLD, w);
 #pragma unroll
                 for (int q = 0; q < VT::QR; ++q) {
-                    const float xv = xin[(lane + 32 * q) * XLD + c];
+                    const float xv = xin[(rbase + lane + 32 * q) * XLD + c];
 #pragma unroll
                     for (int o = 0; o < VT::TN; ++o) h0[q][o] = fmaf(xv, w[o], h0[q][o]);
                 }
@@ -241,9 +271,9 @@ XW_GLOBAL void k_vnet_tile_fwd(VtileFwdArgs a) {
         }
         // ---- hidden layers ---------------------------------------------------------------------
         for (int layer = 0; layer < a.nv; ++layer) {
-            tile_store_relu_tangent<HV, QR>(tile, grp, lane, acc);
+            tile_store_relu_tangent<HV, QR>(tile_w, grp, lane, acc);
             XW_SYNCTHREADS();
-            tile_hidden_layer<HV, QR, false>(sw, tile, grp, lane, acc);
+            tile_hidden_layer<HV, QR, false>(sw, tile_w, grp, lane, acc);
             XW_SYNCTHREADS();
         }
         // ---- tanh + output layer: partial dot products of this warp's outputs -------------------
@@ -259,7 +289,7 @@ XW_GLOBAL void k_vnet_tile_fwd(VtileFwdArgs a) {
                 pt = fmaf(wz[o] * (1.f - y * y), ht, pt);
             }
             f2 out; out.x = pv; out.y = pt;
-            *reinterpret_cast<f2*>(redv + (grp * VT::ROWS + lane + 32 * q) * 2) = out;
+            *reinterpret_cast<f2*>(redv + (grp * VT::ROWS + rbase + lane + 32 * q) * 2) = out;
         }
         XW_SYNCTHREADS();
         // ---- per-point weak-form terms (one thread per row) ------------------------------------
@@ -581,34 +611,7 @@ XW_GLOBAL void k_vnet_tile_bwd(VtileBwdArgs a) {
                 for (int q = 0; q < QR; ++q)
 #pragma unroll
                     for (int o = 0; o < TN; ++o) acc[q][o] = pack2(0.f, 0.f);
-                const float* trow = tileD + lane * VT::RS;
-                const float* wrow = swr + grp * VT::TNP;
-#pragma unroll 1
-                for (int gk = 0; gk < VT::NG; ++gk) {
-                    const int nvalid = (HV - gk * TN) < TN ? (HV - gk * TN) : TN;
-                    const float* tg = trow + 2 * VT::GP * gk;
-                    const float* wg = wrow + gk * TN * VT::WLD;
-#pragma unroll 2
-                    for (int jp = 0; jp < nvalid / 2; ++jp) {
-                        fpair aa[QR], bb[QR];
-#pragma unroll
-                        for (int q = 0; q < QR; ++q) {
-                            const f4 v = ld4(tg + q * 32 * VT::RS + 4 * jp);
-                            aa[q] = pack2(v.x, v.y); bb[q] = pack2(v.z, v.w);
-                        }
-                        tile_fma_unit<HV, QR>(wg + (2 * jp) * VT::WLD, aa, acc);
-                        tile_fma_unit<HV, QR>(wg + (2 * jp + 1) * VT::WLD, bb, acc);
-                    }
-                    if (nvalid & 1) {
-                        fpair aa[QR];
-#pragma unroll
-                        for (int q = 0; q < QR; ++q) {
-                            const f2 v = ld2(tg + q * 32 * VT::RS + 2 * (nvalid - 1));
-                            aa[q] = pack2(v.x, v.y);
-                        }
-                        tile_fma_unit<HV, QR>(wg + (nvalid - 1) * VT::WLD, aa, acc);
-                    }
-                }
+                tile_contract<HV, QR>(swr + grp * VT::TNP, tileD + lane * VT::RS, acc);
 #pragma unroll
                 for (int q = 0; q < QR; ++q)
 #pragma unroll
