@@ -62,11 +62,13 @@ def _loss_and_grads(s, dom, X, XV, BX, phase):
     return val, [q.grad.detach().clone() for q in net.parameters()]
 
 
-def test_mid_size_against_oracle_d20():
-    """d=20, N=2048 (more than one CTA per kernel, tail warps) vs the fp64 closed-form oracle"""
-    s, prob = _rand_case(20, 2048 + 37, 1024 + 5, 3)
+@pytest.mark.parametrize("d,N,Nb", [(20, 2048 + 37, 1024 + 5), (100, 300 + 7, 200 + 3)])
+def test_mid_size_against_oracle(d, N, Nb):
+    """d=20, N=2085 (several CTAs per kernel, ragged tail tiles) and d=100 (BASELINE configs[4]: V = 2^100,
+    float shape_param) vs the fp64 closed-form oracle"""
+    s, prob = _rand_case(d, N, Nb, 3)
     dom = s.new_domain()
-    pts = xw.Comb_loader(2048 + 37, 1024 + 5, dom, DEV)
+    pts = xw.Comb_loader(N, Nb, dom, DEV)
     X, XV, BX = pts[0]
     thu, thv = cf.theta_from_state([q.detach().cpu().numpy() for q in s.u_net.parameters()],
                                    [q.detach().cpu().numpy() for q in s.v_net.parameters()])
@@ -80,7 +82,7 @@ def test_mid_size_against_oracle_d20():
     for phase in ("u", "v"):
         o = cf.weak_form(thu, thv, Xc.numpy(), XVc.numpy(), BXc.numpy(), coef, cfg, phase)
         val, grads = _loss_and_grads(s, dom, X, XV, BX, phase)
-        assert abs(val.item() - o["loss_" + phase]) <= 1e-4 * abs(o["loss_" + phase])
+        assert abs(val.item() - o["loss_" + phase]) <= 1e-4 * abs(o["loss_" + phase]) + 1e-6
         assert abs(val.components["I"].item() - o["I"]) <= 1e-4 * abs(o["I"])
         for a, b in zip(grads, o["grads"]):
             assert G.rel(a.cpu().numpy(), b) < 1e-3
