@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -59,7 +61,15 @@ int check_launch(const char* name) {
 template <class K>
 int set_smem(K kern, size_t bytes, const char* name) {
     if (bytes <= 48 * 1024) return 0;
+    // remember the largest opt-in per kernel: no CUDA API call on the steady-state path (keeps the
+    // launch sequence capturable into a CUDA graph)
+    static std::map<const void*, size_t> done;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = done[(const void*)kern];
+    if (have >= bytes) return 0;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
     if (e != cudaSuccess) return fail("%s: cannot opt in to %zu bytes of shared memory: %s", name, bytes, cudaGetErrorString(e));
     return 0;
 }

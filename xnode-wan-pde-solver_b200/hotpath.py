@@ -183,6 +183,9 @@ class _Workspace:
         self.buf = {}
 
     def get(self, dev, nbytes):
+        if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            # a captured graph must own its scratch (the shared buffer may be re-grown later)
+            return torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         b = self.buf.get(dev)
         if b is None or b.numel() < nbytes:
             b = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)

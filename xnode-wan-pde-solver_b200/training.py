@@ -70,12 +70,19 @@ class NODE_WAN_solver:
     """weak adversarial training loop; constructor arguments as the reference (src/training.py:65-66)"""
 
     def __init__(self, params: dict, func_a, func_b, func_c, func_h, func_f, func_g, device, path, stop=None,
-                 func_u_sol=None, p: float = 1, log_json: bool = True):
+                 func_u_sol=None, p: float = 1, log_json: bool = True, use_cuda_graph: bool = False,
+                 sample_on_device: bool = False, collapsed_layout: bool = False):
         self.params = params
         self.func_a, self.func_b, self.func_c = func_a, func_b, func_c
         self.func_h, self.func_f, self.func_g = func_h, func_f, func_g
         self.device, self.path, self.stop, self.func_u_sol, self.p = device, path, stop, func_u_sol, p
         self.log_json = log_json
+        self.use_cuda_graph = use_cuda_graph and torch.device(device).type == "cuda"
+        self._graphs = None
+        # extensions over the reference: draw the samples on the GPU (same distributions, different RNG
+        # stream) and keep them in the collapsed layout (times[L] + x[N,d]); both default to the
+        # reference behaviour (CPU sampling, repeated [N,L,C] tensors)
+        self.sample_on_device, self.collapsed_layout = sample_on_device, collapsed_layout
         it = iter(params.items())                       # positional split, as the reference
         self.config = dict(itertools.islice(it, 13))
         self.setup = dict(itertools.islice(it, 7))
@@ -93,18 +100,24 @@ class NODE_WAN_solver:
         self.v_net = torch.nn.DataParallel(discriminator(self.config, self.setup), device_ids=ids).to(device)
         self.u_net.apply(init_weights)
         self.v_net.apply(init_weights)
-        self.optimizer_u = torch.optim.Adam(self.u_net.parameters(), lr=self.config['u_rate'])
-        self.optimizer_v = torch.optim.Adam(self.v_net.parameters(), lr=self.config['v_rate'])
+        cap = self.use_cuda_graph        # step counters on the device so that Adam can live inside a CUDA graph
+        self.optimizer_u = torch.optim.Adam(self.u_net.parameters(), lr=self.config['u_rate'], capturable=cap)
+        self.optimizer_v = torch.optim.Adam(self.v_net.parameters(), lr=self.config['v_rate'], capturable=cap)
         # one process per GPU: N_r / N_b are GLOBAL counts, every rank samples its own shard; identical
         # seeds give identical initial weights, all-reduced sums/gradients keep the replicas identical
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self._warm = 0                   # completed eager iterations (the first one warms up before graph capture)
         self.best_l = float('inf')
         self.av_l = 0
         self.history = {"loss_u": [], "loss_v": [], "L2": [], "time": []}
 
     def new_domain(self, **kw):
         s = self.setup
+        if getattr(self, "sample_on_device", False):
+            kw.setdefault("sample_device", self.device)
+        if getattr(self, "collapsed_layout", False):
+            kw.setdefault("collapsed", True)
         dom = self.domain(s['shape_param'], s['dim'], s['T0'], s['T'], s['N_t'], **kw)
         if getattr(self, "world", 1) > 1:          # the time grid must be the same on every rank
             t = dom.times.to(self.device)
@@ -136,6 +149,60 @@ class NODE_WAN_solver:
             val = Loss.v(prediction_u, prediction_v, datau, datav)
             val.backward()
             self.optimizer_v.step()
+        # hand back a detached scalar: keeping the autograd graph alive would pin the parameters'
+        # AccumulateGrad nodes to the stream of this call (and break later CUDA-graph capture)
+        out = val.detach()
+        out.components = val.components
+        return out
+
+    # ------------------------------------------------------------------ CUDA-graph replay of a sub-step
+    def _capture(self, domain, batch):
+        """record one u-step and one v-step (coefficient evaluation + fused loss + backward + Adam)
+        on static copies of the sample; later samples are copied into the static buffers and the
+        graphs replayed: one launch per sub-step instead of ~150 (matters at the shipped N=4000,
+        where a sub-step is host-bound)."""
+        static = tuple(t.clone() for t in batch)
+        for t, src in zip(static, batch):
+            t._xw_start = getattr(src, "_xw_start", None)
+        graphs, outs = {}, {}
+        for phase in ("u", "v"):
+            g = torch.cuda.CUDAGraph()
+            opt = self.optimizer_u if phase == "u" else self.optimizer_v
+            with torch.cuda.graph(g):
+                opt.zero_grad(set_to_none=True)
+                outs[phase] = self._step(phase, domain, static)
+            graphs[phase] = g
+        self._graphs = dict(static=static, graphs=graphs, outs=outs)
+
+    def _graph_step(self, phase, batch):
+        st = self._graphs["static"]
+        if batch is not self._graphs.get("loaded"):
+            for dst, src in zip(st, batch):
+                if hasattr(dst, "times"):
+                    dst.times.copy_(src.times, non_blocking=True)
+                    dst.x.copy_(src.x, non_blocking=True)
+                else:
+                    dst.copy_(src, non_blocking=True)
+            self._graphs["loaded"] = batch
+        self._graphs["graphs"][phase].replay()
+        self._last_losses = [self._graphs["outs"][phase]]
+        return self._graphs["outs"][phase]
+
+    def sub_step(self, phase, domain, points):
+        """one u- or v- sub-iteration over every batch of `points` (zero_grad once, a step per batch,
+        as the reference: src/training.py:127-138 / :152-162); returns the last loss tensor"""
+        single = not isinstance(points.interioru, list)
+        if self.use_cuda_graph and single and self._graphs is not None:
+            return self._graph_step(phase, points[0])
+        (self.optimizer_u if phase == "u" else self.optimizer_v).zero_grad()
+        val = None
+        self._last_losses = []
+        for batch in points:
+            val = self._step(phase, domain, batch)
+            self._last_losses.append(val)
+        if self.use_cuda_graph and single and self._graphs is None and self._warm >= 1:
+            torch.cuda.synchronize()
+            self._capture(domain, points[0])
         return val
 
     def train_iteration(self, domain, points):
@@ -144,13 +211,10 @@ class NODE_WAN_solver:
         (loss_u, loss_v) tensors; nothing here synchronises the host."""
         loss_u = loss_v = None
         for _ in range(self.n1):
-            self.optimizer_u.zero_grad()
-            for batch in points:
-                loss_u = self._step("u", domain, batch)
+            loss_u = self.sub_step("u", domain, points)
         for _ in range(self.n2):
-            self.optimizer_v.zero_grad()
-            for batch in points:
-                loss_v = self._step("v", domain, batch)
+            loss_v = self.sub_step("v", domain, points)
+        self._warm += 1
         return loss_u, loss_v
 
     def train(self, report: bool = False, report_it: int = 10, show_plt: bool = False, max_seconds=None):
@@ -163,11 +227,8 @@ class NODE_WAN_solver:
             n_r, n_b = self.local_counts()
             points = Comb_loader(n_r, n_b, domain, self.device)
             for i in range(self.n1):
-                self.av_l = 0
-                self.optimizer_u.zero_grad()
-                for batch in points:
-                    loss_u = self._step("u", domain, batch)
-                    self.av_l += loss_u.item()
+                loss_u = self.sub_step("u", domain, points)
+                self.av_l = sum(v.item() for v in self._last_losses)
                 past_losses.append(self.av_l)
                 if self.log_json:
                     with open('losses_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
@@ -182,9 +243,8 @@ class NODE_WAN_solver:
                         torch.save(self.u_net.state_dict(), 'best_model_weights_NODE.pth')
                     self.best_l = self.av_l
             for j in range(self.n2):
-                self.optimizer_v.zero_grad()
-                for batch in points:
-                    loss_v = self._step("v", domain, batch)
+                loss_v = self.sub_step("v", domain, points)
+            self._warm += 1
             L2 = None
             if self.func_u_sol is not None:
                 fresh = Comb_loader(n_r, n_b, domain, self.device)
