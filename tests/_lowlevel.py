@@ -114,13 +114,25 @@ def run_case(lib, be, case, coef_a=None, coef_b=None):
     ws = be.zeros(wsb, np.uint8)
     sums = be.zeros(L_.NSUMS, np.float64)
     cot_u, cot_v, u_out = be.zeros(N * L), be.zeros(N * L), be.zeros(N * L)
+    vcache = be.zeros(lib.cdll.xw_vcache_floats(C.byref(dims), N, L))
     lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), be.ptr(thu), be.ptr(thv),
              be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L, C.byref(pts), be.ptr(h), be.ptr(gh), be.ptr(f), N,
-             be.ptr(sums), be.ptr(cot_u), be.ptr(cot_v), be.ptr(u_out), be.ptr(ws), wsb, be.stream, be.ptr(s0))
+             be.ptr(sums), be.ptr(cot_u), be.ptr(cot_v), be.ptr(u_out), be.ptr(ws), wsb, be.stream, be.ptr(s0),
+             be.ptr(vcache), 1)
     gu = be.zeros(Pu)
     lib.call("xw_boundary_u", C.byref(dims), be.ptr(thu), be.ptr_off(BXd, 1), Lb * Cc, be.ptr(times_b), Lb,
              be.ptr(sb), be.ptr(g), Nb, alpha / (Nb * Lb), be.ptr(sums), be.ptr(gu), 0, be.ptr(ws), wsb, be.stream)
     be.sync()
+    # second evaluation from the test-function cache (mode 2) must reproduce the sums and the seeds
+    sums2 = be.zeros(L_.NSUMS, np.float64)
+    cu2, cv2 = be.zeros(N * L), be.zeros(N * L)
+    lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), be.ptr(thu), be.ptr(thv),
+             be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L, C.byref(pts), be.ptr(h), be.ptr(gh), be.ptr(f), N,
+             be.ptr(sums2), be.ptr(cu2), be.ptr(cv2), None, be.ptr(ws), wsb, be.stream, be.ptr(s0), be.ptr(vcache), 2)
+    be.sync()
+    s_a, s_b = be.host(sums)[:5].copy(), be.host(sums2)[:5].copy()
+    assert np.allclose(s_a, s_b, rtol=1e-6, atol=1e-6 * np.abs(s_a).max()), (s_a, s_b)
+    assert np.array_equal(be.host(cot_u), be.host(cu2)) and np.array_equal(be.host(cot_v), be.host(cv2))
     s = be.host(sums).copy()
     I = V / N * s[0] - V / (N * L) * (s[1] - s[2])
     S = V * s[3] / (N * L)

@@ -189,3 +189,22 @@ def test_train_iteration_runs_and_updates_both_nets(emu):
     assert torch.isfinite(lu) and torch.isfinite(lv)
     after = list(s.u_net.parameters()) + list(s.v_net.parameters())
     assert all(not torch.equal(a, b) for a, b in zip(before, after))
+
+
+def test_test_function_cache_gives_the_same_training_step(emu):
+    """2nd u-step and the v-step of an iteration reuse the cached v-net values (same sample, same
+    theta_v): the parameters after one full iteration must equal those of the uncached path"""
+    case = G.load("cube_d3_small_nets")
+    outs = []
+    for reuse in (True, False):
+        s, _ = make_solver(case)
+        s.reuse_v = reuse
+        torch.manual_seed(0)
+        dom = s.new_domain()
+        pts = xw.Comb_loader(24, 16, dom, "cpu")
+        calls0 = dict(xw.hotpath.CALLS)
+        s.train_iteration(dom, pts)
+        s.train_iteration(dom, xw.Comb_loader(24, 16, dom, "cpu"))
+        outs.append([q.detach().clone() for q in list(s.u_net.parameters()) + list(s.v_net.parameters())])
+    for a, b in zip(*outs):
+        assert G.rel(a.numpy(), b.numpy()) < 1e-5

@@ -85,7 +85,7 @@ def main():
         lib.call("xw_vnet_eval", C.byref(dims), p(thv), C.byref(pts), N, L, p(v_out), st)
     def ifwd():
         lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), p(thu), p(thv), p(x), d, p(times), L,
-                 C.byref(pts), p(h), p(gh), p(f), N, p(sums), p(cot_u), p(cot_v), p(u_out), p(ws), wsb, st, None)
+                 C.byref(pts), p(h), p(gh), p(f), N, p(sums), p(cot_u), p(cot_v), p(u_out), p(ws), wsb, st, None, None, 0)
     def bdry():
         lib.call("xw_boundary_u", C.byref(dims), p(thu), p(xb), d, p(times), L, p(sb), p(g), Nb, 1e-3, p(sums), p(gu), 0,
                  p(ws), wsb, st)

@@ -51,7 +51,8 @@ _SIGS = {
     "xw_vnet_eval": (C.c_int, [C.POINTER(Dims), _P, C.POINTER(Points), C.c_int, C.c_int, _P, _P]),
     "xw_interior_forward": (C.c_int, [C.POINTER(Dims), C.POINTER(Domain), C.POINTER(Coef), _P, _P, _P, C.c_longlong,
                                       _P, C.c_int, C.POINTER(Points), _P, _P, _P, C.c_int, _P, _P, _P, _P, _P,
-                                      C.c_size_t, _P, _P]),
+                                      C.c_size_t, _P, _P, _P, C.c_int]),
+    "xw_vcache_floats": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
     "xw_boundary_u": (C.c_int, [C.POINTER(Dims), _P, _P, C.c_longlong, _P, C.c_int, _P, _P, C.c_int, C.c_double, _P,
                                 _P, C.c_int, _P, C.c_size_t, _P]),
     "xw_interior_backward_u": (C.c_int, [C.POINTER(Dims), _P, _P, C.c_longlong, _P, C.c_int, _P, _P, C.c_int, _P, _P,
@@ -74,7 +75,10 @@ class XwLib:
         self.path = path
         self.cdll = C.CDLL(path)
         for name, (res, args) in _SIGS.items():
-            fn = getattr(self.cdll, name)
+            try:
+                fn = getattr(self.cdll, name)
+            except AttributeError:
+                raise XwError("%s does not export %s: stale build, rebuild it (python __graft_entry__.py)" % (path, name))
             fn.restype = res
             fn.argtypes = args
         if self.cdll.xw_abi_version() != 1:

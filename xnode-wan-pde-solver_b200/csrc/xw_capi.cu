@@ -240,6 +240,7 @@ const char* xw_last_error(void) { return g_err; }
 
 int xw_theta_u_size(const xw_dims* m) { return m ? xw::ULayout(m->d, m->H, m->hh).size : -1; }
 int xw_theta_v_size(const xw_dims* m) { return m ? xw::VLayout(m->d, m->Hv).size : -1; }
+size_t xw_vcache_floats(const xw_dims* m, int n, int L) { return m ? (size_t)4 * n * L + (size_t)n * m->d : 0; }
 
 size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
     if (check_dims(m) || !device() || n < 1 || L < 1) return 0;
@@ -289,7 +290,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
                         const float* theta_v, const float* x, long long x_sn, const float* times, int L,
                         const xw_points* xv, const float* h, const float* grad_h, const float* f, int n,
                         double* sums, float* cot_u, float* cot_v, float* u_out, void* workspace,
-                        size_t workspace_bytes, void* stream, const float* s0) {
+                        size_t workspace_bytes, void* stream, const float* s0, float* vcache, int vcache_mode) {
     if (check_dims(m)) return 1;
     if (!device()) return fail("no CUDA device");
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
@@ -297,6 +298,8 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         !sums || !cot_u || !cot_v || !workspace)
         return fail("NULL pointer argument");
     if (dom->kind < 0 || dom->kind > 2) return fail("unknown domain kind %d", dom->kind);
+    if (vcache_mode < 0 || vcache_mode > 2 || (vcache_mode != 0 && !vcache)) return fail("bad vcache arguments");
+    float* gcache = vcache ? vcache + (size_t)4 * n * L : nullptr;
     const int gf = grid_for(n, kBlkFwd, 8);
     const size_t du_b = align_up((size_t)n * m->d * 4, 256), u_b = align_up((size_t)n * L * 4, 256);
     const size_t hist_b = align_up((size_t)L * kH * gf * kBlkFwd * 4, 256);
@@ -317,6 +320,15 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     b.dom_kind = dom->kind; b.dp0 = dom->p0; b.dp1 = dom->p1; b.dp2 = dom->p2;
     b.c0 = coef->c0; b.c1 = coef->c1; b.ca = coef->a; b.cb = coef->b;
     b.u = ubuf; b.du = du; b.h = h; b.f = f; b.sums = sums; b.cot_u = cot_u; b.cot_v = cot_v; b.v_out = nullptr;
+    b.gcache = vcache_mode == 1 ? gcache : nullptr;
+    if (vcache_mode == 2) {          // sample and theta_v unchanged: reuse the cached test-function values
+        xw::CombineArgs q{};
+        q.d = m->d; q.n = n; q.L = L; q.c0 = coef->c0; q.c1 = coef->c1; q.ca = coef->a; q.cb = coef->b;
+        q.vcache = vcache; q.gcache = gcache; q.u = ubuf; q.du = du; q.h = h; q.f = f;
+        q.sums = sums; q.cot_u = cot_u; q.cot_v = cot_v;
+        XW_LAUNCH(xw::k_weak_combine, grid_for((long long)n * L, 256, 8), 256, 4 * 32 * 8, stream, q);
+        return XW_CHECK_LAUNCH("k_weak_combine");
+    }
     const size_t smem = smem_vnet_fwd(m->d);
     if (use_point_kernels()) {
         if (XW_SET_SMEM((xw::k_vnet_points<kHV, 1>), smem)) return 1;
@@ -331,6 +343,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
     t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
     t.c0 = coef->c0; t.c1 = coef->c1; t.u = ubuf; t.h = h; t.f = f; t.sums = sums; t.cot_u = cot_u; t.cot_v = cot_v;
+    t.vcache = vcache_mode == 1 ? vcache : nullptr;
     using VT = xw::VTile<kHV, kQR, kNH>;
     const size_t tsmem = smem_vtile_fwd(m->d);
     if (tsmem > device()->smem_optin) return fail("tiled v-net forward needs %zu B shared memory (> %zu): dim too large", tsmem, device()->smem_optin);

@@ -244,6 +244,7 @@ struct VnetFwdArgs {
     float c0, c1; const float* ca; const float* cb;
     const float* u; const float* du; const float* h; const float* f;
     double* sums; float* cot_u; float* cot_v; float* v_out;
+    float* gcache;           // MODE 2, optional: [n*d] grad_x phi at time-row 0 (for k_weak_combine)
 };
 
 template <int HV, int MODE>
@@ -279,6 +280,7 @@ XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
             float s31 = 0.f;
             for (int i = 0; i < d; ++i) {
                 const float dphi_i = fmaf(W.w, vnet_input_grad<HV>(sv, 1 + i, dl), v * domain_dw_x(W, i, xp));
+                if (a.gcache) a.gcache[n * d + i] = dphi_i;
                 float q;
                 if (a.ca) {
                     q = 0.f;
@@ -775,3 +777,62 @@ XW_GLOBAL void k_reduce_partials(const float* gpart, int nblocks, int P, float* 
 }  // namespace xw
 
 #include "xw_vnet_tile.cuh"
+
+namespace xw {
+
+// =============================================================================================
+// weak-form sums from the CACHED test-function values: when the sample and theta_v are unchanged
+// (2nd u-step and the v-step of one outer iteration, src/training.py:125-162) only u, du change, so
+// the v net need not be evaluated again.  One thread per point; time-row-0 threads add the
+// a grad(phi).du + b.du phi term from the cached grad_x phi.
+// =============================================================================================
+struct CombineArgs {
+    int d, n, L;
+    float c0, c1; const float* ca; const float* cb;
+    const float* vcache; const float* gcache;
+    const float* u; const float* du; const float* h; const float* f;
+    double* sums; float* cot_u; float* cot_v;
+};
+
+XW_GLOBAL void k_weak_combine(CombineArgs a) {
+    XW_DYN_SMEM(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);
+    const long long nthr = (long long)XW_GDIM * XW_BDIM;
+    const long long npts = (long long)a.n * a.L;
+    const int L = a.L, d = a.d;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long p = (long long)XW_BID * XW_BDIM + XW_TID; p < npts; p += nthr) {
+        const long long n = p / L;
+        const int l = (int)(p - n * L);
+        const f4 c = ld4(a.vcache + 4 * p);
+        float cu, cv;
+        weak_point_terms(c.x, c.y, c.z, c.w, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, a.c0, a.c1, acc, cu, cv);
+        a.cot_u[p] = cu;
+        a.cot_v[p] = cv;
+        if (l == 0) {
+            const float* dun = a.du + n * d;
+            const float* gp = a.gcache + n * d;
+            float s31 = 0.f;
+            for (int i = 0; i < d; ++i) {
+                float q;
+                if (a.ca) {
+                    q = 0.f;
+                    for (int j = 0; j < d; ++j) q = fmaf(a.ca[i * d + j], dun[j], q);
+                } else {
+                    q = dun[i];
+                }
+                s31 = fmaf(gp[i], q, s31);
+            }
+            if (a.cb) {
+                float bq = 0.f;
+                for (int j = 0; j < d; ++j) bq = fmaf(a.cb[j], dun[j], bq);
+                s31 = fmaf(c.x * c.z, bq, s31);
+            }
+            acc[2] += (double)s31;
+        }
+    }
+    const int idx[4] = {0, 1, 2, 3};
+    block_sum_to_global<4>(acc, red, a.sums, idx);
+}
+
+}  // namespace xw

@@ -186,7 +186,28 @@ struct VtileFwdArgs {
     float c0, c1;
     const float* u; const float* h; const float* f;
     double* sums; float* cot_u; float* cot_v;
+    float* vcache;           // optional [n*L] x (v, dv/dt, w, dw/dt): lets later sub-steps on the same sample
+                             // and the same theta_v skip the v net entirely (k_weak_combine)
 };
+
+// the weak-form integrands of one point from (v, dv/dt, w, dw/dt) and (u, f, h): src/loss.py:64-73
+// without the time-row-0 gradient term; accumulates into acc[0..3], writes the cotangent seeds
+XW_DEV void weak_point_terms(float v, float dv_t, float w, float dw_t, float u, float fv, float hn, int l, int L,
+                             float c0, float c1, double (&acc)[4], float& cu, float& cv) {
+    const float phi = v * w;
+    const float dphi0 = fmaf(w, dv_t, v * dw_t);
+    const float cu_ = fmaf(c1, u, c0);
+    const float A = cu_ * u, Ap = fmaf(c1, u, cu_);
+    float s1 = 0.f;
+    cu = Ap * phi;
+    cv = w * (A + fv);
+    if (l == L - 1) { s1 = fmaf(u, v, s1); cu = fmaf((float)L, v, cu); cv = fmaf((float)L, u, cv); }
+    if (l == 0) { s1 = fmaf(-hn, v, s1); cv = fmaf(-(float)L, hn, cv); }
+    acc[0] += (double)s1;
+    acc[1] += (double)(u * dphi0);
+    acc[2] += (double)((A + fv) * phi);
+    acc[3] += (double)(v * v);
+}
 
 template <int HV, int QR, int NH>
 XW_GLOBAL void
@@ -306,25 +327,11 @@ k_vnet_tile_fwd(VtileFwdArgs a) {
                 const int n = rown[r], l = rowl[r];
                 const float* xr = xin + r * XLD;
                 const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, xr[0], xr + 1, a.d);
-                const float phi = v * W.w;
-                const float dphi0 = fmaf(W.w, dv_t, v * W.dw_t);
-                const float u = a.u[p], fv = a.f[p];
-                const float cu_ = fmaf(a.c1, u, a.c0);
-                const float A = cu_ * u, Ap = fmaf(a.c1, u, cu_);
-                float s1 = 0.f;
-                float cu = Ap * phi, cv = W.w * (A + fv);
-                if (l == L - 1) { s1 = fmaf(u, v, s1); cu = fmaf((float)L, v, cu); cv = fmaf((float)L, u, cv); }
-                if (l == 0) {
-                    const float hn = a.h[n];
-                    s1 = fmaf(-hn, v, s1);
-                    cv = fmaf(-(float)L, hn, cv);
-                }
+                float cu, cv;
+                weak_point_terms(v, dv_t, W.w, W.dw_t, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, a.c0, a.c1, accs, cu, cv);
                 a.cot_u[p] = cu;
                 a.cot_v[p] = cv;
-                accs[0] += (double)s1;
-                accs[1] += (double)(u * dphi0);
-                accs[2] += (double)((A + fv) * phi);
-                accs[3] += (double)(v * v);
+                if (a.vcache) { f4 cch; cch.x = v; cch.y = dv_t; cch.z = W.w; cch.w = W.dw_t; st4(a.vcache + 4 * p, cch); }
             }
         }
         XW_SYNCTHREADS();

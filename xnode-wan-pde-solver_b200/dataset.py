@@ -73,6 +73,9 @@ class Hypercube:
         return (self.top - self.bot) ** self.dim * (self.T - self.T0)
 
 
+_LOADER_UID = [0]
+
+
 class Comb_loader:
     """(datau, datav, bdata) batches of equally long paths (reference src/dataset.py:293-322).
     For a tensor-valued domain (the cube) there is one batch; the test-function points are an
@@ -80,6 +83,8 @@ class Comb_loader:
 
     def __init__(self, N_r: int, N_b: int, shape, device):
         self.N_r, self.N_b, self.shape, self.device = N_r, N_b, shape, device
+        _LOADER_UID[0] += 1
+        self.uid = _LOADER_UID[0]          # identifies the sample (the solver's test-function cache keys on it)
         interior = shape.interior(N_r)
         if isinstance(interior, list):
             self.interioru = interior
@@ -96,6 +101,8 @@ class Comb_loader:
         """wrap an existing sample (e.g. pinned host tensors / CollapsedPaths); the host->device copy
         happens on first access, as in the reference's __getitem__ (src/dataset.py:321)"""
         self = cls.__new__(cls)
+        _LOADER_UID[0] += 1
+        self.uid = _LOADER_UID[0]
         self.N_r, self.N_b = interioru.shape[0], boundary.shape[0]
         self.shape, self.device = None, device
         self.interioru, self.interiorv, self.boundary = interioru, interiorv, boundary

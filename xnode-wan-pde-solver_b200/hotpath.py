@@ -218,8 +218,17 @@ def _allreduce(t, group):
         torch.distributed.all_reduce(t, group=group)
 
 
-def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, alpha, boundary_grad=None):
-    """launches the forward kernels; returns (sums[8] fp64 device tensor, cot_u, cot_v)"""
+def vcache_buffer(lib, spec, batch, dev):
+    """device buffer for the test-function cache of xw_interior_forward (see include/xnode_wan_b200.h)"""
+    dims = spec.c()
+    n = lib.cdll.xw_vcache_floats(C.byref(dims), batch.N, batch.L)
+    return torch.empty(int(n), dtype=torch.float32, device=dev)
+
+
+def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, alpha, boundary_grad=None,
+                 vcache=None, vmode=0):
+    """launches the forward kernels; returns (sums[8] fp64 device tensor, cot_u, cot_v).
+    vcache/vmode: 0 none, 1 evaluate the v net and fill `vcache`, 2 reuse `vcache` (same sample, same theta_v)"""
     dev = theta_u.device
     dims = spec.c()
     st = _stream(dev)
@@ -233,7 +242,7 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
     _call(lib, "xw_interior_forward", dev, C.byref(dims), C.byref(cdom), C.byref(ccoef), _ptr(theta_u), _ptr(theta_v),
              C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), L, C.byref(pts),
              _ptr(batch.h), _ptr(batch.grad_h), _ptr(batch.f), N, _ptr(sums), _ptr(cot_u), _ptr(cot_v), None,
-             _ptr(ws), ws.numel(), st, _ptr(batch.s0))
+             _ptr(ws), ws.numel(), st, _ptr(batch.s0), _ptr(vcache) if vmode else None, int(vmode))
     if with_boundary:
         gscale = float(alpha) / (batch.Nb_glob * batch.Lb)
         _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
@@ -259,13 +268,14 @@ class WeakLoss(torch.autograd.Function):
     side effects of the two helper backward calls at src/loss.py:55,60 (`side_effect=True`)."""
 
     @staticmethod
-    def forward(ctx, phase, lib, spec, dom, coef, alpha, batch, group, side_effect, nu_params, *params):
+    def forward(ctx, phase, lib, spec, dom, coef, alpha, batch, group, side_effect, vcache, vmode, nu_params, *params):
         pu, pv = params[:nu_params], params[nu_params:]
         theta_u, theta_v = flatten_params(pu), flatten_params(pv)
         _check_dev(theta_u, "parameters")
         dev = theta_u.device
         gb = torch.zeros(theta_u.numel(), dtype=torch.float32, device=dev) if phase == "u" else None
-        sums, cot_u, cot_v = forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, phase == "u", alpha, gb)
+        sums, cot_u, cot_v = forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, phase == "u", alpha, gb,
+                                          vcache, vmode)
         _allreduce(sums, group)
         I, S, init, bdry, integ = loss_from_sums(sums, batch, dom.V, alpha)
         ctx.phase, ctx.lib, ctx.spec, ctx.dom, ctx.batch, ctx.group = phase, lib, spec, dom, batch, group
@@ -288,7 +298,7 @@ class WeakLoss(torch.autograd.Function):
         lib, spec, batch = ctx.lib, ctx.spec, ctx.batch
         dims = spec.c()
         nup = ctx.nu_params
-        none = (None,) * 10
+        none = (None,) * 12
         if ctx.phase == "u":
             theta_u, cot_u, k, gb = ctx.saved_tensors
             dev = theta_u.device
@@ -319,14 +329,15 @@ class WeakLoss(torch.autograd.Function):
         return none + (None,) * nup + tuple(gl)
 
 
-def weak_loss(phase, spec, dom, coef, alpha, batch, u_params, v_params, group=None, side_effect=True, lib=None):
+def weak_loss(phase, spec, dom, coef, alpha, batch, u_params, v_params, group=None, side_effect=True, lib=None,
+              vcache=None, vmode=0):
     """public functional entry: returns the scalar loss tensor (fp64) with autograd wired to the
     phase's own parameters.  `loss.components` is attached for logging (I, S, init, bdry)."""
     assert phase in ("u", "v")
     lib = lib or _lib.get()
     u_params, v_params = list(u_params), list(v_params)
-    out = WeakLoss.apply(phase, lib, spec, dom, coef, alpha, batch, group, side_effect, len(u_params),
-                         *(u_params + v_params))
+    out = WeakLoss.apply(phase, lib, spec, dom, coef, alpha, batch, group, side_effect, vcache, vmode,
+                         len(u_params), *(u_params + v_params))
     out.components = getattr(out.grad_fn, "components", None)
     return out
 

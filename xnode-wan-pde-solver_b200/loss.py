@@ -61,6 +61,7 @@ class loss:
         self.N_glob = None           # global path counts when the batch is one rank's shard
         self.Nb_glob = None
         self.side_effect = True      # reproduce the reference's helper-backward side effects
+        self.vcache = None           # (buffer or None, mode): test-function cache, managed by NODE_WAN_solver
         for nm, obj, cls in (("a", a, CoefA), ("b", b, CoefB), ("c", c, CoefC)):
             if not isinstance(obj, cls):
                 raise TypeError("coefficient %s must be a %s produced by func_eval (dense tensors of the reference "
@@ -118,9 +119,12 @@ class loss:
         batch = self._batch(u_mod, X, XV, border)
         spec = u_mod.spec(v_mod)
         dom = domain_spec(self.domain)
+        vbuf, vmode = self.vcache if self.vcache is not None else (None, 0)
+        if vmode and vbuf is None:
+            raise RuntimeError("vcache mode without a buffer")
         return hotpath.weak_loss(phase, spec, dom, self._coef(X.device), float(self.alpha), batch,
                                  u_mod.kernel_parameters(), v_mod.flat_parameters(), group=self.group,
-                                 side_effect=self.side_effect)
+                                 side_effect=self.side_effect, vcache=vbuf, vmode=vmode)
 
     # ------------------------------------------------------------------------------ reference API
     def u(self, y_output_u, y_output_v, u_net, X, XV, border):

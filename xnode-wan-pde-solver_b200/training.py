@@ -108,6 +108,8 @@ class NODE_WAN_solver:
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self._warm = 0                   # completed eager iterations (the first one warms up before graph capture)
+        self.reuse_v = True              # cache the test-function values across the sub-steps of one iteration
+        self._vc_buf, self._vc_key, self._theta_v_gen = None, None, 0
         self.best_l = float('inf')
         self.av_l = 0
         self.history = {"loss_u": [], "loss_v": [], "L2": [], "time": []}
@@ -132,7 +134,23 @@ class NODE_WAN_solver:
             raise RuntimeError("N_r and N_b must be divisible by the number of ranks")
         return self.setup['N_r'] // w, self.setup['N_b'] // w
 
-    def _step(self, phase, domain, batch):
+    def _vcache_plan(self, points):
+        """(buffer, mode) for the next sub-step on `points`: the test-function values depend only on
+        the sample and theta_v, both unchanged between the sub-steps of one outer iteration until a
+        v-step runs (src/training.py:125-162), so only the first sub-step evaluates the v net."""
+        if not self.reuse_v or isinstance(points.interioru, list):
+            return None, 0
+        key = (points.uid, self._theta_v_gen)
+        return self._vc_buf, (2 if self._vc_key == key else 1)
+
+    def _vcache_commit(self, phase, points):
+        if self.reuse_v and not isinstance(points.interioru, list):
+            if phase == "v":
+                self._theta_v_gen += 1          # theta_v just changed: cached values are stale
+            else:
+                self._vc_key = (points.uid, self._theta_v_gen)
+
+    def _step(self, phase, domain, batch, vplan=(None, 0)):
         datau, datav, bdata = batch
         prediction_v = self.v_net(datav)
         prediction_u = self.u_net(datau)
@@ -141,6 +159,14 @@ class NODE_WAN_solver:
         Loss = loss(self.config['alpha'], a, b, c, h, f, g, self.setup, domain, self.device)
         if self.world > 1:
             Loss.N_glob, Loss.Nb_glob = datau.shape[0] * self.world, bdata.shape[0] * self.world
+        vbuf, vmode = vplan
+        if vmode and vbuf is None:
+            um, vm = self.u_net.module, self.v_net.module
+            from . import hotpath as _hp
+            bt = _hp.Batch(N=datau.shape[0], L=datau.shape[1], d=self.setup['dim'], times=None, x=None, x_off=0, x_sn=0,
+                           xv=None, tv_off=0, tv_sn=0, tv_sl=0, xv_off=0, xv_sn=0, xv_sl=0)
+            vbuf = self._vc_buf = _hp.vcache_buffer(_hp._lib.get(), um.spec(vm), bt, datau.device)
+        Loss.vcache = (vbuf, vmode)
         if phase == "u":
             val = Loss.u(prediction_u, prediction_v, self.u_net, datau, datav, bdata)
             val.backward()
@@ -164,17 +190,22 @@ class NODE_WAN_solver:
         static = tuple(t.clone() for t in batch)
         for t, src in zip(static, batch):
             t._xw_start = getattr(src, "_xw_start", None)
-        graphs, outs = {}, {}
-        for phase in ("u", "v"):
+        self._graphs = dict(static=static, graphs={}, outs={}, domain=domain)
+
+    def _graph_for(self, phase, vmode):
+        key = (phase, vmode)
+        if key not in self._graphs["graphs"]:
             g = torch.cuda.CUDAGraph()
             opt = self.optimizer_u if phase == "u" else self.optimizer_v
+            torch.cuda.synchronize()
             with torch.cuda.graph(g):
                 opt.zero_grad(set_to_none=True)
-                outs[phase] = self._step(phase, domain, static)
-            graphs[phase] = g
-        self._graphs = dict(static=static, graphs=graphs, outs=outs)
+                self._graphs["outs"][key] = self._step(phase, self._graphs["domain"], self._graphs["static"],
+                                                       (self._vc_buf, vmode))
+            self._graphs["graphs"][key] = g
+        return key
 
-    def _graph_step(self, phase, batch):
+    def _graph_step(self, phase, batch, vmode):
         st = self._graphs["static"]
         if batch is not self._graphs.get("loaded"):
             for dst, src in zip(st, batch):
@@ -184,22 +215,27 @@ class NODE_WAN_solver:
                 else:
                     dst.copy_(src, non_blocking=True)
             self._graphs["loaded"] = batch
-        self._graphs["graphs"][phase].replay()
-        self._last_losses = [self._graphs["outs"][phase]]
-        return self._graphs["outs"][phase]
+        key = self._graph_for(phase, vmode)
+        self._graphs["graphs"][key].replay()
+        self._last_losses = [self._graphs["outs"][key]]
+        return self._graphs["outs"][key]
 
     def sub_step(self, phase, domain, points):
         """one u- or v- sub-iteration over every batch of `points` (zero_grad once, a step per batch,
         as the reference: src/training.py:127-138 / :152-162); returns the last loss tensor"""
         single = not isinstance(points.interioru, list)
+        vplan = self._vcache_plan(points)
         if self.use_cuda_graph and single and self._graphs is not None:
-            return self._graph_step(phase, points[0])
+            val = self._graph_step(phase, points[0], vplan[1])
+            self._vcache_commit(phase, points)
+            return val
         (self.optimizer_u if phase == "u" else self.optimizer_v).zero_grad()
         val = None
         self._last_losses = []
         for batch in points:
-            val = self._step(phase, domain, batch)
+            val = self._step(phase, domain, batch, vplan)
             self._last_losses.append(val)
+        self._vcache_commit(phase, points)
         if self.use_cuda_graph and single and self._graphs is None and self._warm >= 1:
             torch.cuda.synchronize()
             self._capture(domain, points[0])
