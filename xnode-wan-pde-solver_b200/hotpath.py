@@ -28,8 +28,15 @@ KERNELS_PER_CALL = {"xw_interior_forward": 2, "xw_boundary_u": 2, "xw_interior_b
                     "xw_interior_backward_v": 2, "xw_xnode_eval": 1, "xw_vnet_eval": 1}
 
 
+LAUNCHES = [0]                # kernels launched by this package (counted per C-ABI call)
+
+
 def _call(lib, name, dev, *args):
     CALLS[name] = CALLS.get(name, 0) + 1
+    k = KERNELS_PER_CALL[name]
+    if name == "xw_interior_forward":          # xnode_fwd + (row-0 kernel + tiled pass | combine from the cache)
+        k = 2 if args[-1] == 2 else 3
+    LAUNCHES[0] += k
     if PROFILE is not None and dev.type == "cuda":
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(dev))
