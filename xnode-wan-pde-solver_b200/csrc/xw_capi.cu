@@ -178,13 +178,61 @@ int ctas_per_sm_for(size_t smem, int cap) {
     return std::max(1, std::min(k, cap));
 }
 
+// Experiment kept behind a macro: XNODE weights in the constant bank instead of shared memory
+// (to take the warp-uniform weight reads off the LSU pipe).  Measured on B200 (r01): no gain --
+// ptxas turns the constant reads into LDC + register operands and hoists them (255 registers,
+// spills): xnode_eval 0.381 ms vs 0.390 ms, interior forward 7.46 ms vs 6.78 ms at 2^17 paths.
+bool use_const_weights() {
+#ifdef XW_ENABLE_CONST_W
+    const char* e = getenv("XW_XNODE_W");
+    return e && strcmp(e, "const") == 0;
+#else
+    return false;
+#endif
+}
+
+// stage theta_u into the constant bank (c_theta_u) in the USmem image layout
+int upload_u_image(const xw_dims* m, const float* theta_u, void* stream) {
+    using S = xw::USmem<kH, kHH>;
+    const size_t n = (size_t)S::size(m->d);
+    if (n > (size_t)xw::kConstUFloats) return fail("dim %d too large for the constant-bank weight image", m->d);
+#ifdef XW_EMU
+    static float img[xw::kConstUFloats];
+    XW_LAUNCH((xw::k_build_u_image<kH, kHH>), 1, 256, 0, stream, theta_u, m->d, m->H, m->hh, img);
+    memcpy(xw::c_theta_u, img, n * 4);
+    return 0;
+#else
+    static float* img = nullptr;
+    if (!img && cudaMalloc(&img, xw::kConstUFloats * 4) != cudaSuccess) return fail("cudaMalloc failed");
+    XW_LAUNCH((xw::k_build_u_image<kH, kHH>), 1, 256, 0, stream, theta_u, m->d, m->H, m->hh, img);
+    if (check_launch("k_build_u_image")) return 1;
+    cudaError_t e = cudaMemcpyToSymbolAsync(xw::c_theta_u, img, n * 4, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("cudaMemcpyToSymbolAsync: %s", cudaGetErrorString(e));
+    return 0;
+#endif
+}
+
+#ifdef XW_ENABLE_CONST_W
+#define XW_CONST_LAUNCH(SOLV)                                                               \
+    if (XW_SET_SMEM((k_xnode_fwd<kH, kHH, SOLV, MODE, WConst>), smem)) return 1;            \
+    XW_LAUNCH((k_xnode_fwd<kH, kHH, SOLV, MODE, WConst>), grid, kBlkFwd, smem, stream, a);
+#else
+#define XW_CONST_LAUNCH(SOLV)
+#endif
+
 template <int MODE>
 int launch_xnode_fwd(const xw_dims* m, const xw::XnodeFwdArgs& a, int grid, size_t smem, void* stream) {
     using namespace xw;
+    const bool cw = use_const_weights();
+    if (cw && upload_u_image(m, a.theta, stream)) return 1;
 #define XW_CASE(SOLV)                                                                       \
     case SOLV: {                                                                            \
-        if (XW_SET_SMEM((k_xnode_fwd<kH, kHH, SOLV, MODE>), smem)) return 1;                \
-        XW_LAUNCH((k_xnode_fwd<kH, kHH, SOLV, MODE>), grid, kBlkFwd, smem, stream, a);      \
+        if (cw) {                                                                           \
+            XW_CONST_LAUNCH(SOLV)                                                           \
+        } else {                                                                            \
+            if (XW_SET_SMEM((k_xnode_fwd<kH, kHH, SOLV, MODE, WSmem>), smem)) return 1;     \
+            XW_LAUNCH((k_xnode_fwd<kH, kHH, SOLV, MODE, WSmem>), grid, kBlkFwd, smem, stream, a); \
+        }                                                                                   \
         break;                                                                              \
     }
     switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }

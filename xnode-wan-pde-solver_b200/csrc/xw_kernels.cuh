@@ -50,25 +50,25 @@ struct XnodeFwdArgs {
     const float* hloss;          // func_h values used by loss.init (== s0 when the batch starts at T0)
 };
 
-template <int H, int HH>
-XW_DEV void hoist_ax(const float* sw, const float* XW_RESTRICT xp, int d, float (&ax)[HH]) {
+template <int H, int HH, class W>
+XW_DEV void hoist_ax(const W& sw, const float* XW_RESTRICT xp, int d, float (&ax)[HH]) {
     using S = USmem<H, HH>;
-    load_row<HH>(sw + S::BA, ax);
+    load_row<HH>(sw.at(S::BA), ax);
     for (int j = 0; j < d; ++j) {
         float w[HH];
-        load_row<HH>(sw + S::WXT + j * S::HHP, w);
+        load_row<HH>(sw.at(S::WXT + j * S::HHP), w);
         const float xj = xp[j];
 #pragma unroll
         for (int o = 0; o < HH; ++o) ax[o] = fmaf(w[o], xj, ax[o]);
     }
 }
 
-template <int H, int HH>
-XW_DEV float project_u(const float* sw, const float (&y)[H]) {
+template <int H, int HH, class W>
+XW_DEV float project_u(const W& sw, const float (&y)[H]) {
     using S = USmem<H, HH>;
     float wo[H];
-    load_row<H>(sw + S::WO, wo);
-    float u0 = sw[S::BO], u1 = 0.f;
+    load_row<H>(sw.at(S::WO), wo);
+    float u0 = *sw.at(S::BO), u1 = 0.f;
 #pragma unroll
     for (int i = 0; i + 1 < H; i += 2) { u0 = fmaf(wo[i], y[i], u0); u1 = fmaf(wo[i + 1], y[i + 1], u1); }
     if (H & 1) u0 = fmaf(wo[H - 1], y[H - 1], u0);
@@ -77,8 +77,8 @@ XW_DEV float project_u(const float* sw, const float (&y)[H]) {
 
 // one explicit RK step y <- y + dt * sum_s b_s k_s, recording stage internals in rec[s] and
 // (optionally) the stage inputs in yin[s]
-template <int H, int HH, int SOLVER, class Rec, bool KEEP_YIN>
-XW_DEV void rk_step(const float* sw, const float (&ax)[HH], float t0, float dt, int nsh, float (&y)[H],
+template <int H, int HH, int SOLVER, class Rec, bool KEEP_YIN, class W>
+XW_DEV void rk_step(const W& sw, const float (&ax)[HH], float t0, float dt, int nsh, float (&y)[H],
                     Rec (&rec)[Tableau<SOLVER>::S], float (*yin_keep)[H]) {
     using T = Tableau<SOLVER>;
     float k[T::S][H];
@@ -114,15 +114,16 @@ XW_DEV void rk_step(const float* sw, const float (&ax)[HH], float t0, float dt, 
     }
 }
 
-template <int H, int HH, int SOLVER, int MODE>
+template <int H, int HH, int SOLVER, int MODE, class WS>
 XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
     using S = USmem<H, HH>;
     using T = Tableau<SOLVER>;
     XW_DYN_SMEM(smem_raw);
-    float* sw = reinterpret_cast<float*>(smem_raw);
-    float* st = sw + pad4(S::size(a.d));
+    float* swp = reinterpret_cast<float*>(smem_raw);
+    float* st = swp + pad4(S::size(a.d));
     double* red = reinterpret_cast<double*>(st + pad4(a.L) + 4);
-    stage_theta_u<H, HH>(sw, a.theta, a.d, a.Hr, a.HHr);
+    const WS sw = WS::make(swp);
+    if (WS::kStage) stage_theta_u<H, HH>(swp, a.theta, a.d, a.Hr, a.HHr);
     for (int i = XW_TID; i < a.L; i += XW_BDIM) st[i] = a.times[i];
     XW_SYNCTHREADS();
 
@@ -161,7 +162,7 @@ XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
         if (MODE == 1) {
             // reverse sweep with cotangent 1 on every u[l]: lam = d sum_l u_l / d y_l
             float lam[H], a0[HH];
-            load_row<H>(sw + S::WO, lam);
+            load_row<H>(sw.at(S::WO), lam);
 #pragma unroll
             for (int i = 0; i < HH; ++i) a0[i] = 0.f;
             for (int l = L - 2; l >= 0; --l) {
@@ -199,7 +200,7 @@ XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
                     }
                 }
                 float wo[H];
-                load_row<H>(sw + S::WO, wo);
+                load_row<H>(sw.at(S::WO), wo);
 #pragma unroll
                 for (int i = 0; i < H; ++i) lam[i] = ybar[i] + wo[i];
             }
@@ -209,16 +210,16 @@ XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
             float dz2[H], dz1[H];
 #pragma unroll
             for (int i = 0; i < H; ++i) { dz2[i] = 0.f; dz1[i] = 0.f; }
-            matvec_acc<H, H, S::HP>(sw + S::W2, lam, dz2);
+            matvec_acc<H, H, S::HP>(sw.at(S::W2), lam, dz2);
 #pragma unroll
             for (int i = 0; i < H; ++i) dz2[i] = z2[i] > 0.f ? dz2[i] : 0.f;
-            matvec_acc<H, H, S::HP>(sw + S::W1, dz2, dz1);
+            matvec_acc<H, H, S::HP>(sw.at(S::W1), dz2, dz1);
             float gs = 0.f;
 #pragma unroll
-            for (int i = 0; i < H; ++i) gs = fmaf(z1[i] > 0.f ? dz1[i] : 0.f, sw[S::W0 + i], gs);
+            for (int i = 0; i < H; ++i) gs = fmaf(z1[i] > 0.f ? dz1[i] : 0.f, (*sw.at(S::W0 + i)), gs);
             for (int j = 0; j < a.d; ++j) {
                 float w[HH];
-                load_row<HH>(sw + S::WXT + j * S::HHP, w);
+                load_row<HH>(sw.at(S::WXT + j * S::HHP), w);
                 float g = gs * a.grad_h[n * a.d + j];
 #pragma unroll
                 for (int o = 0; o < HH; ++o) g = fmaf(w[o], a0[o], g);
@@ -231,6 +232,12 @@ XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
         const int idx[1] = {4};
         block_sum_to_global<1>(v, red, a.sums, idx);
     }
+}
+
+// builds the USmem weight image in GLOBAL memory (one CTA); the host then copies it into the constant bank
+template <int H, int HH>
+XW_GLOBAL void k_build_u_image(const float* theta, int d, int Hr, int HHr, float* img) {
+    stage_theta_u<H, HH>(img, theta, d, Hr, HHr);
 }
 
 // =============================================================================================
@@ -382,7 +389,7 @@ constexpr int kStgRowsV = 64 + 64;     // per-point v-net kernel
 
 // reverse of one field evaluation with parameter gradients
 template <int H, int HH>
-XW_DEV void field_rev_grads(const float* sw, const float* acts, int stride, int nsh, float tstage,
+XW_DEV void field_rev_grads(const WSmem& sw, const float* acts, int stride, int nsh, float tstage,
                             const float (&yin)[H], const float (&gout)[H], float (&gy)[H], float (&a0)[HH],
                             float* stg, float* gw, const ULayout& g) {
     using S = USmem<H, HH>;
@@ -399,7 +406,7 @@ XW_DEV void field_rev_grads(const float* sw, const float* acts, int stride, int 
     float dl[HH];
 #pragma unroll
     for (int i = 0; i < HH; ++i) dl[i] = 0.f;
-    matvec_acc<H, HH, S::HHP>(sw + S::WF, gout, dl);
+    matvec_acc<H, HH, S::HHP>(sw.at(S::WF), gout, dl);
 #pragma unroll
     for (int i = 0; i < HH; ++i) dl[i] *= (1.f - tau1[i] * tau1[i]);
     for (int j = nsh; j > 0; --j) {
@@ -415,7 +422,7 @@ XW_DEV void field_rev_grads(const float* sw, const float* acts, int stride, int 
         float dn[HH];
 #pragma unroll
         for (int i = 0; i < HH; ++i) dn[i] = 0.f;
-        matvec_acc<HH, HH, S::HHP>(sw + S::WS, dl, dn);
+        matvec_acc<HH, HH, S::HHP>(sw.at(S::WS), dl, dn);
 #pragma unroll
         for (int i = 0; i < HH; ++i) dl[i] = r1[i] > 0.f ? dn[i] : 0.f;
     }
@@ -432,7 +439,7 @@ XW_DEV void field_rev_grads(const float* sw, const float* acts, int stride, int 
     });
 #pragma unroll
     for (int i = 0; i < HH; ++i) a0[i] += dl[i];
-    matvec_acc<HH, H, S::HP>(sw + S::WY, dl, gy);
+    matvec_acc<HH, H, S::HP>(sw.at(S::WY), dl, gy);
 }
 
 template <int H, int HH, int SOLVER, int MODE>
@@ -443,13 +450,14 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
     const int nwarps = XW_BDIM >> 5, warp = XW_TID >> 5, lane = XW_TID & 31;
     const ULayout g(a.d, a.Hr, a.HHr);
     const int Pp = pad4(g.size);
-    float* sw = reinterpret_cast<float*>(smem_raw);
-    float* st = sw + pad4(S::size(a.d));
+    float* swp = reinterpret_cast<float*>(smem_raw);
+    const WSmem sw = WSmem::make(swp);
+    float* st = swp + pad4(S::size(a.d));
     float* sacts = st + pad4(a.L) + 4;                                  // [(nsh+1)*HH][BDIM]  ONE stage at a time
     float* sstg = sacts + (size_t)(a.nsh + 1) * HH * XW_BDIM;    // [nwarps][kStgRowsU][kStgLd]
     float* sgrad = sstg + (size_t)nwarps * kStgRowsU * kStgLd;                // [nwarps][Pp]
     double* red = reinterpret_cast<double*>(sgrad + (size_t)nwarps * Pp);
-    stage_theta_u<H, HH>(sw, a.theta, a.d, a.Hr, a.HHr);
+    stage_theta_u<H, HH>(swp, a.theta, a.d, a.Hr, a.HHr);
     for (int i = XW_TID; i < a.L; i += XW_BDIM) st[i] = a.times[i];
     for (int i = XW_TID; i < nwarps * Pp; i += XW_BDIM) sgrad[i] = 0.f;
     XW_SYNCTHREADS();
@@ -505,7 +513,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
         {
             const float G = cot_at(L - 1, project_u<H, HH>(sw, y));
             float wo[H];
-            load_row<H>(sw + S::WO, wo);
+            load_row<H>(sw.at(S::WO), wo);
 #pragma unroll
             for (int i = 0; i < H; ++i) { lam[i] = wo[i] * G; gwo[i] = fmaf(G, y[i], gwo[i]); }
             gbo += G;
@@ -579,7 +587,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
             }
             const float G = cot_at(l, project_u<H, HH>(sw, yl));
             float wo[H];
-            load_row<H>(sw + S::WO, wo);
+            load_row<H>(sw.at(S::WO), wo);
 #pragma unroll
             for (int i = 0; i < H; ++i) { lam[i] = fmaf(wo[i], G, ybar[i]); gwo[i] = fmaf(G, yl[i], gwo[i]); }
             gbo += G;
@@ -604,7 +612,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
         float dz2[H], dz1[H];
 #pragma unroll
         for (int i = 0; i < H; ++i) { dz2[i] = 0.f; dz1[i] = 0.f; }
-        matvec_acc<H, H, S::HP>(sw + S::W2, lam, dz2);
+        matvec_acc<H, H, S::HP>(sw.at(S::W2), lam, dz2);
 #pragma unroll
         for (int i = 0; i < H; ++i) dz2[i] = z2[i] > 0.f ? dz2[i] : 0.f;
         {
@@ -618,7 +626,7 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
                 return i < a.Hr ? gw + g.W1 + o * a.Hr + i : nullptr;
             });
         }
-        matvec_acc<H, H, S::HP>(sw + S::W1, dz2, dz1);
+        matvec_acc<H, H, S::HP>(sw.at(S::W1), dz2, dz1);
 #pragma unroll
         for (int i = 0; i < H; ++i) dz1[i] = z1[i] > 0.f ? dz1[i] : 0.f;
         {

@@ -161,6 +161,28 @@ XW_DEV void stage_theta_v(float* s, const float* XW_RESTRICT th, int d, int Hvr)
 }
 
 // ---------------------------------------------------------------------------------------------
+// where the XNODE weight image lives: shared memory (LDS: the one LSU pipe per SM) or the constant
+// bank (FFMA takes c[bank][imm] operands directly: no LSU traffic for the warp-uniform weights)
+// ---------------------------------------------------------------------------------------------
+constexpr int kConstUFloats = 8192;
+#ifdef XW_EMU
+inline float c_theta_u[kConstUFloats];
+#else
+__constant__ float c_theta_u[kConstUFloats];
+#endif
+struct WSmem {
+    static constexpr bool kStage = true;
+    const float* p;
+    XW_DEV static WSmem make(const float* smem) { return WSmem{smem}; }
+    XW_DEV const float* at(int off) const { return p + off; }
+};
+struct WConst {
+    static constexpr bool kStage = false;
+    XW_DEV static WConst make(const float*) { return WConst{}; }
+    XW_DEV const float* at(int off) const { return c_theta_u + off; }
+};
+
+// ---------------------------------------------------------------------------------------------
 // explicit Runge-Kutta tableaus of the reference's fixed-grid solvers (torchdiffeq 0.1.1:
 // euler, midpoint, rk4 = 3/8 rule); see oracle/shims/torchdiffeq/__init__.py
 // ---------------------------------------------------------------------------------------------
@@ -192,17 +214,20 @@ template <> struct Tableau<2> {
 // ---------------------------------------------------------------------------------------------
 // XNODE pieces
 // ---------------------------------------------------------------------------------------------
-template <int H, int HH>
-XW_DEV void lift_fwd(const float* s, float s0, float (&z1)[H], float (&z2)[H], float (&y)[H]) {
+template <int H, int HH, class W>
+XW_DEV void lift_fwd(const W& s, float s0, float (&z1)[H], float (&z2)[H], float (&y)[H]) {
     using S = USmem<H, HH>;
+    float w0[H], b0[H];
+    load_row<H>(s.at(S::W0), w0);
+    load_row<H>(s.at(S::B0), b0);
 #pragma unroll
-    for (int o = 0; o < H; ++o) z1[o] = fmaxf(fmaf(s[S::W0 + o], s0, s[S::B0 + o]), 0.f);
-    load_row<H>(s + S::B1, z2);
-    matvec_acc<H, H, S::HP>(s + S::W1T, z1, z2);
+    for (int o = 0; o < H; ++o) z1[o] = fmaxf(fmaf(w0[o], s0, b0[o]), 0.f);
+    load_row<H>(s.at(S::B1), z2);
+    matvec_acc<H, H, S::HP>(s.at(S::W1T), z1, z2);
 #pragma unroll
     for (int o = 0; o < H; ++o) z2[o] = fmaxf(z2[o], 0.f);
-    load_row<H>(s + S::B2, y);
-    matvec_acc<H, H, S::HP>(s + S::W2T, z2, y);
+    load_row<H>(s.at(S::B2), y);
+    matvec_acc<H, H, S::HP>(s.at(S::W2T), z2, y);
 }
 
 // recorders for the internals of one field evaluation
@@ -242,56 +267,56 @@ struct RecSmem {                       // post-relu activations of every shared 
 };
 
 // F(t, y) = net(cat(x, t, y)); ax = Wa[:, :d] x + ba (path constant, hoisted)
-template <int H, int HH, class Rec>
-XW_DEV void field_fwd(const float* s, const float (&ax)[HH], float t, const float (&y)[H], int nsh,
+template <int H, int HH, class Rec, class W>
+XW_DEV void field_fwd(const W& s, const float (&ax)[HH], float t, const float (&y)[H], int nsh,
                       float (&out)[H], float (&tau)[HH], Rec& rec) {
     using S = USmem<H, HH>;
     float a[HH], wt[HH];
-    load_row<HH>(s + S::WT, wt);
+    load_row<HH>(s.at(S::WT), wt);
 #pragma unroll
     for (int o = 0; o < HH; ++o) a[o] = fmaf(wt[o], t, ax[o]);
-    matvec_acc<H, HH, S::HHP>(s + S::WYT, y, a);
+    matvec_acc<H, HH, S::HHP>(s.at(S::WYT), y, a);
     for (int j = 0; j < nsh; ++j) {
         float r[HH], b[HH];
 #pragma unroll
         for (int i = 0; i < HH; ++i) r[i] = fmaxf(a[i], 0.f);
         rec.relu_in(j, r);
-        load_row<HH>(s + S::BS, b);
-        matvec_acc<HH, HH, S::HHP>(s + S::WST, r, b);
+        load_row<HH>(s.at(S::BS), b);
+        matvec_acc<HH, HH, S::HHP>(s.at(S::WST), r, b);
 #pragma unroll
         for (int i = 0; i < HH; ++i) a[i] = b[i];
     }
 #pragma unroll
     for (int i = 0; i < HH; ++i) tau[i] = tanh_fast(a[i]);
     rec.tanh_out(tau);
-    load_row<H>(s + S::BF, out);
-    matvec_acc<HH, H, S::HP>(s + S::WFT, tau, out);
+    load_row<H>(s.at(S::BF), out);
+    matvec_acc<HH, H, S::HP>(s.at(S::WFT), tau, out);
 }
 
 // reverse of one field evaluation, input-VJP only (relu masks from a bit stack).
 // gout: cotangent of F.  gy += dF/dy^T gout ; a0 += cotangent of the first pre-activation.
-template <int H, int HH>
-XW_DEV void field_rev_bits(const float* s, RecBits<HH>& rec, int nsh, const float (&gout)[H],
+template <int H, int HH, class W>
+XW_DEV void field_rev_bits(const W& s, RecBits<HH>& rec, int nsh, const float (&gout)[H],
                            float (&gy)[H], float (&a0)[HH]) {
     using S = USmem<H, HH>;
     float dl[HH];
 #pragma unroll
     for (int i = 0; i < HH; ++i) dl[i] = 0.f;
-    matvec_acc<H, HH, S::HHP>(s + S::WF, gout, dl);            // Wf^T gout
+    matvec_acc<H, HH, S::HHP>(s.at(S::WF), gout, dl);          // Wf^T gout
 #pragma unroll
     for (int i = 0; i < HH; ++i) dl[i] *= (1.f - rec.tau[i] * rec.tau[i]);
     for (int j = nsh; j > 0; --j) {
         float dn[HH];
 #pragma unroll
         for (int i = 0; i < HH; ++i) dn[i] = 0.f;
-        matvec_acc<HH, HH, S::HHP>(s + S::WS, dl, dn);         // Ws^T delta
+        matvec_acc<HH, HH, S::HHP>(s.at(S::WS), dl, dn);       // Ws^T delta
         unsigned bits = rec.m.template pop<HH>();
 #pragma unroll
         for (int i = 0; i < HH; ++i) dl[i] = ((bits >> i) & 1u) ? dn[i] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < HH; ++i) a0[i] += dl[i];
-    matvec_acc<HH, H, S::HP>(s + S::WY, dl, gy);               // Wy^T delta0
+    matvec_acc<HH, H, S::HP>(s.at(S::WY), dl, gy);             // Wy^T delta0
 }
 
 // ---------------------------------------------------------------------------------------------
