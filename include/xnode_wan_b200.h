@@ -74,7 +74,8 @@ int xw_abi_version(void);
 const char* xw_last_error(void);
 int xw_theta_u_size(const xw_dims* dims);
 int xw_theta_v_size(const xw_dims* dims);
-/* floats in the optional test-function cache of xw_interior_forward */
+/* floats in the optional state-history / test-function cache buffers of xw_interior_forward */
+size_t xw_yhist_floats(const xw_dims* dims, int n, int L);
 size_t xw_vcache_floats(const xw_dims* dims, int n, int L);
 /* upper bound of the scratch any call below needs for n paths of length L */
 size_t xw_workspace_bytes(const xw_dims* dims, int n, int L);
@@ -101,14 +102,16 @@ int xw_vnet_eval(const xw_dims* dims, const float* theta_v, const xw_points* pts
  * vcache (xw_vcache_floats(dims, n, L) floats) / vcache_mode: the reference runs n1 u-steps and n2
  * v-steps on ONE sample (src/training.py:125,151); while the sample and theta_v are unchanged the
  * test-function values (v, dv/dt, w, dw/dt per point, grad_x phi on time-row 0) do not change either:
- *   0 = no cache, 1 = evaluate the v net and fill the cache, 2 = skip the v net and read the cache. */
+ *   0 = no cache, 1 = evaluate the v net and fill the cache, 2 = skip the v net and read the cache.
+ * y_hist (optional, xw_yhist_floats(dims, n, L) floats): the XNODE state history y_l of every path, kept so
+ * that xw_interior_backward_u does not integrate the ODE forward again. */
 int xw_interior_forward(const xw_dims* dims, const xw_domain* dom, const xw_coef* coef,
                         const float* theta_u, const float* theta_v,
                         const float* x, long long x_sn, const float* times, int L,
                         const xw_points* xv, const float* h, const float* grad_s0, const float* f,
                         int n, double* sums, float* cot_u, float* cot_v, float* u_out,
                         void* workspace, size_t workspace_bytes, void* stream, const float* s0,
-                        float* vcache, int vcache_mode);
+                        float* vcache, int vcache_mode, float* y_hist);
 
 /* Boundary term (replaces loss.bdry = mean((u_net(BX) - g)^2), src/loss.py:83-85, and its
  * backward): adds sum (u_b - g)^2 to sums[BDRY]; if grad_u != NULL also accumulates
@@ -125,7 +128,8 @@ int xw_boundary_u(const xw_dims* dims, const float* theta_u, const float* xb, lo
 int xw_interior_backward_u(const xw_dims* dims, const float* theta_u, const float* x, long long x_sn,
                            const float* times, int L, const float* h, const float* cot_u, int n,
                            const double* coefs_dev, float* grad_u, int accumulate,
-                           void* workspace, size_t workspace_bytes, void* stream, const float* s0);
+                           void* workspace, size_t workspace_bytes, void* stream, const float* s0,
+                           const float* y_hist);
 
 /* theta_v gradient of loss_v (replaces loss_v.backward() for v_net, src/training.py:160,
  * including the side effect of src/loss.py:60):

@@ -84,7 +84,7 @@ def make_domain(dom):
     return L_.Domain(kind, ps[0], ps[1], ps[2])
 
 
-def run_case(lib, be, case, coef_a=None, coef_b=None):
+def run_case(lib, be, case, coef_a=None, coef_b=None, use_yhist=True):
     """full u-phase and v-phase evaluation of one golden case through the C ABI.
     returns dict(I,S,init,bdry,loss_u,loss_v,grads_u,grads_v,sums,u)"""
     z, p = case["z"], case["params"]
@@ -115,10 +115,11 @@ def run_case(lib, be, case, coef_a=None, coef_b=None):
     sums = be.zeros(L_.NSUMS, np.float64)
     cot_u, cot_v, u_out = be.zeros(N * L), be.zeros(N * L), be.zeros(N * L)
     vcache = be.zeros(lib.cdll.xw_vcache_floats(C.byref(dims), N, L))
+    yhist = be.zeros(lib.cdll.xw_yhist_floats(C.byref(dims), N, L)) if use_yhist else None
     lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), be.ptr(thu), be.ptr(thv),
              be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L, C.byref(pts), be.ptr(h), be.ptr(gh), be.ptr(f), N,
              be.ptr(sums), be.ptr(cot_u), be.ptr(cot_v), be.ptr(u_out), be.ptr(ws), wsb, be.stream, be.ptr(s0),
-             be.ptr(vcache), 1)
+             be.ptr(vcache), 1, be.ptr(yhist))
     gu = be.zeros(Pu)
     lib.call("xw_boundary_u", C.byref(dims), be.ptr(thu), be.ptr_off(BXd, 1), Lb * Cc, be.ptr(times_b), Lb,
              be.ptr(sb), be.ptr(g), Nb, alpha / (Nb * Lb), be.ptr(sums), be.ptr(gu), 0, be.ptr(ws), wsb, be.stream)
@@ -128,7 +129,7 @@ def run_case(lib, be, case, coef_a=None, coef_b=None):
     cu2, cv2 = be.zeros(N * L), be.zeros(N * L)
     lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), be.ptr(thu), be.ptr(thv),
              be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L, C.byref(pts), be.ptr(h), be.ptr(gh), be.ptr(f), N,
-             be.ptr(sums2), be.ptr(cu2), be.ptr(cv2), None, be.ptr(ws), wsb, be.stream, be.ptr(s0), be.ptr(vcache), 2)
+             be.ptr(sums2), be.ptr(cu2), be.ptr(cv2), None, be.ptr(ws), wsb, be.stream, be.ptr(s0), be.ptr(vcache), 2, None)
     be.sync()
     s_a, s_b = be.host(sums)[:5].copy(), be.host(sums2)[:5].copy()
     assert np.allclose(s_a, s_b, rtol=1e-6, atol=1e-6 * np.abs(s_a).max()), (s_a, s_b)
@@ -142,7 +143,7 @@ def run_case(lib, be, case, coef_a=None, coef_b=None):
                u=be.host(u_out).reshape(N, L).copy())
     ku = be.arr(np.array([(2.0 / I) * V / (N * L), 2.0 * alpha / N, 1.0]), np.float64)
     lib.call("xw_interior_backward_u", C.byref(dims), be.ptr(thu), be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L,
-             be.ptr(h), be.ptr(cot_u), N, be.ptr(ku), be.ptr(gu), 1, be.ptr(ws), wsb, be.stream, be.ptr(s0))
+             be.ptr(h), be.ptr(cot_u), N, be.ptr(ku), be.ptr(gu), 1, be.ptr(ws), wsb, be.stream, be.ptr(s0), be.ptr(yhist))
     kv = be.arr(np.array([-(2.0 / I) * V / (N * L), 2.0 / s[3], 1.0]), np.float64)
     gv = be.zeros(Pv)
     lib.call("xw_interior_backward_v", C.byref(dims), C.byref(dom), be.ptr(thv), C.byref(pts), be.ptr(cot_v), N, L,

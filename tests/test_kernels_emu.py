@@ -54,6 +54,15 @@ def test_emulated_kernels_dense_a_and_b_match_oracle(emu):
     check_against(r, ref, refs["u"]["grads"], refs["v"]["grads"])
 
 
+def test_backward_u_without_state_history_recomputes(emu):
+    """y_hist = NULL: xw_interior_backward_u integrates the ODE forward itself; same gradients"""
+    c = G.load("cube_d5_alpha1_randbias")
+    r1 = LL.run_case(emu, LL.NumpyBackend(), c, use_yhist=True)
+    r0 = LL.run_case(emu, LL.NumpyBackend(), c, use_yhist=False)
+    for a, b in zip(r1["grads_u"], r0["grads_u"]):
+        assert G.rel(a, b) < 1e-5
+
+
 def test_capi_rejects_unsupported(emu):
     import ctypes as C
     d = xw._lib.Dims(5, 64, 10, 8, 50, 9, 1)

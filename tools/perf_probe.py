@@ -65,6 +65,7 @@ def main():
     u_out = torch.empty(N * L, device=dev)
     v_out = torch.empty(N * L, device=dev)
     gu = torch.zeros(Pu, device=dev)
+    yh = torch.empty(int(lib.cdll.xw_yhist_floats(C.byref(dims), N, L)), device=dev)
     gv = torch.zeros(Pv, device=dev)
     ku = torch.tensor([0.3, 0.1, 1.0], dtype=torch.float64, device=dev)
     res = {"N": N, "d": d, "L": L}
@@ -85,13 +86,13 @@ def main():
         lib.call("xw_vnet_eval", C.byref(dims), p(thv), C.byref(pts), N, L, p(v_out), st)
     def ifwd():
         lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), p(thu), p(thv), p(x), d, p(times), L,
-                 C.byref(pts), p(h), p(gh), p(f), N, p(sums), p(cot_u), p(cot_v), p(u_out), p(ws), wsb, st, None, None, 0)
+                 C.byref(pts), p(h), p(gh), p(f), N, p(sums), p(cot_u), p(cot_v), p(u_out), p(ws), wsb, st, None, None, 0, p(yh))
     def bdry():
         lib.call("xw_boundary_u", C.byref(dims), p(thu), p(xb), d, p(times), L, p(sb), p(g), Nb, 1e-3, p(sums), p(gu), 0,
                  p(ws), wsb, st)
     def bwdu():
         lib.call("xw_interior_backward_u", C.byref(dims), p(thu), p(x), d, p(times), L, p(h), p(cot_u), N, p(ku), p(gu), 1,
-                 p(ws), wsb, st, None)
+                 p(ws), wsb, st, None, p(yh))
     def bwdv():
         lib.call("xw_interior_backward_v", C.byref(dims), C.byref(dom), p(thv), C.byref(pts), p(cot_v), N, L, p(ku), p(gv),
                  0, p(ws), wsb, st)

@@ -51,12 +51,13 @@ _SIGS = {
     "xw_vnet_eval": (C.c_int, [C.POINTER(Dims), _P, C.POINTER(Points), C.c_int, C.c_int, _P, _P]),
     "xw_interior_forward": (C.c_int, [C.POINTER(Dims), C.POINTER(Domain), C.POINTER(Coef), _P, _P, _P, C.c_longlong,
                                       _P, C.c_int, C.POINTER(Points), _P, _P, _P, C.c_int, _P, _P, _P, _P, _P,
-                                      C.c_size_t, _P, _P, _P, C.c_int]),
+                                      C.c_size_t, _P, _P, _P, C.c_int, _P]),
+    "xw_yhist_floats": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
     "xw_vcache_floats": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
     "xw_boundary_u": (C.c_int, [C.POINTER(Dims), _P, _P, C.c_longlong, _P, C.c_int, _P, _P, C.c_int, C.c_double, _P,
                                 _P, C.c_int, _P, C.c_size_t, _P]),
     "xw_interior_backward_u": (C.c_int, [C.POINTER(Dims), _P, _P, C.c_longlong, _P, C.c_int, _P, _P, C.c_int, _P, _P,
-                                         C.c_int, _P, C.c_size_t, _P, _P]),
+                                         C.c_int, _P, C.c_size_t, _P, _P, _P]),
     "xw_interior_backward_v": (C.c_int, [C.POINTER(Dims), C.POINTER(Domain), _P, C.POINTER(Points), _P, C.c_int,
                                          C.c_int, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "xw_fma_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), _P]),

@@ -103,6 +103,11 @@ int check_dims(const xw_dims* m) {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int grid_for(long long items, int block, int ctas_per_sm);
 int ctas_per_sm_for(size_t smem, int cap);
+// per-thread scratch of the interior forward kernel: (mask bits + tanh) of every field evaluation
+size_t fwd_hist_floats(const xw_dims* m, int L) {
+    const int S = m->solver == 0 ? 1 : m->solver == 1 ? 2 : 4;
+    return (size_t)std::max(L, 1) * S * xw::kRecWords<kHH>;
+}
 
 int stages_of(int solver) { return solver == 0 ? 1 : solver == 1 ? 2 : 4; }
 int bwd_block(int solver) { (void)solver; return 128; }
@@ -288,6 +293,7 @@ const char* xw_last_error(void) { return g_err; }
 
 int xw_theta_u_size(const xw_dims* m) { return m ? xw::ULayout(m->d, m->H, m->hh).size : -1; }
 int xw_theta_v_size(const xw_dims* m) { return m ? xw::VLayout(m->d, m->Hv).size : -1; }
+size_t xw_yhist_floats(const xw_dims* m, int n, int L) { return m ? (size_t)L * kH * n : 0; }
 size_t xw_vcache_floats(const xw_dims* m, int n, int L) { return m ? (size_t)4 * n * L + (size_t)n * m->d : 0; }
 
 size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
@@ -295,7 +301,7 @@ size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
     // interior forward: du[n*d] + u[n*L] + yhist
     int gf = grid_for(n, kBlkFwd, 8);
     size_t fwd = align_up((size_t)n * m->d * 4, 256) + align_up((size_t)n * L * 4, 256) +
-                 align_up((size_t)L * kH * gf * kBlkFwd * 4, 256);
+                 align_up(fwd_hist_floats(m, L) * gf * kBlkFwd * 4, 256);
     XnodeBwdPlan pb;
     if (plan_xnode_bwd(m, n, L, &pb)) return 0;
     size_t bwd_u = pb.hist_bytes + pb.part_bytes;
@@ -338,7 +344,8 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
                         const float* theta_v, const float* x, long long x_sn, const float* times, int L,
                         const xw_points* xv, const float* h, const float* grad_h, const float* f, int n,
                         double* sums, float* cot_u, float* cot_v, float* u_out, void* workspace,
-                        size_t workspace_bytes, void* stream, const float* s0, float* vcache, int vcache_mode) {
+                        size_t workspace_bytes, void* stream, const float* s0, float* vcache, int vcache_mode,
+                        float* y_hist) {
     if (check_dims(m)) return 1;
     if (!device()) return fail("no CUDA device");
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
@@ -350,7 +357,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     float* gcache = vcache ? vcache + (size_t)4 * n * L : nullptr;
     const int gf = grid_for(n, kBlkFwd, 8);
     const size_t du_b = align_up((size_t)n * m->d * 4, 256), u_b = align_up((size_t)n * L * 4, 256);
-    const size_t hist_b = align_up((size_t)L * kH * gf * kBlkFwd * 4, 256);
+    const size_t hist_b = align_up(fwd_hist_floats(m, L) * gf * kBlkFwd * 4, 256);
     if (workspace_bytes < du_b + u_b + hist_b) return fail("workspace too small: %zu < %zu", workspace_bytes, du_b + u_b + hist_b);
     char* ws = (char*)workspace;
     float* du = (float*)ws;
@@ -360,7 +367,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     xw::XnodeFwdArgs a{};
     a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
     a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0 ? s0 : h; a.u_out = ubuf;
-    a.grad_h = grad_h; a.du_out = du; a.yhist = yhist; a.sums = sums; a.hloss = h;
+    a.grad_h = grad_h; a.du_out = du; a.yhist = yhist; a.sums = sums; a.hloss = h; a.ypath = y_hist;
     if (launch_xnode_fwd<1>(m, a, gf, smem_xnode_fwd(m->d, L), stream)) return 1;
 
     xw::VnetFwdArgs b{};
@@ -423,7 +430,8 @@ int xw_boundary_u(const xw_dims* m, const float* theta_u, const float* xb, long 
 
 int xw_interior_backward_u(const xw_dims* m, const float* theta_u, const float* x, long long x_sn, const float* times,
                            int L, const float* h, const float* cot_u, int n, const double* coefs_dev, float* grad_u,
-                           int accumulate, void* workspace, size_t workspace_bytes, void* stream, const float* s0) {
+                           int accumulate, void* workspace, size_t workspace_bytes, void* stream, const float* s0,
+                           const float* y_hist) {
     if (check_dims(m)) return 1;
     if (!device()) return fail("no CUDA device");
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
@@ -433,7 +441,7 @@ int xw_interior_backward_u(const xw_dims* m, const float* theta_u, const float* 
     if (workspace_bytes < p.hist_bytes + p.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, p.hist_bytes + p.part_bytes);
     xw::XnodeBwdArgs a{};
     a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
-    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0 ? s0 : h; a.hloss = h; a.cot = cot_u; a.coefs = coefs_dev;
+    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0 ? s0 : h; a.hloss = h; a.cot = cot_u; a.coefs = coefs_dev; a.ypath = y_hist;
     a.gscale = 0.0; a.yhist = (float*)workspace; a.gpart = (float*)((char*)workspace + p.hist_bytes); a.sums = nullptr;
     if (launch_xnode_bwd<0>(m, a, p.grid, p.block, p.smem, stream)) return 1;
     return reduce_partials(a.gpart, p.grid, xw_theta_u_size(m), grad_u, accumulate, stream);

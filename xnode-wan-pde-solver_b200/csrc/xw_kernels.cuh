@@ -48,6 +48,7 @@ struct XnodeFwdArgs {
     float* u_out;
     const float* grad_h; float* du_out; float* yhist; double* sums;
     const float* hloss;          // func_h values used by loss.init (== s0 when the batch starts at T0)
+    float* ypath;                // MODE 1, optional: [L][H][n] state history kept for the interior backward
 };
 
 template <int H, int HH, class W>
@@ -114,6 +115,9 @@ XW_DEV void rk_step(const W& sw, const float (&ax)[HH], float t0, float dt, int 
     }
 }
 
+// words kept per field evaluation for the reverse "ones" sweep: 128 mask bits + HH tanh outputs
+template <int HH> constexpr int kRecWords = 4 + HH;
+
 template <int H, int HH, int SOLVER, int MODE, class WS>
 XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
     using S = USmem<H, HH>;
@@ -145,18 +149,39 @@ XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
         if (a.u_out) a.u_out[n * L] = u;
         if (MODE == 1) {
             { const float hd = u - a.hloss[n]; init_acc += (double)(hd * hd); }
+            if (a.ypath) {
 #pragma unroll
-            for (int i = 0; i < H; ++i) a.yhist[(long long)i * nthr + gtid] = y[i];
+                for (int i = 0; i < H; ++i) a.ypath[(long long)i * a.n + n] = y[i];
+            }
         }
         for (int l = 0; l + 1 < L; ++l) {
             const float t0 = st[l], dt = st[l + 1] - st[l];
-            RecNone<HH> rec[T::S];
-            rk_step<H, HH, SOLVER, RecNone<HH>, false>(sw, ax, t0, dt, nsh, y, rec, nullptr);
+            if (MODE == 1) {
+                // keep what the reverse "ones" sweep needs of every field evaluation (relu masks as
+                // bits + tanh outputs: 4 + HH words per stage) so that it does not recompute the stages
+                RecBits<HH> rec[T::S];
+#pragma unroll
+                for (int s = 0; s < T::S; ++s) rec[s].m.clear();
+                rk_step<H, HH, SOLVER, RecBits<HH>, false>(sw, ax, t0, dt, nsh, y, rec, nullptr);
+#pragma unroll
+                for (int s = 0; s < T::S; ++s) {
+                    float* hp = a.yhist + ((long long)(l * T::S + s) * kRecWords<HH>) * nthr + gtid;
+                    hp[0] = __uint_as_float((unsigned)rec[s].m.lo);
+                    hp[nthr] = __uint_as_float((unsigned)(rec[s].m.lo >> 32));
+                    hp[2 * nthr] = __uint_as_float((unsigned)rec[s].m.hi);
+                    hp[3 * nthr] = __uint_as_float((unsigned)(rec[s].m.hi >> 32));
+#pragma unroll
+                    for (int i = 0; i < HH; ++i) hp[(4 + i) * nthr] = rec[s].tau[i];
+                }
+            } else {
+                RecNone<HH> rec[T::S];
+                rk_step<H, HH, SOLVER, RecNone<HH>, false>(sw, ax, t0, dt, nsh, y, rec, nullptr);
+            }
             u = project_u<H, HH>(sw, y);
             if (a.u_out) a.u_out[n * L + l + 1] = u;
-            if (MODE == 1 && l + 2 < L) {
+            if (MODE == 1 && a.ypath) {
 #pragma unroll
-                for (int i = 0; i < H; ++i) a.yhist[((long long)(l + 1) * H + i) * nthr + gtid] = y[i];
+                for (int i = 0; i < H; ++i) a.ypath[((long long)(l + 1) * H + i) * a.n + n] = y[i];
             }
         }
         if (MODE == 1) {
@@ -167,13 +192,15 @@ XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
             for (int i = 0; i < HH; ++i) a0[i] = 0.f;
             for (int l = L - 2; l >= 0; --l) {
                 const float t0 = st[l], dt = st[l + 1] - st[l];
-                float yl[H];
-#pragma unroll
-                for (int i = 0; i < H; ++i) yl[i] = a.yhist[((long long)l * H + i) * nthr + gtid];
                 RecBits<HH> rec[T::S];
 #pragma unroll
-                for (int s = 0; s < T::S; ++s) rec[s].m.clear();
-                rk_step<H, HH, SOLVER, RecBits<HH>, false>(sw, ax, t0, dt, nsh, yl, rec, nullptr);
+                for (int s = 0; s < T::S; ++s) {
+                    const float* hp = a.yhist + ((long long)(l * T::S + s) * kRecWords<HH>) * nthr + gtid;
+                    rec[s].m.lo = (unsigned long long)__float_as_uint(hp[0]) | ((unsigned long long)__float_as_uint(hp[nthr]) << 32);
+                    rec[s].m.hi = (unsigned long long)__float_as_uint(hp[2 * nthr]) | ((unsigned long long)__float_as_uint(hp[3 * nthr]) << 32);
+#pragma unroll
+                    for (int i = 0; i < HH; ++i) rec[s].tau[i] = hp[(4 + i) * nthr];
+                }
                 float kbar[T::S][H], ybar[H];
 #pragma unroll
                 for (int s = 0; s < T::S; ++s)
@@ -361,6 +388,7 @@ struct XnodeBwdArgs {
     const float* cot;            // MODE 0: cot_u[n*L]   MODE 1: g[n*L]
     const double* coefs;         // MODE 0: device k0,k1,k2
     const float* hloss;          // MODE 0: func_h values of loss.init
+    const float* ypath;          // MODE 0, optional: [L][H][n] state history written by the forward kernel
     double gscale;               // MODE 1
     float* yhist; float* gpart; double* sums;
 };
@@ -484,15 +512,21 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
         hoist_ax<H, HH>(sw, xp, a.d, ax);
         const float s0 = a.s0[n];
         float y[H];
-        {
-            float z1[H], z2[H];
-            lift_fwd<H, HH>(sw, s0, z1, z2, y);
-        }
-        for (int l = 0; l + 1 < L; ++l) {
+        const bool have_hist = MODE == 0 && a.ypath != nullptr;
+        if (have_hist) {               // the forward kernel kept the state history: no forward sweep here
 #pragma unroll
-            for (int i = 0; i < H; ++i) a.yhist[((long long)l * H + i) * nthr + gtid] = y[i];
-            RecNone<HH> rec[T::S];
-            rk_step<H, HH, SOLVER, RecNone<HH>, false>(sw, ax, st[l], st[l + 1] - st[l], nsh, y, rec, nullptr);
+            for (int i = 0; i < H; ++i) y[i] = a.ypath[((long long)(L - 1) * H + i) * a.n + n];
+        } else {
+            {
+                float z1[H], z2[H];
+                lift_fwd<H, HH>(sw, s0, z1, z2, y);
+            }
+            for (int l = 0; l + 1 < L; ++l) {
+#pragma unroll
+                for (int i = 0; i < H; ++i) a.yhist[((long long)l * H + i) * nthr + gtid] = y[i];
+                RecNone<HH> rec[T::S];
+                rk_step<H, HH, SOLVER, RecNone<HH>, false>(sw, ax, st[l], st[l + 1] - st[l], nsh, y, rec, nullptr);
+            }
         }
         // cotangent of u[n, l]
         auto cot_at = [&](int l, float u) -> float {
@@ -522,7 +556,10 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
             const float t0 = st[l], dt = st[l + 1] - st[l];
             float yl[H], ycur[H];
 #pragma unroll
-            for (int i = 0; i < H; ++i) { yl[i] = a.yhist[((long long)l * H + i) * nthr + gtid]; ycur[i] = yl[i]; }
+            for (int i = 0; i < H; ++i) {
+                yl[i] = have_hist ? a.ypath[((long long)l * H + i) * a.n + n] : a.yhist[((long long)l * H + i) * nthr + gtid];
+                ycur[i] = yl[i];
+            }
             // stage inputs yin[s] (forward through the stages; only the LAST stage records its
             // internals: the shared-memory activation buffer holds one stage at a time, earlier
             // stages are re-evaluated right before their own reverse -> 2S-1 field evaluations)

@@ -46,6 +46,11 @@
 // weight loads out of the layer / time-step loops, which would need thousands of registers
 #define XW_FENCE() asm volatile("" ::: "memory")
 
+#ifdef XW_EMU
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+#endif
+
 namespace xw {
 
 constexpr int pad4(int x) { return (x + 3) & ~3; }

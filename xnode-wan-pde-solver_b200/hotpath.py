@@ -35,7 +35,7 @@ def _call(lib, name, dev, *args):
     CALLS[name] = CALLS.get(name, 0) + 1
     k = KERNELS_PER_CALL[name]
     if name == "xw_interior_forward":          # xnode_fwd + (row-0 kernel + tiled pass | combine from the cache)
-        k = 2 if args[-1] == 2 else 3
+        k = 2 if args[-2] == 2 else 3
     LAUNCHES[0] += k
     if PROFILE is not None and dev.type == "cuda":
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -233,7 +233,7 @@ def vcache_buffer(lib, spec, batch, dev):
 
 
 def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, alpha, boundary_grad=None,
-                 vcache=None, vmode=0):
+                 vcache=None, vmode=0, y_hist=None):
     """launches the forward kernels; returns (sums[8] fp64 device tensor, cot_u, cot_v).
     vcache/vmode: 0 none, 1 evaluate the v net and fill `vcache`, 2 reuse `vcache` (same sample, same theta_v)"""
     dev = theta_u.device
@@ -249,7 +249,8 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
     _call(lib, "xw_interior_forward", dev, C.byref(dims), C.byref(cdom), C.byref(ccoef), _ptr(theta_u), _ptr(theta_v),
              C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), L, C.byref(pts),
              _ptr(batch.h), _ptr(batch.grad_h), _ptr(batch.f), N, _ptr(sums), _ptr(cot_u), _ptr(cot_v), None,
-             _ptr(ws), ws.numel(), st, _ptr(batch.s0), _ptr(vcache) if vmode else None, int(vmode))
+             _ptr(ws), ws.numel(), st, _ptr(batch.s0), _ptr(vcache) if vmode else None, int(vmode),
+          _ptr(y_hist))
     if with_boundary:
         gscale = float(alpha) / (batch.Nb_glob * batch.Lb)
         _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
@@ -281,8 +282,12 @@ class WeakLoss(torch.autograd.Function):
         _check_dev(theta_u, "parameters")
         dev = theta_u.device
         gb = torch.zeros(theta_u.numel(), dtype=torch.float32, device=dev) if phase == "u" else None
+        yh = None
+        if phase == "u":       # XNODE state history for the interior backward (saves its forward sweep)
+            dims_ = spec.c()
+            yh = torch.empty(int(lib.cdll.xw_yhist_floats(C.byref(dims_), batch.N, batch.L)), dtype=torch.float32, device=dev)
         sums, cot_u, cot_v = forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, phase == "u", alpha, gb,
-                                          vcache, vmode)
+                                          vcache, vmode, yh)
         _allreduce(sums, group)
         I, S, init, bdry, integ = loss_from_sums(sums, batch, dom.V, alpha)
         ctx.phase, ctx.lib, ctx.spec, ctx.dom, ctx.batch, ctx.group = phase, lib, spec, dom, batch, group
@@ -291,7 +296,7 @@ class WeakLoss(torch.autograd.Function):
         N, L = batch.N_glob, batch.L
         if phase == "u":
             k = torch.stack([(2.0 / I) * (dom.V / (N * L)), torch.full_like(I, 2.0 * alpha / N), torch.full_like(I, ctx.side)])
-            ctx.save_for_backward(theta_u, cot_u, k, gb)
+            ctx.save_for_backward(theta_u, cot_u, k, gb, yh)
             out = integ + alpha * (init + bdry)
         else:
             k = torch.stack([-(2.0 / I) * (dom.V / (N * L)), 2.0 / sums[_lib.SUM_VV], torch.full_like(I, ctx.side)])
@@ -307,7 +312,7 @@ class WeakLoss(torch.autograd.Function):
         nup = ctx.nu_params
         none = (None,) * 12
         if ctx.phase == "u":
-            theta_u, cot_u, k, gb = ctx.saved_tensors
+            theta_u, cot_u, k, gb, yh = ctx.saved_tensors
             dev = theta_u.device
             st = _stream(dev)
             ws = _WS.get(dev, lib.workspace_bytes(dims, batch.N, batch.L))
@@ -317,7 +322,7 @@ class WeakLoss(torch.autograd.Function):
             _call(lib, "xw_interior_backward_u", dev, C.byref(dims), _ptr(theta_u),
                      C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), batch.L,
                      _ptr(batch.h), _ptr(cot_u), batch.N, _ptr(ks), _ptr(grad), 1, _ptr(ws), ws.numel(), st,
-                     _ptr(batch.s0))
+                     _ptr(batch.s0), _ptr(yh))
             _allreduce(grad, ctx.group)
             gl = unflatten_like(grad, ctx.meta[:nup])
             return none + tuple(gl) + (None,) * (len(ctx.meta) - nup)
