@@ -251,6 +251,13 @@ def run_ours(args):
                   "xw_interior_backward_u": n_loc * d * 4 + pts_call * 4 + n_loc * 4,
                   "xw_boundary_u": n_loc * d * 4 + pts_call * 4 + n_loc * 4}
     step_flops = (2 * (fl_["u_interior"] + fl_["u_boundary"]) + fl_["v_interior"]) * n_loc * L_T
+    traffic, traffic_src = None, None
+    try:       # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture, per launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tj["dram_bytes_per_point"][tj["entry_to_kernel"][dom_k]] * pts_call
+        traffic_src = tj["source"]
+    except Exception:
+        pass
     line = {"metric": "weak-loss+grad path-points/sec", "value": pp_step / (ms * 1e-3), "unit": "path-points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -259,7 +266,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "loss_u": last.get("lu"), "loss_v": last.get("lv")},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32_fma", "kernel": dom_k, "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fma_peak, "traffic": None,
+                         "frac": achieved / fma_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": bytes_call.get(dom_k),
                          "peak_source": "xw_fma_probe (FFMA chains) measured in this run; nominal 74.4",
                          "flops_per_point": fl_[dom_k], "points_per_launch": pts_call,
                          "step_frac": step_flops / (ms * 1e-3) / 1e12 / fma_peak,
