@@ -115,11 +115,13 @@ def evaluate(solver, domain, batch, phase):
     if phase == 'u':
         l = L.u(pu, pv, solver.u_net, X, XV, BX)
         l.backward(retain_graph=True)
-        out['grads'] = [p.grad.detach().clone().numpy() for p in solver.u_net.parameters()]
+        out['grads'] = [(p.grad if p.grad is not None else torch.zeros_like(p)).detach().clone().numpy()
+                        for p in solver.u_net.parameters()]
     else:
         l = L.v(pu, pv, X, XV)
         l.backward(retain_graph=True)
-        out['grads'] = [p.grad.detach().clone().numpy() for p in solver.v_net.parameters()]
+        out['grads'] = [(p.grad if p.grad is not None else torch.zeros_like(p)).detach().clone().numpy()
+                        for p in solver.v_net.parameters()]
     out['loss'] = float(l.item())
     out['u'] = pu.detach().numpy().copy()
     out['v'] = pv.detach().numpy().copy()

@@ -10,8 +10,10 @@ from oracle import closed_form as cf
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+def names(degenerate=False):
+    """regular cases; degenerate=True: the single-time-point interior groups (reference rank-2 shortcut)"""
+    alln = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in alln if ("single_time" in n) == degenerate]
 
 
 def load(name):

@@ -41,6 +41,8 @@ SPHERE_CASES = {
     "hourglass_d5_g2_reentry": ("NSphere_THourglass", 2, 3),
     "hourglass_d5_g4_reentry": ("NSphere_THourglass", 4, 3),
     "hourglass_d5_g18": ("NSphere_THourglass", 18, 3),
+    # group 0: single time point at T0 -> the reference's rank-2 shortcut and its [n, n] broadcasts
+    "cone_d5_g0_single_time": ("NSphere_TCone", 0, 3),
 }
 
 

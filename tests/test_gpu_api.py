@@ -126,3 +126,32 @@ def test_large_size_properties():
     h2 = sums_of(X[N // 2:], XV[N // 2:], BX[N // 2:])
     # path 0's time grid is shared, so the halves see the same grid
     assert np.allclose(h1 + h2, whole, rtol=1e-9, atol=1e-9 * np.abs(whole).max())
+
+
+def test_time_varying_domain_training_runs_on_gpu():
+    """BASELINE configs[2]: Ex4_3 problem on NSphere_TCone / NSphere_THourglass with boundary-path sampling:
+    a few outer iterations over all variable-length groups on the GPU (sampled by this package's own
+    samplers, which reproduce the reference's groups)"""
+    for domain in ("NSphere_TCone", "NSphere_THourglass"):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        p = xw.problems.cube_params(dim=5, N_r=300, N_b=300, alpha=10.0, shape_param=1.0, domain=domain, iterations=3)
+        prob = xw.problems.ex4_3(5)
+        s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, DEV,
+                               "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
+        hist = s.train()
+        assert len(hist["loss_u"]) == 3 and all(np.isfinite(v) for v in hist["loss_u"])
+        assert all(np.isfinite(v) for v in hist["L2"])
+        assert all(torch.isfinite(q).all() for q in s.u_net.parameters())
+
+
+@pytest.mark.parametrize("name", G.names(degenerate=True))
+def test_single_time_group_matches_golden_on_gpu(name):
+    case = G.load(name)
+    s, _ = make_solver(case, DEV)
+    z = case["z"]
+    for phase, gold_l, gold_g in (("u", float(z["loss_u"]), case["gu"]), ("v", float(z["loss_v"]), case["gv"])):
+        val, grads = eval_phase(s, case, phase, DEV)
+        assert abs(val.item() - gold_l) <= 1e-6 * abs(gold_l)
+        for a, b in zip(grads, gold_g):
+            assert G.rel(a, b) < 1e-6 or np.linalg.norm(b) == 0.0

@@ -46,7 +46,7 @@ def eval_phase(s, case, phase, device="cpu"):
     val = L.u(pu, pv, s.u_net, X, XV, BX) if phase == "u" else L.v(pu, pv, X, XV)
     val.backward()
     net = s.u_net if phase == "u" else s.v_net
-    return val, [q.grad.detach().cpu().numpy() for q in net.parameters()]
+    return val, [(q.grad if q.grad is not None else torch.zeros_like(q)).detach().cpu().numpy() for q in net.parameters()]
 
 
 @pytest.mark.parametrize("name", ["cube_d5_alpha1_randbias", "cube_d3_small_nets", "cube_d4_ex43", "cube_d3_rk4",
@@ -103,7 +103,7 @@ def test_hypercube_sampler_reproduces_reference_stream():
 
 def make_solver_for_rng(case):
     p = dict(case["params"])
-    p["domain"] = "Hypercube"
+    p["domain"] = case["meta"].get("domain_class", "Hypercube")
     prob = xw.problems.by_name(case["meta"]["funcs"], p["dim"])
     s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, "cpu",
                            "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
@@ -208,3 +208,53 @@ def test_test_function_cache_gives_the_same_training_step(emu):
         outs.append([q.detach().clone() for q in list(s.u_net.parameters()) + list(s.v_net.parameters())])
     for a, b in zip(*outs):
         assert G.rel(a.numpy(), b.numpy()) < 1e-5
+
+
+def test_single_time_group_matches_reference_golden(emu):
+    """first interior group of the sphere domains (one time point at T0): the reference's rank-2
+    shortcut + [n, n] broadcasts, reproduced on the host side"""
+    case = G.load("cone_d5_g0_single_time")
+    s, _ = make_solver(case)
+    z = case["z"]
+    for phase, gold_l, gold_g in (("u", float(z["loss_u"]), case["gu"]), ("v", float(z["loss_v"]), case["gv"])):
+        val, grads = eval_phase(s, case, phase)
+        assert abs(val.item() - gold_l) <= 1e-6 * abs(gold_l)
+        assert abs(val.components["I"].item() - float(z["I"])) <= 1e-6 * abs(float(z["I"]))
+        for a, b in zip(grads, gold_g):
+            assert G.rel(a, b) < 1e-6 or np.linalg.norm(b) == 0.0
+
+
+def test_sphere_samplers_reproduce_reference_groups():
+    """same seeds -> the group shapes / first times the unmodified reference produced (SURVEY Appendix B
+    protocol; the bit-for-bit comparison against the reference's samplers was done in the build container)"""
+    for name, golden in (("NSphere_TCone", "cone_d5_g2"), ("NSphere_THourglass", "hourglass_d5_g4_reentry")):
+        case = G.load(golden)
+        seed = case["meta"]["seed"]
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        s, _ = make_solver_for_rng(case)       # consumes the RNG exactly like the reference constructor
+        dom = s.new_domain()
+        pts = xw.Comb_loader(300, 300, dom, "cpu")
+        X, XV, BX = pts[case["meta"]["group"]]
+        z = case["z"]
+        assert torch.equal(X, torch.from_numpy(z["X"])) and torch.equal(XV, torch.from_numpy(z["XV"]))
+        assert torch.equal(BX, torch.from_numpy(z["BX"]))
+
+
+def test_training_iteration_on_cone_domain(emu):
+    """one outer iteration over every variable-length group of NSphere_TCone, including the
+    single-time-point group and the single-time boundary groups"""
+    case = G.load("cone_d5_g2")
+    s, _ = make_solver(case)
+    s.setup["N_r"], s.setup["N_b"] = 60, 60
+    torch.manual_seed(1)
+    np.random.seed(1)
+    dom = s.new_domain()
+    pts = xw.Comb_loader(60, 60, dom, "cpu")
+    assert len(pts) > 2
+    before = [q.detach().clone() for q in list(s.u_net.parameters()) + list(s.v_net.parameters())]
+    lu, lv = s.train_iteration(dom, pts)
+    assert torch.isfinite(lu) and torch.isfinite(lv)
+    after = list(s.u_net.parameters()) + list(s.v_net.parameters())
+    assert all(torch.isfinite(a).all() for a in after)
+    assert any(not torch.equal(a, b) for a, b in zip(before, after))

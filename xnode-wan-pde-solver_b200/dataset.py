@@ -10,6 +10,7 @@ host sampling + H2D of the repeated [N, L, C] tensors would dominate (SURVEY.md 
 """
 import math
 
+import numpy as np
 import torch
 
 from .paths import CollapsedPaths
@@ -138,10 +139,10 @@ def _ball_volume(dim, r):
 
 
 class _SphereDomain:
-    """time-varying ball domains of the reference (src/dataset.py:48-229): the weight func_w, its
-    in-kernel counterpart (loss.domain_spec) and the Monte-Carlo volume V are provided; the
-    variable-length group SAMPLERS (`interior`, `boundary`) are a later row of the scope table
-     -- batches sampled by the reference's own classes run through loss.u / loss.v."""
+    """time-varying ball domains of the reference (src/dataset.py:48-229).  Paths are groups of equal
+    length (float64, requires no grad here): a point stays in the domain only while |x| < radius(t).
+    Random numbers are drawn in the reference's order (numpy normal for the directions, numpy rand
+    for the radii, torch uniform for the time grid), so seeded runs reproduce its groups exactly."""
 
     def __init__(self, r: float, dim: int, T0: float, T: float, N_t: int, times=None):
         self.r, self.dim, self.T0, self.T, self.N_t = r, dim, T0, T, N_t
@@ -150,11 +151,29 @@ class _SphereDomain:
             times[0], times[-1] = T0, T
         self.times = times
 
-    def interior(self, N_r: int):
-        raise NotImplementedError("%s.interior: sphere-domain samplers are not part of this round" % type(self).__name__)
+    def surf(self, N: int):
+        """N points on the sphere of radius r, [dim, N] (normalised normal deviates)"""
+        z = np.random.normal(size=(self.dim, N))
+        return self.r * z / np.sqrt((z ** 2).sum(axis=0))
+
+    def _ball(self, N: int):
+        pts = self.surf(N)
+        pts *= np.random.rand(N) ** (1 / self.dim)
+        return pts
+
+    def _radius_scale(self, t):
+        raise NotImplementedError
 
     def boundary(self, N_b: int):
-        raise NotImplementedError("%s.boundary: sphere-domain samplers are not part of this round" % type(self).__name__)
+        """one single-time group per grid time with int(N_b * scale(t)^dim) points on the sphere of that time"""
+        groups = []
+        for t in self.times.numpy():
+            sc = self._radius_scale(t)
+            n = int(N_b * sc ** self.dim)
+            x = torch.from_numpy(self.surf(n) * sc).transpose(0, 1).unsqueeze(1)
+            if n != 0:
+                groups.append(torch.cat((t * torch.ones(n, 1, 1), x), 2))
+        return groups
 
     def bound_pad(self, x):
         raise NotImplementedError("bound_pad / fillt (evaluation from inside the domain) is not supported yet")
@@ -162,6 +181,25 @@ class _SphereDomain:
 
 class NSphere_TCone(_SphereDomain):
     """ball of radius r (1 - t)   (reference src/dataset.py:162-229)"""
+
+    def _radius_scale(self, t):
+        return 1 - t
+
+    def interior(self, N_r: int):
+        """a path lives on times[0:k) where k = number of grid times with |x| < r (1 - t); paths of equal k
+        form one group [n, k, C]; groups in ascending k"""
+        pts = self._ball(N_r)                                       # [dim, N_r]
+        grid = self.times.repeat(N_r, 1).unsqueeze(2)               # [N_r, N_t, 1]
+        groups = []
+        k = self.N_t
+        for t in self.times.numpy()[::-1]:
+            inside = np.sqrt(np.sum(pts ** 2, 0)) < self.r * (1 - t)
+            x = torch.from_numpy(pts[:, inside]).transpose(0, 1).unsqueeze(1).repeat(1, k, 1)
+            pts = np.delete(pts, inside, 1)
+            if x.shape[0] != 0:
+                groups.append(torch.cat((grid[:x.shape[0], :k], x), 2))
+            k -= 1
+        return groups[::-1]
 
     def func_w(self, x: torch.Tensor):
         return self.r * (1 - x[:, :, 0]) - x[:, :, 1:].pow(2).sum(2).sqrt()
@@ -173,6 +211,40 @@ class NSphere_TCone(_SphereDomain):
 
 class NSphere_THourglass(_SphereDomain):
     """ball of radius r ((T-T0) - t) for t <= (T-T0)/2 and r t afterwards (reference src/dataset.py:48-159)"""
+
+    def _radius_scale(self, t):
+        return (self.T - self.T0) - t if t < (self.T - self.T0) / 2 else t
+
+    def interior(self, N_r: int):
+        """every path is inside at T0, leaves when the ball shrinks below |x| and re-enters when it grows
+        back: it contributes a first segment (times before the exit) and, if it was ever outside, a second
+        segment (times after the re-entry) that gets one extra leading row at the exact entry time
+        t = |x| / r.  Segments of equal length are concatenated into groups, ascending length."""
+        pts = torch.from_numpy(self._ball(N_r)).transpose(0, 1)    # [N_r, dim] float64
+        grid = self.times.repeat(N_r, 1)                            # [N_r, N_t]
+        half = (self.T - self.T0) / 2
+        radius = torch.where(grid <= half, self.r * ((self.T - self.T0) - grid).double(), self.r * grid.double())
+        inside = pts.pow(2).sum(1).sqrt().unsqueeze(1) < radius     # [N_r, N_t]
+        full = torch.cat((grid.unsqueeze(2).double(), pts.unsqueeze(1).repeat(1, self.N_t, 1)), 2).to(torch.float64)
+        first, second = [], []
+        for k in range(N_r):
+            out = torch.nonzero(~inside[k]).flatten()
+            if out.numel() == 0:
+                first.append(full[k].unsqueeze(0))
+                continue
+            a, b = int(out[0]), self.N_t - int(out[-1]) - 1
+            kept = full[k, inside[k]]
+            first.append(kept[:a].unsqueeze(0))
+            seg = kept[a:a + b]
+            entry = torch.cat(((seg[0, 1:].pow(2).sum().sqrt() / self.r).view(1, 1), seg[0, 1:].unsqueeze(0)), dim=1)
+            second.append(torch.cat((entry, seg), 0).unsqueeze(0))
+
+        def grouped(segs):
+            out = {}
+            for sgm in sorted(segs, key=lambda z: z.shape[1]):
+                out.setdefault(sgm.shape[1], []).append(sgm)
+            return [torch.cat(v, 0) for _, v in sorted(out.items())]
+        return sorted(grouped(first) + grouped(second), key=lambda z: z.shape[1])
 
     def func_w(self, x: torch.Tensor):
         t = x[:, :, 0]

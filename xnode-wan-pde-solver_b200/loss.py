@@ -114,7 +114,63 @@ class loss:
                                 hotpath.as_f32(a).to(dev) if a is not None else None,
                                 hotpath.as_f32(bb).to(dev) if bb is not None else None)
 
+    def _single_time_group(self, phase, u_mod, v_mod, X, XV, border):
+        """Interior group with ONE time point at T0 (first group of the sphere domains).  The reference
+        returns rank-2 predictions there (src/model.py:89-91) and its loss then broadcasts [n]x[n,1]
+        into [n, n] (src/loss.py:65-72,79,84): reproduced here as the equivalent sums, in PyTorch on
+        the device -- there is no ODE and no path structure to accelerate (n points, a few kFLOP)."""
+        d = self.setup['dim']
+        lift, fin = u_mod.initial_layers, u_mod.final_linear
+        Xl = X.detach().clone().requires_grad_(True)
+        XVl = XV.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            U = fin(lift(u_mod.h(Xl[:, 0, :]).unsqueeze(1).double()))[:, 0]           # [n]
+            Vv = v_mod.net(XVl.double())[:, 0, 0]                                       # [n]
+            w = self.func_w(XVl)[:, 0]
+            Phi = Vv * w
+            du = torch.autograd.grad(U.sum(), Xl, retain_graph=True)[0][:, 0, 1:].to(X.dtype)
+            dphi = torch.autograd.grad(Phi.sum(), XVl, retain_graph=True)[0][:, 0, :].to(XV.dtype)
+            n = U.shape[0]
+            V = float(self.V)
+            h, f = self.h.to(U.dtype), self.f[:, 0].to(U.dtype)
+            A = self.a.matrix.to(du) if self.a.matrix is not None else None
+            q = du if A is None else du @ A.T                                           # sum_l a_kl du_l
+            s31 = (dphi[:, 1:] * q).sum(1).double()
+            s32 = ((du * self.b.vector.to(du)).sum(1).double().sum() * Phi.detach().sum()) if self.b.vector is not None else 0.0
+            cU = self.c.c0 + self.c.c1 * U
+            s1 = (V / n) * (U * Vv - h * Vv).sum()
+            s2 = (V / n) * (U.detach().sum() * dphi[:, 0].double().sum())
+            s3 = (V / n) * (n * s31.sum() + s32 + n * (cU * U * Phi).sum() + f.sum() * Phi.sum())
+            I = s1 - (s2 - s3)
+            S = V * (Vv ** 2).sum() / n
+            integ = torch.log(I ** 2) - torch.log(S)
+            comps = dict(I=I.detach(), S=S.detach())
+            if phase == "u":
+                init = ((U.unsqueeze(0) - h.unsqueeze(1)) ** 2).mean()
+                g = self.g.to(U.dtype)
+                kb = u_mod.start_kind(border)
+                sb = u_mod.initial_scalar(border.detach(), kb).double()
+                ub = fin(lift(sb.unsqueeze(1)))[:, 0]
+                if border.shape[1] == 1 and kb == "h":
+                    bdry = ((ub.unsqueeze(0) - g[:, 0].unsqueeze(1)) ** 2).mean()       # rank-2 boundary: [nb, nb] too
+                else:
+                    bdry = ((ub - g[:, 0]) ** 2).mean()
+                val = integ + self.alpha * (init + bdry)
+                comps.update(init=init.detach(), bdry=bdry.detach())
+                side = U.sum()
+            else:
+                val = -integ
+                side = Phi.sum()
+            if self.side_effect:              # the helper backward calls of src/loss.py:55,60 also fill .grad
+                val = val + (side - side.detach())
+        val.components = comps
+        return val
+
     def _eval(self, phase, y_output_u, y_output_v, X, XV, border):
+        if not isinstance(y_output_u, LazyPrediction) and X.shape[1] == 1 and isinstance(y_output_v, LazyPrediction):
+            v_mod = y_output_v.net
+            u_mod = getattr(y_output_u, "_xw_net", None) or self._u_module
+            return self._single_time_group(phase, u_mod, v_mod, X, XV, border)
         u_mod, v_mod = self._nets(y_output_u, y_output_v)
         batch = self._batch(u_mod, X, XV, border)
         spec = u_mod.spec(v_mod)
@@ -127,8 +183,11 @@ class loss:
                                  side_effect=self.side_effect, vcache=vbuf, vmode=vmode)
 
     # ------------------------------------------------------------------------------ reference API
+    _u_module = None
+
     def u(self, y_output_u, y_output_v, u_net, X, XV, border):
         """loss_u = int + alpha*(init + bdry)   (reference src/loss.py:92-93)"""
+        self._u_module = unwrap(u_net)
         return self._eval("u", y_output_u, y_output_v, X, XV, border)
 
     def v(self, y_output_u, y_output_v, X, XV):

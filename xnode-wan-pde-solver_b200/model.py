@@ -206,4 +206,6 @@ class NeuralODE(nn.Module):
     def forward(self, inputs: torch.Tensor):
         if torch.is_grad_enabled() and not (inputs.shape[1] == 1):
             return LazyPrediction(self, inputs, "u")
-        return self.evaluate(inputs)
+        out = self.evaluate(inputs)
+        out._xw_net = self            # lets loss.v find the module for the single-time-point group
+        return out

@@ -167,6 +167,7 @@ class NODE_WAN_solver:
                            xv=None, tv_off=0, tv_sn=0, tv_sl=0, xv_off=0, xv_sn=0, xv_sl=0)
             vbuf = self._vc_buf = _hp.vcache_buffer(_hp._lib.get(), um.spec(vm), bt, datau.device)
         Loss.vcache = (vbuf, vmode)
+        Loss._u_module = self.u_net.module
         if phase == "u":
             val = Loss.u(prediction_u, prediction_v, self.u_net, datau, datav, bdata)
             val.backward()
