@@ -144,6 +144,11 @@ int xw_interior_backward_v(const xw_dims* dims, const xw_domain* dom, const floa
  * dependent-chain FFMA blocks on every SM and returns the FLOP count in *flops_host. */
 int xw_fma_probe(int variant, int iters, double* flops_host, void* stream);
 
+/* tcgen05 self-check (groundwork for the tensor-core variant of the Hv x Hv contractions):
+ * D[128 x N] = A[128 x K] * B[N x K]^T with kind::tf32 MMAs, accumulator in TMEM; terms = 1 plain TF32,
+ * 3 = 3xTF32 error compensation.  K multiple of 8 (<= 64), N multiple of 16 (<= 64). */
+int xw_umma_probe(const float* A, const float* B, float* D, int K, int N, int terms, int* err_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

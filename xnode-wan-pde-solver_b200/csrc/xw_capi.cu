@@ -5,6 +5,7 @@
 // product package.
 #include "../../include/xnode_wan_b200.h"
 #include "xw_kernels.cuh"
+#include "xw_umma.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -569,5 +570,20 @@ extern "C" int xw_fma_probe(int variant, int iters, double* flops_host, void* st
     else k_fma_probe<1><<<grid, block, 0, (cudaStream_t)stream>>>(iters, sink, 1.f);
     if (flops_host) *flops_host = 2.0 * 16 * 8 * (double)iters * (double)grid * block;
     return check_launch("k_fma_probe");
+#endif
+}
+
+// tcgen05 probe: D[128 x N] = A[128 x K] * B[N x K]^T on the 5th-gen tensor cores (kind::tf32),
+// terms = 1 (plain TF32) or 3 (3xTF32 error-compensated).  err_dev[0] != 0: a bounded wait expired.
+extern "C" int xw_umma_probe(const float* A, const float* B, float* D, int K, int N, int terms, int* err_dev, void* stream) {
+#ifdef XW_EMU
+    (void)A; (void)B; (void)D; (void)K; (void)N; (void)terms; (void)err_dev; (void)stream;
+    return fail("xw_umma_probe needs a CUDA device");
+#else
+    if (K % 8 || K < 8 || K > 64 || N % 16 || N < 16 || N > 64 || (terms != 1 && terms != 3)) return fail("bad probe shape");
+    const size_t smem = (size_t)(2 * 128 * K + 2 * N * K) * 4 + 64;
+    if (XW_SET_SMEM(xw::umma::k_umma_probe, smem)) return 1;
+    xw::umma::k_umma_probe<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, terms, err_dev);
+    return check_launch("k_umma_probe");
 #endif
 }
