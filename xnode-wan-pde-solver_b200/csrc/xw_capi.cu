@@ -580,10 +580,20 @@ extern "C" int xw_umma_probe(const float* A, const float* B, float* D, int K, in
     (void)A; (void)B; (void)D; (void)K; (void)N; (void)terms; (void)err_dev; (void)stream;
     return fail("xw_umma_probe needs a CUDA device");
 #else
-    if (K % 8 || K < 8 || K > 64 || N % 16 || N < 16 || N > 64 || (terms != 1 && terms != 3)) return fail("bad probe shape");
+    if (terms < 0) {   // transposed (weight-gradient shaped) product: A = P[128 x K], B = Q[128 x N], D[128 x N] = P^T Q (rows >= K are zero)
+        terms = -terms;
+        if (K % 4 || K < 4 || K > 128 || N % 8 || N < 8 || N > 64 || (terms != 1 && terms != 3)) return fail("bad probe shape");
+        const size_t smem_t = (size_t)(2 * 32 * 128 * 4 + 2 * N * 128) * 4 + 64;
+        if (XW_SET_SMEM(xw::umma::k_umma_probe_t, smem_t)) return 1;
+        xw::umma::k_umma_probe_t<<<1, 128, smem_t, (cudaStream_t)stream>>>(A, B, D, K, N, terms, err_dev, getenv("XW_UMMA_VARIANT") ? atoi(getenv("XW_UMMA_VARIANT")) : 0);
+        return check_launch("k_umma_probe_t");
+    }
+    const int ts = terms >= 10;                        /* 11 / 13: A operand from tensor memory */
+    if (ts) terms -= 10;
+    if (K % 8 || K < 8 || K > 64 || N % 8 || N < 8 || N > 64 || (terms != 1 && terms != 3)) return fail("bad probe shape");
     const size_t smem = (size_t)(2 * 128 * K + 2 * N * K) * 4 + 64;
     if (XW_SET_SMEM(xw::umma::k_umma_probe, smem)) return 1;
-    xw::umma::k_umma_probe<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, terms, err_dev);
+    xw::umma::k_umma_probe<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, terms, err_dev, ts);
     return check_launch("k_umma_probe");
 #endif
 }

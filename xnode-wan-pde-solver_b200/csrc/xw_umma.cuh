@@ -27,14 +27,30 @@ __device__ __forceinline__ uint64_t smem_desc(const void* p, int lbo_bytes, int 
     d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
     return d;                                            // layout type [61,64) = 0: no swizzle
 }
-__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor: fp32 accumulate, tf32 x tf32; a_mn / b_mn = 1: that operand is MN-major
+// (the 16-byte chunk runs along M / N and the 8 rows of a core matrix are 8 consecutive k)
+__device__ __forceinline__ uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 8 consecutive columns of this thread's TMEM lane  <-  registers
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"((uint32_t)__cvta_generic_to_shared(mbar)) : "memory");
@@ -82,7 +98,7 @@ __device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__flo
 
 // D[128 x N] = A[128 x K] * B[N x K]^T  (row-major fp32 in global memory), N multiple of 16 <= 64, K multiple of 8
 // terms = 1: plain TF32, terms = 3: 3xTF32.  err[0] != 0 if a bounded wait expired.
-__global__ void __launch_bounds__(128) k_umma_probe(const float* A, const float* B, float* D, int K, int N, int terms, int* err) {
+__global__ void __launch_bounds__(128) k_umma_probe(const float* A, const float* B, float* D, int K, int N, int terms, int* err, int ts) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* a_hi = reinterpret_cast<float*>(smem_raw);
     float* a_lo = a_hi + 128 * K;
@@ -108,12 +124,35 @@ __global__ void __launch_bounds__(128) k_umma_probe(const float* A, const float*
     }
     if (tid == 0) mbar_init(mbar, 1);
     fence_smem_to_async();
-    if (warp == 0) tmem_alloc(slot, 64);
+    if (warp == 0) tmem_alloc(slot, 256);
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tbase = *slot;
-    if (tid == 0) {
+    if (ts) {                                            // A (hi at columns 64.., lo at 128..) into tensor memory
+        const uint32_t lane_base = tbase + ((uint32_t)(32 * warp) << 16);
+        for (int c = 0; c < K / 8; ++c) {
+            float hi[8], lo[8];
+            for (int e = 0; e < 8; ++e) { const float v = A[(size_t)tid * K + 8 * c + e]; hi[e] = tf32_hi(v); lo[e] = v - hi[e]; }
+            tmem_st8(lane_base + 64 + 8 * c, hi);
+            tmem_st8(lane_base + 128 + 8 * c, lo);
+        }
+        tmem_wait_st();
+        fence_before();
+        __syncthreads();
+        fence_after();
+    }
+    if (tid == 0 && ts) {
+        const uint32_t idesc = idesc_tf32(128, N);
+        uint32_t acc = 0;
+        for (int t = 0; t < terms; ++t)
+            for (int ks = 0; ks < K / 8; ++ks) {
+                mma_tf32_ts(tbase, tbase + (t == 1 ? 128 : 64) + 8 * ks,
+                            smem_desc((t == 2 ? b_lo : b_hi) + (size_t)(2 * ks) * N * 4, N * 16, 128), idesc, acc);
+                acc = 1;
+            }
+        commit(mbar);
+    } else if (tid == 0) {
         const uint32_t idesc = idesc_tf32(128, N);
         const int lbo_a = 128 * 16, lbo_b = N * 16, sbo = 128;
         uint32_t acc = 0;
@@ -136,7 +175,76 @@ __global__ void __launch_bounds__(128) k_umma_probe(const float* A, const float*
             float v[16];
             tmem_ld16(tbase + ((uint32_t)(32 * warp) << 16) + n0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) D[(size_t)tid * N + n0 + i] = v[i];
+            for (int i = 0; i < 16; ++i) if (n0 + i < N) D[(size_t)tid * N + n0 + i] = v[i];
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tbase, 256);
+}
+
+// transposed product on the SAME operand images: out[o][i] = sum_r P[r][o] Q[r][i]  (r = 0..127), the
+// shape of the weight-gradient contraction.  P, Q are stored exactly as K-major A operands
+// ([chunk of 4 units][row] with 16-byte cells) and read back as MN-major operands: unit chunk
+// stride = SBO, 8-row group stride = 128 bytes (one MMA = one 8-row group).
+__global__ void __launch_bounds__(128) k_umma_probe_t(const float* P, const float* Q, float* out, int MO, int NI, int terms, int* err, int variant) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* p_hi = reinterpret_cast<float*>(smem_raw);          // 32 chunks x 128 rows x 4 (M = 128: zero beyond MO)
+    float* p_lo = p_hi + 32 * 128 * 4;
+    float* q_hi = p_lo + 32 * 128 * 4;
+    float* q_lo = q_hi + NI * 128;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(q_lo + NI * 128);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int c = 0; c < 32; ++c) {
+        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+        if (4 * c < MO) {
+            const float4 v = *reinterpret_cast<const float4*>(P + (size_t)tid * MO + 4 * c);
+            hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+            lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+        }
+        *reinterpret_cast<float4*>(p_hi + chunk_off_floats(128, c, tid)) = hi;
+        *reinterpret_cast<float4*>(p_lo + chunk_off_floats(128, c, tid)) = lo;
+    }
+    for (int c = 0; c < NI / 4; ++c) {
+        float4 hi, lo;
+        const float4 v = *reinterpret_cast<const float4*>(Q + (size_t)tid * NI + 4 * c);
+        hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+        *reinterpret_cast<float4*>(q_hi + chunk_off_floats(128, c, tid)) = hi;
+        *reinterpret_cast<float4*>(q_lo + chunk_off_floats(128, c, tid)) = lo;
+    }
+    if (tid == 0) mbar_init(mbar, 1);
+    fence_smem_to_async();
+    if (warp == 0) tmem_alloc(slot, 64);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tbase = *slot;
+    if (tid == 0) {
+        const uint32_t idesc = idesc_tf32(128, NI, (variant & 2) ? 0 : 1, (variant & 4) ? 0 : 1);
+        const int lbo = (variant & 1) ? 128 * 16 : 128, sbo = (variant & 1) ? 128 : 128 * 16;
+        uint32_t acc = 0;
+        for (int t = 0; t < terms; ++t) {
+            const float* pa = t == 1 ? p_lo : p_hi;
+            const float* pb = t == 2 ? q_lo : q_hi;
+            for (int ks = 0; ks < 16; ++ks) {              // 8 rows per MMA
+                mma_tf32(tbase, smem_desc(pa + ks * 32, lbo, sbo), smem_desc(pb + ks * 32, lbo, sbo), idesc, acc);
+                acc = 1;
+            }
+        }
+        commit(mbar);
+    }
+    const bool ok = mbar_wait(mbar, 0);
+    if (!ok && tid == 0) err[0] = 1;
+    fence_after();
+    if (ok) {
+        for (int n0 = 0; n0 < NI; n0 += 8) {               // NI multiple of 8: read 16 columns, keep what exists
+            float v[16];
+            if (n0 % 16 == 0) {
+                tmem_ld16(tbase + ((uint32_t)(32 * warp) << 16) + n0, v);
+                for (int i = 0; i < 16; ++i) if (n0 + i < NI) out[(size_t)tid * NI + n0 + i] = v[i];
+            }
         }
     }
     fence_before();
