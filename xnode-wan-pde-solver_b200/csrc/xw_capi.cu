@@ -6,6 +6,7 @@
 #include "../../include/xnode_wan_b200.h"
 #include "xw_kernels.cuh"
 #include "xw_umma.cuh"
+#include "xw_vnet_tc.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -162,6 +163,30 @@ bool use_point_kernels() {
     const char* e = getenv("XW_VNET_IMPL");
     return e && strcmp(e, "points") == 0;
 }
+#ifndef XW_EMU
+// tensor-core backward: one 128-point tile per CTA iteration, one CTA per SM (tensor memory: 512 columns)
+bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
+int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
+    const int kin = xw::tc::kin_of(m->d);
+    p->smem = (size_t)(4 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64 + 4 * xw::tc::TIMG + xw::tc::KP * (xw::tc::KP + kin) + 512) * 4 + 64;
+    if (p->smem > device()->smem_optin) return fail("tensor-core v-net backward needs %zu B shared memory (> %zu)", p->smem, device()->smem_optin);
+    const long long ntiles = ((long long)n * L + 127) / 128;
+    p->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms));
+    p->scratch_bytes = align_up((size_t)p->grid * std::max(m->nv, 1) * 13 * 128 * 16, 256);
+    p->part_bytes = align_up((size_t)p->grid * xw::VLayout(m->d, m->Hv).size * 4, 256);
+    return 0;
+}
+#endif
+// XW_VNET_IMPL: "tc" (default on the device build: tcgen05 3xTF32 kernels), "tile" (FP32 FFMA2 tile engine),
+// "points" (generation 1, one thread per point)
+bool use_tc_kernels() {
+#ifdef XW_EMU
+    return false;
+#else
+    const char* e = getenv("XW_VNET_IMPL");
+    return !e || strcmp(e, "tc") == 0;
+#endif
+}
 size_t smem_vnet_bwd(const xw_dims* m, int block) {
     using S = xw::VSmem<kHV>;
     const int nw = block / 32;
@@ -312,6 +337,12 @@ size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
     VtileBwdPlan pv;
     if (plan_vtile_bwd(m, n, L, &pv)) return 0;
     bwd_v = std::max(bwd_v, pv.scratch_bytes + pv.part_bytes);
+#ifndef XW_EMU
+    if (vtc_bwd_ok(m)) {
+        if (plan_vtc_bwd(m, n, L, &pv)) return 0;
+        bwd_v = std::max(bwd_v, pv.scratch_bytes + pv.part_bytes);
+    }
+#endif
     return std::max(fwd, std::max(bwd_u, bwd_v)) + 1024;
 }
 
@@ -400,6 +431,22 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
     t.c0 = coef->c0; t.c1 = coef->c1; t.u = ubuf; t.h = h; t.f = f; t.sums = sums; t.cot_u = cot_u; t.cot_v = cot_v;
     t.vcache = vcache_mode == 1 ? vcache : nullptr;
+#ifndef XW_EMU
+    if (use_tc_kernels() && xw::tc::kin_of(m->d) <= 224) {
+        // generation 3: hidden-layer contractions on the tensor cores (tcgen05, 3xTF32), 64 points per tile
+        const int kin = xw::tc::kin_of(m->d), KA = std::max(kin, xw::tc::KP);
+        const int need = xw::tc::A_COL + 2 * KA, cols = need <= 256 ? 256 : 512;
+        size_t sm = (size_t)(2 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64) * 4 + 4 * 32 * 8 + 64;
+        // tensor memory holds 512 columns per SM: keep the resident CTAs at 512 / cols by sizing shared memory
+        const int per_sm = 512 / cols;
+        sm = std::max(sm, (size_t)(device()->smem_optin / (per_sm + 1) + 1024));
+        if (XW_SET_SMEM(xw::tc::k_vnet_tc_fwd, sm)) return 1;
+        const long long nt = ((long long)n * L + 63) / 64;
+        const int g3 = (int)std::max<long long>(1, std::min<long long>(nt, (long long)device()->sms * per_sm));
+        xw::tc::k_vnet_tc_fwd<<<g3, 128, sm, (cudaStream_t)stream>>>(t, cols);
+        return XW_CHECK_LAUNCH("k_vnet_tc_fwd");
+    }
+#endif
     using VT = xw::VTile<kHV, kQR, kNH>;
     const size_t tsmem = smem_vtile_fwd(m->d);
     if (tsmem > device()->smem_optin) return fail("tiled v-net forward needs %zu B shared memory (> %zu): dim too large", tsmem, device()->smem_optin);
@@ -456,6 +503,21 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
     if (!dom || !theta_v || !xv || !xv->t || !xv->x || !cot_v || !coefs_dev || !grad_v || !workspace)
         return fail("NULL pointer argument");
+#ifndef XW_EMU
+    if (use_tc_kernels() && vtc_bwd_ok(m)) {
+        VtileBwdPlan pl;
+        if (plan_vtc_bwd(m, n, L, &pl)) return 1;
+        if (workspace_bytes < pl.scratch_bytes + pl.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, pl.scratch_bytes + pl.part_bytes);
+        xw::VtileBwdArgs t{};
+        t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
+        t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
+        t.cot = cot_v; t.coefs = coefs_dev; t.scratch = (float*)workspace; t.gpart = (float*)((char*)workspace + pl.scratch_bytes);
+        if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd, pl.smem)) return 1;
+        xw::tc::k_vnet_tc_bwd<<<pl.grid, 128, pl.smem, (cudaStream_t)stream>>>(t);
+        if (XW_CHECK_LAUNCH("k_vnet_tc_bwd")) return 1;
+        return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
+    }
+#endif
     if (!use_point_kernels()) {
         VtileBwdPlan pl;
         if (plan_vtile_bwd(m, n, L, &pl)) return 1;

@@ -1,0 +1,534 @@
+// xw_vnet_tc.cuh -- test-function net on the 5th-generation tensor cores (generation 3 of the v-net kernels).
+//
+// The hidden layers of v_phi (reference src/model.py:37-47: the SAME Hv x Hv matrix nv times) are
+// [rows x Hv] x [Hv x Hv] contractions.  Here they run as tcgen05.mma kind::tf32 with 3xTF32 error
+// compensation (x = x_hi + x_lo, both exactly representable in TF32 up to the hardware's truncation of
+// x_lo;  a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, accumulated in fp32): measured 1e-6 against fp64 on
+// B200 (tools/umma_probe.py), i.e. the fp32 tolerance of the path is kept.
+//
+//   A operand (activations): TENSOR MEMORY, lane = row, one 32-bit column per hidden unit, written by
+//                            the thread that owns the row (tcgen05.st) -- no shared-memory round trip,
+//                            no bank conflicts, no proxy fence;
+//   B operand (weights)    : shared memory, canonical K-major no-swizzle image [k/4][n][4], staged once
+//                            per CTA as a hi and a lo image; the bias rides in input column 50, which the
+//                            value rows set to 1;
+//   D accumulator          : tensor memory, read back with tcgen05.ld by the owner of the row.
+//
+// One elected thread issues the 21 MMAs of a layer (3 terms x 7 k-steps of 8) and commits them to an
+// mbarrier; the 128 row owners wait on it, apply relu (and the relu mask to the tangent row), split into
+// hi/lo and store the next layer's A operand.  Every wait is bounded (trap instead of hang).
+#pragma once
+#ifndef XW_EMU
+#include "xw_umma.cuh"
+
+namespace xw {
+namespace tc {
+
+constexpr int HV = 50;          // compiled capacity of the hidden width
+constexpr int KP = 56;          // padded contraction length (units 0..49, bias column 50, zeros)
+constexpr int NP = 56;          // MMA N (output units, padded)
+constexpr int BIASC = 50;
+constexpr int D_COL = 0;        // accumulator columns [0, 64)
+constexpr int A_COL = 64;       // A_hi at [64, 64 + KA), A_lo at [64 + KA, 64 + 2 KA)
+
+XW_HD constexpr int kin_of(int d) { return (d + 2 + 7) / 8 * 8; }      // (t, x, 1) padded to k-steps of 8
+
+// B-operand image (K-major, no swizzle): element (k, n) of a [K x NP] operand
+__device__ __forceinline__ int b_off(int k, int n) { return (k >> 2) * (NP * 4) + (n >> 3) * 32 + (n & 7) * 4 + (k & 3); }
+__device__ __forceinline__ void put_split(float* hi, float* lo, int off, float v) {
+    const float h = umma::tf32_hi(v);
+    hi[off] = h;
+    lo[off] = v - h;
+}
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* mbar, uint32_t& parity) {
+    if (!umma::mbar_wait(mbar, parity, 1 << 24)) __trap();
+    parity ^= 1u;
+}
+
+struct WImages {
+    float *wh_hi, *wh_lo;       // [KP x NP]  B[n = o][k = i] = Wh[o][i], k = 50: bh[o]
+    float *wht_hi, *wht_lo;     // [KP x NP]  B[n = i][k = o] = Wh[o][i]            (backward only, else NULL)
+    float *wi_hi, *wi_lo;       // [kin x NP] B[n = o][k = c] = Wi[o][c], k = C: bi[o]
+    float* wz;                  // [64]: Wz[o] (zero padded), wz[KP] = bz
+};
+
+__device__ void stage_images(const WImages& w, const float* XW_RESTRICT th, int d, int Hvr, int kin) {
+    const VLayout g(d, Hvr);
+    const int C = d + 1;
+    for (int i = threadIdx.x; i < KP * NP; i += blockDim.x) {
+        w.wh_hi[i] = 0.f; w.wh_lo[i] = 0.f;
+        if (w.wht_hi) { w.wht_hi[i] = 0.f; w.wht_lo[i] = 0.f; }
+    }
+    for (int i = threadIdx.x; i < kin * NP; i += blockDim.x) { w.wi_hi[i] = 0.f; w.wi_lo[i] = 0.f; }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) w.wz[i] = i < Hvr ? th[g.Wz + i] : (i == KP ? th[g.bz] : 0.f);
+    __syncthreads();
+    for (int e = threadIdx.x; e < Hvr * Hvr; e += blockDim.x) {
+        const int o = e / Hvr, i = e - o * Hvr;
+        const float v = th[g.Wh + e];
+        put_split(w.wh_hi, w.wh_lo, b_off(i, o), v);
+        if (w.wht_hi) put_split(w.wht_hi, w.wht_lo, b_off(o, i), v);
+    }
+    for (int e = threadIdx.x; e < Hvr * C; e += blockDim.x) {
+        const int o = e / C, c = e - o * C;
+        put_split(w.wi_hi, w.wi_lo, b_off(c, o), th[g.Wi + e]);
+    }
+    for (int o = threadIdx.x; o < Hvr; o += blockDim.x) {
+        put_split(w.wh_hi, w.wh_lo, b_off(BIASC, o), th[g.bh + o]);
+        put_split(w.wi_hi, w.wi_lo, b_off(C, o), th[g.bi + o]);
+    }
+    umma::fence_smem_to_async();
+    __syncthreads();
+}
+
+// D[128 x NP] = A[128 x 8*ksteps] * B^T, A from tensor memory (hi / lo column blocks), B images in smem
+__device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tA_hi, uint32_t tA_lo, const float* b_hi, const float* b_lo,
+                                             int ksteps, uint32_t idesc) {
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {                       // small terms first
+        const uint32_t ta = t == 0 ? tA_lo : tA_hi;
+        const float* pb = t == 1 ? b_lo : b_hi;
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+            umma::mma_tf32_ts(tD, ta + 8 * ks, umma::smem_desc(pb + ks * (2 * NP * 4), NP * 16, 128), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+// split 56 fp32 values into the hi / lo A operand of this thread's row
+__device__ __forceinline__ void store_a_row(uint32_t lane_addr, int KA, const float (&v)[KP]) {
+    uint32_t r[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+    umma::tmem_st56(lane_addr + A_COL, r);
+#pragma unroll
+    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i] - __uint_as_float(r[i]));
+    umma::tmem_st56(lane_addr + A_COL + KA, r);
+}
+
+// =============================================================================================
+// interior forward over all points: v, dv/dt (forward-mode tangent), weak-form integrands, seeds.
+// A tile is 64 points = 128 rows: lanes 0..15 of warp w own the VALUE rows of points 16w..16w+15,
+// lanes 16..31 the TANGENT rows of the same points (relu masks travel by warp shuffle).
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_vnet_tc_fwd(VtileFwdArgs a, int tmem_cols) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = a.d + 1, kin = kin_of(a.d), KA = kin > KP ? kin : KP;
+    WImages w;
+    w.wh_hi = reinterpret_cast<float*>(smem_raw);
+    w.wh_lo = w.wh_hi + KP * NP;
+    w.wht_hi = nullptr; w.wht_lo = nullptr;
+    w.wi_hi = w.wh_lo + KP * NP;
+    w.wi_lo = w.wi_hi + kin * NP;
+    w.wz = w.wi_lo + kin * NP;
+    double* red = reinterpret_cast<double*>(w.wz + 64);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 4 * 32);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_tan = lane >= 16;
+    stage_images(w, a.theta, a.d, a.Hvr, kin);
+    if (tid == 0) umma::mbar_init(mbar, 1);
+    if (warp == 0) umma::tmem_alloc(slot, tmem_cols);
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tbase = *slot;
+    const uint32_t lane_addr = tbase + ((uint32_t)(32 * warp) << 16);
+    const uint32_t idesc = umma::idesc_tf32(128, NP);
+    uint32_t parity = 0;
+    const long long npts = (long long)a.n * a.L;
+    const long long ntiles = (npts + 63) / 64;
+    const int L = a.L;
+    double accs[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const long long p = tix * 64 + 16 * warp + (lane & 15);
+        const bool valid = p < npts;
+        const long long n = valid ? p / L : 0;
+        const int l = (int)(p - n * L);
+        const float* xr = a.p.x + n * a.p.x_sn + (long long)l * a.p.x_sl;
+        const float tval = valid ? a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl] : 0.f;
+        // ---- input rows: value (t, x, 1), tangent d/dt = e_0 ----------------------------------
+#pragma unroll 1
+        for (int c8 = 0; c8 < kin; c8 += 8) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = c8 + e;
+                float v = 0.f;
+                if (is_tan) v = idx == 0 ? 1.f : 0.f;
+                else if (valid) v = idx == 0 ? tval : (idx <= a.d ? xr[idx - 1] : (idx == C ? 1.f : 0.f));
+                hi[e] = umma::tf32_hi(v);
+                lo[e] = v - hi[e];
+            }
+            umma::tmem_st8(lane_addr + A_COL + c8, hi);
+            umma::tmem_st8(lane_addr + A_COL + KA + c8, lo);
+        }
+        umma::tmem_wait_st();
+        umma::fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after();
+            issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
+            umma::commit(mbar);
+        }
+        float h[KP];
+        mbar_wait_or_trap(mbar, parity);
+        umma::fence_after();
+        umma::tmem_ld56(lane_addr + D_COL, h);
+        // ---- hidden layers -------------------------------------------------------------------
+#pragma unroll 1
+        for (int layer = 0; layer < a.nv; ++layer) {
+            uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+            for (int o = 0; o < 32; ++o) m0 |= (h[o] > 0.f ? 1u : 0u) << o;
+#pragma unroll
+            for (int o = 32; o < HV; ++o) m1 |= (h[o] > 0.f ? 1u : 0u) << (o - 32);
+            m0 = __shfl_sync(0xffffffffu, m0, lane & 15);      // the value row's mask, for both rows of the point
+            m1 = __shfl_sync(0xffffffffu, m1, lane & 15);
+#pragma unroll
+            for (int o = 0; o < 32; ++o) h[o] = ((m0 >> o) & 1u) ? h[o] : 0.f;
+#pragma unroll
+            for (int o = 32; o < HV; ++o) h[o] = ((m1 >> (o - 32)) & 1u) ? h[o] : 0.f;
+            h[BIASC] = is_tan ? 0.f : 1.f;
+#pragma unroll
+            for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
+            store_a_row(lane_addr, KA, h);
+            umma::tmem_wait_st();
+            umma::fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after();
+                issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wh_hi, w.wh_lo, KP / 8, idesc);
+                umma::commit(mbar);
+            }
+            mbar_wait_or_trap(mbar, parity);
+            umma::fence_after();
+            umma::tmem_ld56(lane_addr + D_COL, h);
+        }
+        // ---- tanh + output layer ---------------------------------------------------------------
+        float pv = 0.f, pt = 0.f;
+#pragma unroll
+        for (int o = 0; o < HV; ++o) {
+            const float wzo = w.wz[o];
+            const float y = tanh_fast(h[o]);
+            const float s = wzo * (1.f - y * y);
+            const float sv = __shfl_sync(0xffffffffu, s, lane & 15);
+            pv = fmaf(wzo, y, pv);
+            pt = fmaf(sv, h[o], pt);
+        }
+        const float dv_t = __shfl_sync(0xffffffffu, pt, (lane & 15) + 16);
+        if (!is_tan && valid) {
+            const float v = pv + w.wz[KP];
+            const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
+            float cu, cv;
+            weak_point_terms(v, dv_t, W.w, W.dw_t, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, a.c0, a.c1, accs, cu, cv);
+            a.cot_u[p] = cu;
+            a.cot_v[p] = cv;
+            if (a.vcache) { f4 cch; cch.x = v; cch.y = dv_t; cch.z = W.w; cch.w = W.dw_t; st4(a.vcache + 4 * p, cch); }
+        }
+    }
+    const int idx[4] = {0, 1, 2, 3};
+    block_sum_to_global<4>(accs, red, a.sums, idx);
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tbase, tmem_cols);
+}
+
+
+// =============================================================================================
+// v net backward on the tensor cores:  parameter gradients of sum_p G[p] v[p],  G = k0*cot_v + k1*v + k2*w
+//
+// A tile is 128 points, thread = point = TMEM lane.  Per tile:
+//   forward : input layer + nv hidden layers as in the forward kernel (value rows only); the post-relu
+//             activations r_0..r_{nv-1} are parked in a per-CTA scratch (global memory, L2 resident,
+//             each thread re-reads exactly what it wrote);
+//   reverse : for k = nv..1   delta_k -> A operand (tensor memory) AND its transpose into shared memory;
+//             r_{k-1} (with a ones column for the bias) transposed into shared memory;
+//             R-op  delta_{k-1} = relu'(r_{k-1}) . (delta_k Wh)      [128 x 56] x [56 x 56]   (A from TMEM)
+//             P-op  dWh += delta_k^T r_{k-1}                         [56 x 128] x [128 x 56]  (both from smem,
+//                   K = the 128 points; the accumulator lives in tensor memory for the whole tile);
+//   input   : dWi += delta_0^T (t, x, 1) the same way;
+//   flush   : threads 0..55 add their accumulator rows (dWh | dbh | dWi | dbi) into an fp32 image in
+//             shared memory, so that no tensor-core accumulator ever sums more than one tile.
+// The transposed images are ordinary K-major operands ([k/4][row][4], chunk stride padded to 228 floats:
+// the 32 lanes of a warp hit 32 different banks with their scalar stores).
+// =============================================================================================
+constexpr int TCS = 228;                     // chunk stride of the transposed images (floats)
+constexpr int TIMG = 32 * TCS;               // one transposed image: 128 points = 32 chunks
+constexpr int WH_COL = 192;                  // dWh accumulator columns [192, 248)
+constexpr int WI_COL = 256;                  // dWi accumulator columns [256, 256 + kin)
+
+__device__ __forceinline__ int t_off(int row, int r) { return (r >> 2) * TCS + (row >> 3) * 32 + (row & 7) * 4 + (r & 3); }
+
+// out[m][n] (+)= sum_{r<128} A^T-image[m][r] * B^T-image[n][r]   (3xTF32, 16 k-steps of 8 points)
+__device__ __forceinline__ void issue_pop(uint32_t tD, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
+                                          uint32_t idesc, uint32_t accumulate) {
+    uint32_t acc = accumulate;
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+        const float* pa = t == 0 ? a_lo : a_hi;
+        const float* pb = t == 1 ? b_lo : b_hi;
+#pragma unroll 1
+        for (int ks = 0; ks < 16; ++ks) {
+            umma::mma_tf32(tD, umma::smem_desc(pa + ks * 2 * TCS, TCS * 4, 128), umma::smem_desc(pb + ks * 2 * TCS, TCS * 4, 128), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = a.d + 1, kin = kin_of(a.d), KA = KP, GS = KP + kin;
+    const VLayout g(a.d, a.Hvr);
+    WImages w;
+    w.wh_hi = reinterpret_cast<float*>(smem_raw);
+    w.wh_lo = w.wh_hi + KP * NP;
+    w.wht_hi = w.wh_lo + KP * NP;
+    w.wht_lo = w.wht_hi + KP * NP;
+    w.wi_hi = w.wht_lo + KP * NP;
+    w.wi_lo = w.wi_hi + kin * NP;
+    w.wz = w.wi_lo + kin * NP;
+    float* dT_hi = w.wz + 64;
+    float* dT_lo = dT_hi + TIMG;
+    float* rT_hi = dT_lo + TIMG;
+    float* rT_lo = rT_hi + TIMG;
+    float* gimg = rT_lo + TIMG;                                  // [56][GS], also the overrun pad of the M = 128 reads
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(gimg + KP * GS + 512);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 4 * TIMG + KP * GS + 512; i += blockDim.x) dT_hi[i] = 0.f;
+    stage_images(w, a.theta, a.d, a.Hvr, kin);
+    if (tid == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(mbar + 1, 1); }
+    if (warp == 0) umma::tmem_alloc(slot, 512);
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tbase = *slot;
+    const uint32_t lane_addr = tbase + ((uint32_t)(32 * warp) << 16);
+    const uint32_t idesc = umma::idesc_tf32(128, NP), idesc_in = umma::idesc_tf32(128, kin);
+    uint32_t parA = 0, parB = 0;
+    const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
+    const long long npts = (long long)a.n * a.L;
+    const long long ntiles = (npts + 127) / 128;
+    const int L = a.L, nv = a.nv;
+    f4* scr = reinterpret_cast<f4*>(a.scratch) + (size_t)blockIdx.x * (nv > 0 ? nv : 1) * 13 * 128 + tid;
+    float gwz[HV];
+#pragma unroll
+    for (int o = 0; o < HV; ++o) gwz[o] = 0.f;
+    float gbz = 0.f;
+
+    for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const long long p = tix * 128 + tid;
+        const bool valid = p < npts;
+        const long long n = valid ? p / L : 0;
+        const int l = (int)(p - n * L);
+        const float* xr = a.p.x + n * a.p.x_sn + (long long)l * a.p.x_sl;
+        const float tval = valid ? a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl] : 0.f;
+        // ---------------------------------------------------------------- forward (recompute)
+#pragma unroll 1
+        for (int c8 = 0; c8 < kin; c8 += 8) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = c8 + e;
+                float v = 0.f;
+                if (valid) v = idx == 0 ? tval : (idx <= a.d ? xr[idx - 1] : (idx == C ? 1.f : 0.f));
+                hi[e] = umma::tf32_hi(v);
+                lo[e] = v - hi[e];
+            }
+            umma::tmem_st8(lane_addr + A_COL + c8, hi);
+            umma::tmem_st8(lane_addr + A_COL + KA + c8, lo);
+        }
+        umma::tmem_wait_st();
+        umma::fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after();
+            issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
+            umma::commit(mbar);
+        }
+        float h[KP];
+        mbar_wait_or_trap(mbar, parA);
+        umma::fence_after();
+        umma::tmem_ld56(lane_addr + D_COL, h);
+#pragma unroll 1
+        for (int layer = 0; layer < nv; ++layer) {
+#pragma unroll
+            for (int o = 0; o < HV; ++o) h[o] = fmaxf(h[o], 0.f);
+            h[BIASC] = 0.f; h[BIASC + 1] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 13; ++c) {
+                f4 v; v.x = h[4 * c]; v.y = h[4 * c + 1]; v.z = h[4 * c + 2]; v.w = h[4 * c + 3];
+                scr[(size_t)(layer * 13 + c) * 128] = v;
+            }
+            h[BIASC] = 1.f;
+#pragma unroll
+            for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
+            store_a_row(lane_addr, KA, h);
+            umma::tmem_wait_st();
+            umma::fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after();
+                issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wh_hi, w.wh_lo, KP / 8, idesc);
+                umma::commit(mbar);
+            }
+            mbar_wait_or_trap(mbar, parA);
+            umma::fence_after();
+            umma::tmem_ld56(lane_addr + D_COL, h);
+        }
+        // ---------------------------------------------------------------- output layer, cotangent G
+        {
+            float v = w.wz[KP];
+#pragma unroll
+            for (int o = 0; o < HV; ++o) {
+                h[o] = tanh_fast(h[o]);
+                v = fmaf(w.wz[o], h[o], v);
+            }
+            float G = 0.f;
+            if (valid) {
+                const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
+                G = fmaf(k0, a.cot[p], fmaf(k1, v, k2 * W.w));
+            }
+            gbz += G;
+#pragma unroll
+            for (int o = 0; o < HV; ++o) {
+                const float t = h[o];
+                gwz[o] = fmaf(G, t, gwz[o]);
+                h[o] = G * w.wz[o] * (1.f - t * t);              // delta_nv
+            }
+#pragma unroll
+            for (int o = HV; o < KP; ++o) h[o] = 0.f;
+        }
+        // ---------------------------------------------------------------- reverse sweep
+        uint32_t pacc = 0;                                        // the first P-op of a tile overwrites the accumulator
+#pragma unroll 1
+        for (int k = nv; k >= 0; --k) {
+            // delta_k: transposed image (A of the P-op) and, for k > 0, tensor-memory row (A of the R-op)
+#pragma unroll
+            for (int o = 0; o < HV; ++o) {
+                const float hi = umma::tf32_hi(h[o]);
+                dT_hi[t_off(o, tid)] = hi;
+                dT_lo[t_off(o, tid)] = h[o] - hi;
+            }
+            if (k == 0) break;
+            store_a_row(lane_addr, KA, h);
+            // r_{k-1}: back from the scratch -> relu mask + transposed image with the ones column
+            uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+            for (int c = 0; c < 13; ++c) {
+                const f4 v = scr[(size_t)((k - 1) * 13 + c) * 128];
+                const float rv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int o = 4 * c + e;
+                    if (o < HV) {
+                        if (o < 32) m0 |= (rv[e] > 0.f ? 1u : 0u) << o; else m1 |= (rv[e] > 0.f ? 1u : 0u) << (o - 32);
+                        const float hi = umma::tf32_hi(rv[e]);
+                        rT_hi[t_off(o, tid)] = hi;
+                        rT_lo[t_off(o, tid)] = rv[e] - hi;
+                    }
+                }
+            }
+            rT_hi[t_off(BIASC, tid)] = 1.f; rT_lo[t_off(BIASC, tid)] = 0.f;
+#pragma unroll
+            for (int o = BIASC + 1; o < KP; ++o) { rT_hi[t_off(o, tid)] = 0.f; rT_lo[t_off(o, tid)] = 0.f; }
+            umma::fence_smem_to_async();
+            umma::tmem_wait_st();
+            umma::fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after();
+                issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wht_hi, w.wht_lo, KP / 8, idesc);
+                umma::commit(mbar);
+                issue_pop(tbase + WH_COL, dT_hi, dT_lo, rT_hi, rT_lo, idesc, pacc);
+                umma::commit(mbar + 1);
+            }
+            pacc = 1;
+            mbar_wait_or_trap(mbar, parA);
+            umma::fence_after();
+            umma::tmem_ld56(lane_addr + D_COL, h);
+#pragma unroll
+            for (int o = 0; o < 32; ++o) h[o] = ((m0 >> o) & 1u) ? h[o] : 0.f;
+#pragma unroll
+            for (int o = 32; o < HV; ++o) h[o] = ((m1 >> (o - 32)) & 1u) ? h[o] : 0.f;
+#pragma unroll
+            for (int o = HV; o < KP; ++o) h[o] = 0.f;
+            mbar_wait_or_trap(mbar + 1, parB);                    // the images and the A rows are free again
+        }
+        // ---------------------------------------------------------------- input layer: dWi | dbi
+#pragma unroll 1
+        for (int c = 0; c < kin; ++c) {
+            float v = 0.f;
+            if (valid) v = c == 0 ? tval : (c <= a.d ? xr[c - 1] : (c == C ? 1.f : 0.f));
+            const float hi = umma::tf32_hi(v);
+            rT_hi[t_off(c, tid)] = hi;
+            rT_lo[t_off(c, tid)] = v - hi;
+        }
+        umma::fence_smem_to_async();
+        umma::fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after();
+            issue_pop(tbase + WI_COL, dT_hi, dT_lo, rT_hi, rT_lo, idesc_in, 0u);
+            umma::commit(mbar + 1);
+        }
+        mbar_wait_or_trap(mbar + 1, parB);
+        umma::fence_after();
+        // ---------------------------------------------------------------- flush the tile's accumulators
+        if (warp < 2) {                                           // rows o = tid < 56 carry data; warps stay converged for tcgen05.ld
+            float* grow = gimg + (tid < KP ? tid : 0) * GS;
+            if (nv > 0) {
+                float acc[KP];
+                umma::tmem_ld56(lane_addr + WH_COL, acc);
+                if (tid < KP) {
+#pragma unroll
+                    for (int i = 0; i < KP; ++i) grow[i] += acc[i];
+                }
+            }
+#pragma unroll 1
+            for (int c8 = 0; c8 < kin; c8 += 8) {
+                float acc[8];
+                umma::tmem_ld8(lane_addr + WI_COL + c8, acc);
+                if (tid < KP) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) grow[KP + c8 + e] += acc[e];
+                }
+            }
+        }
+        umma::fence_before();
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------------ write the CTA's partial
+    float* zimg = dT_hi;                                           // [64]: dWz | dbz
+    if (tid < 64) zimg[tid] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < HV; ++o) {
+        const float sred = warp_sum(gwz[o]);
+        if (lane == 0) atomicAdd(zimg + o, sred);
+    }
+    {
+        const float sb = warp_sum(gbz);
+        if (lane == 0) atomicAdd(zimg + KP, sb);
+    }
+    __syncthreads();
+    float* out = a.gpart + (size_t)blockIdx.x * g.size;
+    const int Hvr = a.Hvr;
+    for (int e = tid; e < Hvr * C; e += blockDim.x) { const int o = e / C, c = e - o * C; out[g.Wi + e] = gimg[o * GS + KP + c]; }
+    for (int e = tid; e < Hvr * Hvr; e += blockDim.x) { const int o = e / Hvr, i = e - o * Hvr; out[g.Wh + e] = gimg[o * GS + i]; }
+    for (int o = tid; o < Hvr; o += blockDim.x) {
+        out[g.bi + o] = gimg[o * GS + KP + C];
+        out[g.bh + o] = gimg[o * GS + BIASC];
+        out[g.Wz + o] = zimg[o];
+    }
+    if (tid == 0) out[g.bz] = zimg[KP];
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tbase, 512);
+}
+
+}  // namespace tc
+}  // namespace xw
+#endif
