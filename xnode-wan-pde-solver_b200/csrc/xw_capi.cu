@@ -168,11 +168,11 @@ bool use_point_kernels() {
 bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
 int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
     const int kin = xw::tc::kin_of(m->d);
-    p->smem = (size_t)(4 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64 + 4 * xw::tc::TIMG + xw::tc::KP * (xw::tc::KP + kin) + 512) * 4 + 64;
+    p->smem = (size_t)(4 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64 + 4 * xw::tc::TIMG + xw::tc::KP * (xw::tc::KP + kin) + 512 + 64) * 4 + 128;
     if (p->smem > device()->smem_optin) return fail("tensor-core v-net backward needs %zu B shared memory (> %zu)", p->smem, device()->smem_optin);
     const long long ntiles = ((long long)n * L + 127) / 128;
     p->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms));
-    p->scratch_bytes = align_up((size_t)p->grid * std::max(m->nv, 1) * 13 * 128 * 16, 256);
+    p->scratch_bytes = align_up((size_t)p->grid * 2 * std::max(m->nv, 1) * 14 * 128 * 16, 256);   // double-buffered (pipelined variant)
     p->part_bytes = align_up((size_t)p->grid * xw::VLayout(m->d, m->Hv).size * 4, 256);
     return 0;
 }
@@ -512,9 +512,16 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
         t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
         t.cot = cot_v; t.coefs = coefs_dev; t.scratch = (float*)workspace; t.gpart = (float*)((char*)workspace + pl.scratch_bytes);
-        if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd, pl.smem)) return 1;
-        xw::tc::k_vnet_tc_bwd<<<pl.grid, 128, pl.smem, (cudaStream_t)stream>>>(t);
-        if (XW_CHECK_LAUNCH("k_vnet_tc_bwd")) return 1;
+        const char* ev = getenv("XW_VNET_BWD");
+        if (ev && strcmp(ev, "serial") == 0) {           // single warpgroup, everything in sequence (kept for A/B runs)
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd, pl.smem)) return 1;
+            xw::tc::k_vnet_tc_bwd<<<pl.grid, 128, pl.smem, (cudaStream_t)stream>>>(t);
+            if (XW_CHECK_LAUNCH("k_vnet_tc_bwd")) return 1;
+        } else {
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, pl.smem)) return 1;
+            xw::tc::k_vnet_tc_bwd3<<<pl.grid, 384, pl.smem, (cudaStream_t)stream>>>(t);
+            if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
+        }
         return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
     }
 #endif
@@ -655,7 +662,7 @@ extern "C" int xw_umma_probe(const float* A, const float* B, float* D, int K, in
     if (K % 8 || K < 8 || K > 64 || N % 8 || N < 8 || N > 64 || (terms != 1 && terms != 3)) return fail("bad probe shape");
     const size_t smem = (size_t)(2 * 128 * K + 2 * N * K) * 4 + 64;
     if (XW_SET_SMEM(xw::umma::k_umma_probe, smem)) return 1;
-    xw::umma::k_umma_probe<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, terms, err_dev, ts);
+    xw::umma::k_umma_probe<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, terms, err_dev, ts, getenv("XW_UMMA_M64") ? 1 : 0);
     return check_launch("k_umma_probe");
 #endif
 }

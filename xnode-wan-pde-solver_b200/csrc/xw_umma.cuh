@@ -59,6 +59,11 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)) : "memory");
+}
+// barrier among the 128 threads of one warpgroup (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 // bounded wait: returns false if the phase did not complete within `spins` probes
 __device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity, int spins = 1 << 22) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
@@ -130,7 +135,7 @@ __device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__flo
 
 // D[128 x N] = A[128 x K] * B[N x K]^T  (row-major fp32 in global memory), N multiple of 16 <= 64, K multiple of 8
 // terms = 1: plain TF32, terms = 3: 3xTF32.  err[0] != 0 if a bounded wait expired.
-__global__ void __launch_bounds__(128) k_umma_probe(const float* A, const float* B, float* D, int K, int N, int terms, int* err, int ts) {
+__global__ void __launch_bounds__(128) k_umma_probe(const float* A, const float* B, float* D, int K, int N, int terms, int* err, int ts, int ts_m64) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* a_hi = reinterpret_cast<float*>(smem_raw);
     float* a_lo = a_hi + 128 * K;
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(128) k_umma_probe(const float* A, const float*
             }
         commit(mbar);
     } else if (tid == 0) {
-        const uint32_t idesc = idesc_tf32(128, N);
+        const uint32_t idesc = idesc_tf32(ts_m64 ? 64 : 128, N);
         const int lbo_a = 128 * 16, lbo_b = N * 16, sbo = 128;
         uint32_t acc = 0;
         for (int t = 0; t < terms; ++t) {

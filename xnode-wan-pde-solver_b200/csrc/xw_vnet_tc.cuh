@@ -80,18 +80,31 @@ __device__ void stage_images(const WImages& w, const float* XW_RESTRICT th, int 
     __syncthreads();
 }
 
-// D[128 x NP] = A[128 x 8*ksteps] * B^T, A from tensor memory (hi / lo column blocks), B images in smem
+// D[128 x NP] = A[128 x 8*ksteps] * B^T, A from tensor memory (hi / lo column blocks), B images in smem.
+// KS > 0: compile-time k-step count (straight-line issue: one IADD on the descriptor per MMA)
+template <int KS>
 __device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tA_hi, uint32_t tA_lo, const float* b_hi, const float* b_lo,
-                                             int ksteps, uint32_t idesc) {
-    uint32_t acc = 0;
+                                             int ksteps_rt, uint32_t idesc) {
+    const uint64_t dh = umma::smem_desc(b_hi, NP * 16, 128), dl = umma::smem_desc(b_lo, NP * 16, 128);
+    constexpr uint64_t kStep = (2 * NP * 16) >> 4;        // two 16-byte chunks of k per MMA
+    if (KS > 0) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {                     // small terms first
+#pragma unroll
+            for (int ks = 0; ks < (KS > 0 ? KS : 1); ++ks)
+                umma::mma_tf32_ts(tD, (t == 0 ? tA_lo : tA_hi) + 8 * ks, (t == 1 ? dl : dh) + kStep * ks, idesc, (t | ks) ? 1u : 0u);
+        }
+    } else {
+        uint32_t acc = 0;
 #pragma unroll 1
-    for (int t = 0; t < 3; ++t) {                       // small terms first
-        const uint32_t ta = t == 0 ? tA_lo : tA_hi;
-        const float* pb = t == 1 ? b_lo : b_hi;
+        for (int t = 0; t < 3; ++t) {
+            const uint32_t ta = t == 0 ? tA_lo : tA_hi;
+            const uint64_t db = t == 1 ? dl : dh;
 #pragma unroll 1
-        for (int ks = 0; ks < ksteps; ++ks) {
-            umma::mma_tf32_ts(tD, ta + 8 * ks, umma::smem_desc(pb + ks * (2 * NP * 4), NP * 16, 128), idesc, acc);
-            acc = 1;
+            for (int ks = 0; ks < ksteps_rt; ++ks) {
+                umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, acc);
+                acc = 1;
+            }
         }
     }
 }
@@ -169,7 +182,7 @@ __global__ void __launch_bounds__(128) k_vnet_tc_fwd(VtileFwdArgs a, int tmem_co
         __syncthreads();
         if (tid == 0) {
             umma::fence_after();
-            issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
+            issue_3xtf32<0>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
             umma::commit(mbar);
         }
         float h[KP];
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(128) k_vnet_tc_fwd(VtileFwdArgs a, int tmem_co
             __syncthreads();
             if (tid == 0) {
                 umma::fence_after();
-                issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wh_hi, w.wh_lo, KP / 8, idesc);
+                issue_3xtf32<KP / 8>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wh_hi, w.wh_lo, 0, idesc);
                 umma::commit(mbar);
             }
             mbar_wait_or_trap(mbar, parity);
@@ -264,16 +277,14 @@ __device__ __forceinline__ int t_off(int row, int r) { return (r >> 2) * TCS + (
 // out[m][n] (+)= sum_{r<128} A^T-image[m][r] * B^T-image[n][r]   (3xTF32, 16 k-steps of 8 points)
 __device__ __forceinline__ void issue_pop(uint32_t tD, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
                                           uint32_t idesc, uint32_t accumulate) {
-    uint32_t acc = accumulate;
-#pragma unroll 1
+    constexpr uint64_t kStep = (2 * TCS * 4) >> 4;
+    const uint64_t ah = umma::smem_desc(a_hi, TCS * 4, 128), al = umma::smem_desc(a_lo, TCS * 4, 128);
+    const uint64_t bh = umma::smem_desc(b_hi, TCS * 4, 128), bl = umma::smem_desc(b_lo, TCS * 4, 128);
+#pragma unroll
     for (int t = 0; t < 3; ++t) {
-        const float* pa = t == 0 ? a_lo : a_hi;
-        const float* pb = t == 1 ? b_lo : b_hi;
-#pragma unroll 1
-        for (int ks = 0; ks < 16; ++ks) {
-            umma::mma_tf32(tD, umma::smem_desc(pa + ks * 2 * TCS, TCS * 4, 128), umma::smem_desc(pb + ks * 2 * TCS, TCS * 4, 128), idesc, acc);
-            acc = 1;
-        }
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+            umma::mma_tf32(tD, (t == 0 ? al : ah) + kStep * ks, (t == 1 ? bl : bh) + kStep * ks, idesc, (t | ks) ? 1u : accumulate);
     }
 }
 
@@ -345,7 +356,7 @@ __global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
         __syncthreads();
         if (tid == 0) {
             umma::fence_after();
-            issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
+            issue_3xtf32<0>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
             umma::commit(mbar);
         }
         float h[KP];
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
             __syncthreads();
             if (tid == 0) {
                 umma::fence_after();
-                issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wh_hi, w.wh_lo, KP / 8, idesc);
+                issue_3xtf32<KP / 8>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wh_hi, w.wh_lo, 0, idesc);
                 umma::commit(mbar);
             }
             mbar_wait_or_trap(mbar, parA);
@@ -440,7 +451,7 @@ __global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
             __syncthreads();
             if (tid == 0) {
                 umma::fence_after();
-                issue_3xtf32(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wht_hi, w.wht_lo, KP / 8, idesc);
+                issue_3xtf32<KP / 8>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wht_hi, w.wht_lo, 0, idesc);
                 umma::commit(mbar);
                 issue_pop(tbase + WH_COL, dT_hi, dT_lo, rT_hi, rT_lo, idesc, pacc);
                 umma::commit(mbar + 1);
@@ -525,6 +536,330 @@ __global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
     }
     if (tid == 0) out[g.bz] = zimg[KP];
     umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tbase, 512);
+}
+
+// =============================================================================================
+// The same backward as a three-stage warp-specialised pipeline (384 threads, one CTA per SM):
+//   F (warps 0-3)  : forward recompute of tile t+1, output layer, cotangent G, dWz, delta_nv -> mailbox (D_f)
+//   R (warps 4-7)  : the delta chain of tile t: delta_k -> A_r (tensor memory), R-op, relu mask
+//   P (warps 8-11) : reads delta_k back from A_r, builds the transposed images of delta_k and r_{k-1},
+//                    issues the weight-gradient MMAs (P-op), flushes the accumulators per tile
+// Thread j of every group owns point row j = TMEM lane j (a warp reaches lane quadrant warp % 4).
+// The tensor pipe then always has queued work from three independent issuers.  Every cross-group
+// hand-off is an mbarrier with a bounded wait; F's activations and relu masks travel through a
+// double-buffered per-CTA scratch in global memory (L2 resident).
+// =============================================================================================
+constexpr int P3_DF = 0, P3_AF = 64, P3_DR = 176, P3_AR = 240, P3_WH = 352, P3_WI = 416;
+
+__device__ __forceinline__ void store_a_row_at(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[KP]) {
+    uint32_t r[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+    umma::tmem_st56(addr_hi, r);
+#pragma unroll
+    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i] - __uint_as_float(r[i]));
+    umma::tmem_st56(addr_lo, r);
+}
+
+__global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = a.d + 1, kin = kin_of(a.d), GS = KP + kin;
+    const VLayout g(a.d, a.Hvr);
+    WImages w;
+    w.wh_hi = reinterpret_cast<float*>(smem_raw);
+    w.wh_lo = w.wh_hi + KP * NP;
+    w.wht_hi = w.wh_lo + KP * NP;
+    w.wht_lo = w.wht_hi + KP * NP;
+    w.wi_hi = w.wht_lo + KP * NP;
+    w.wi_lo = w.wi_hi + kin * NP;
+    w.wz = w.wi_lo + kin * NP;
+    float* dT_hi = w.wz + 64;
+    float* dT_lo = dT_hi + TIMG;
+    float* rT_hi = dT_lo + TIMG;
+    float* rT_lo = rT_hi + TIMG;
+    float* gimg = rT_lo + TIMG;                                  // [56][GS] (+512: overrun pad of the M = 128 reads)
+    float* zacc = gimg + KP * GS + 512;                          // [64] dWz | dbz
+    uint64_t* mb = reinterpret_cast<uint64_t*>(zacc + 64);
+    uint64_t *mF = mb, *mR = mb + 1, *mP = mb + 2, *mFD = mb + 3, *mFC = mb + 4, *mDP = mb + 5, *mPR = mb + 6;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mb + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid >> 7, j = tid & 127;
+    for (int i = tid; i < 4 * TIMG + KP * GS + 512 + 64; i += blockDim.x) dT_hi[i] = 0.f;
+    stage_images(w, a.theta, a.d, a.Hvr, kin);
+    if (tid == 0) {
+        umma::mbar_init(mF, 1); umma::mbar_init(mR, 1); umma::mbar_init(mP, 1);
+        umma::mbar_init(mFD, 128); umma::mbar_init(mFC, 128); umma::mbar_init(mDP, 128); umma::mbar_init(mPR, 128);
+    }
+    if (warp == 0) umma::tmem_alloc(slot, 512);
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tbase = *slot;
+    const uint32_t lane_addr = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+    const uint32_t idesc = umma::idesc_tf32(128, NP), idesc_in = umma::idesc_tf32(128, kin);
+    const long long npts = (long long)a.n * a.L;
+    const long long ntiles = (npts + 127) / 128;
+    const int L = a.L, nv = a.nv, nvs = nv > 0 ? nv : 1;
+    f4* scr = reinterpret_cast<f4*>(a.scratch) + (size_t)blockIdx.x * 2 * nvs * 14 * 128 + j;
+
+    if (wg == 0) {
+        // ======================================================================== F: forward of every tile
+        const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
+        uint32_t pF = 0, pFC = 0;
+        int it = 0;
+        for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
+            const long long p = tix * 128 + j;
+            const bool valid = p < npts;
+            const long long n = valid ? p / L : 0;
+            const int l = (int)(p - n * L);
+            const float* xr = a.p.x + n * a.p.x_sn + (long long)l * a.p.x_sl;
+            const float tval = valid ? a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl] : 0.f;
+            f4* sb = scr + (size_t)(it & 1) * nvs * 14 * 128;
+#pragma unroll 1
+            for (int c8 = 0; c8 < kin; c8 += 8) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int idx = c8 + e;
+                    float v = 0.f;
+                    if (valid) v = idx == 0 ? tval : (idx <= a.d ? xr[idx - 1] : (idx == C ? 1.f : 0.f));
+                    hi[e] = umma::tf32_hi(v);
+                    lo[e] = v - hi[e];
+                }
+                umma::tmem_st8(lane_addr + P3_AF + c8, hi);
+                umma::tmem_st8(lane_addr + P3_AF + KP + c8, lo);
+            }
+            umma::tmem_wait_st();
+            umma::fence_before();
+            if (it > 0) mbar_wait_or_trap(mFC, pFC);              // R has taken the previous tile out of the mailbox
+            umma::group_sync(1);
+            if (j == 0) {
+                umma::fence_after();
+                issue_3xtf32<0>(tbase + P3_DF, tbase + P3_AF, tbase + P3_AF + KP, w.wi_hi, w.wi_lo, kin / 8, idesc);
+                umma::commit(mF);
+            }
+            float h[KP];
+            mbar_wait_or_trap(mF, pF);
+            umma::fence_after();
+            umma::tmem_ld56(lane_addr + P3_DF, h);
+#pragma unroll 1
+            for (int layer = 0; layer < nv; ++layer) {
+                uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+                for (int o = 0; o < 32; ++o) m0 |= (h[o] > 0.f ? 1u : 0u) << o;
+#pragma unroll
+                for (int o = 32; o < HV; ++o) m1 |= (h[o] > 0.f ? 1u : 0u) << (o - 32);
+#pragma unroll
+                for (int o = 0; o < HV; ++o) h[o] = fmaxf(h[o], 0.f);
+                h[BIASC] = 0.f; h[BIASC + 1] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 13; ++c) {
+                    f4 v; v.x = h[4 * c]; v.y = h[4 * c + 1]; v.z = h[4 * c + 2]; v.w = h[4 * c + 3];
+                    sb[(size_t)(layer * 14 + c) * 128] = v;
+                }
+                { f4 v; v.x = __uint_as_float(m0); v.y = __uint_as_float(m1); v.z = 0.f; v.w = 0.f; sb[(size_t)(layer * 14 + 13) * 128] = v; }
+                h[BIASC] = 1.f;
+#pragma unroll
+                for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
+                store_a_row_at(lane_addr + P3_AF, lane_addr + P3_AF + KP, h);
+                umma::tmem_wait_st();
+                umma::fence_before();
+                umma::group_sync(1);
+                if (j == 0) {
+                    umma::fence_after();
+                    issue_3xtf32<KP / 8>(tbase + P3_DF, tbase + P3_AF, tbase + P3_AF + KP, w.wh_hi, w.wh_lo, 0, idesc);
+                    umma::commit(mF);
+                }
+                mbar_wait_or_trap(mF, pF);
+                umma::fence_after();
+                umma::tmem_ld56(lane_addr + P3_DF, h);
+            }
+            // output layer, cotangent G, dWz | dbz, delta_nv -> mailbox
+            {
+                float v = w.wz[KP];
+#pragma unroll
+                for (int o = 0; o < HV; ++o) {
+                    h[o] = tanh_fast(h[o]);
+                    v = fmaf(w.wz[o], h[o], v);
+                }
+                float G = 0.f;
+                if (valid) {
+                    const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
+                    G = fmaf(k0, a.cot[p], fmaf(k1, v, k2 * W.w));
+                }
+                {
+                    const float sb2 = warp_sum(G);
+                    if (lane == 0) atomicAdd(zacc + KP, sb2);
+                }
+#pragma unroll
+                for (int o = 0; o < HV; ++o) {
+                    const float t = h[o];
+                    const float sz = warp_sum(G * t);
+                    if (lane == 0) atomicAdd(zacc + o, sz);
+                    h[o] = G * w.wz[o] * (1.f - t * t);
+                }
+                uint32_t r[KP];
+#pragma unroll
+                for (int o = 0; o < KP; ++o) r[o] = o < HV ? __float_as_uint(h[o]) : 0u;
+                umma::tmem_st56(lane_addr + P3_DF, r);
+                umma::tmem_wait_st();
+                umma::fence_before();
+                umma::mbar_arrive(mFD);
+            }
+        }
+    } else if (wg == 1) {
+        // ======================================================================== R: the delta chain
+        uint32_t pR = 0, pFD = 0, pPR = 0;
+        bool wrote = false;
+        int it = 0;
+        for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
+            const f4* sb = scr + (size_t)(it & 1) * nvs * 14 * 128;
+            float h[KP];
+            mbar_wait_or_trap(mFD, pFD);
+            umma::fence_after();
+            umma::tmem_ld56(lane_addr + P3_DF, h);
+            umma::fence_before();
+            umma::mbar_arrive(mFC);
+#pragma unroll 1
+            for (int k = nv; k >= 0; --k) {
+                if (wrote) mbar_wait_or_trap(mPR, pPR);          // P has read the previous delta out of A_r
+                store_a_row_at(lane_addr + P3_AR, lane_addr + P3_AR + KP, h);
+                umma::tmem_wait_st();
+                umma::fence_before();
+                umma::mbar_arrive(mDP);
+                wrote = true;
+                if (k == 0) break;
+                umma::group_sync(2);
+                if (j == 0) {
+                    umma::fence_after();
+                    issue_3xtf32<KP / 8>(tbase + P3_DR, tbase + P3_AR, tbase + P3_AR + KP, w.wht_hi, w.wht_lo, 0, idesc);
+                    umma::commit(mR);
+                }
+                const f4 mv = sb[(size_t)((k - 1) * 14 + 13) * 128];
+                const uint32_t m0 = __float_as_uint(mv.x), m1 = __float_as_uint(mv.y);
+                mbar_wait_or_trap(mR, pR);
+                umma::fence_after();
+                umma::tmem_ld56(lane_addr + P3_DR, h);
+#pragma unroll
+                for (int o = 0; o < 32; ++o) h[o] = ((m0 >> o) & 1u) ? h[o] : 0.f;
+#pragma unroll
+                for (int o = 32; o < HV; ++o) h[o] = ((m1 >> (o - 32)) & 1u) ? h[o] : 0.f;
+#pragma unroll
+                for (int o = HV; o < KP; ++o) h[o] = 0.f;
+            }
+        }
+    } else {
+        // ======================================================================== P: weight gradients
+        uint32_t pP = 0, pDP = 0;
+        bool pending = false;
+        int it = 0;
+        for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
+            const long long p = tix * 128 + j;
+            const bool valid = p < npts;
+            const long long n = valid ? p / L : 0;
+            const int l = (int)(p - n * L);
+            const float* xr = a.p.x + n * a.p.x_sn + (long long)l * a.p.x_sl;
+            const float tval = valid ? a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl] : 0.f;
+            const f4* sb = scr + (size_t)(it & 1) * nvs * 14 * 128;
+#pragma unroll 1
+            for (int k = nv; k >= 0; --k) {
+                // r_{k-1} and delta_k are fetched while the previous P-op still runs; only the image stores wait for it
+                f4 rv4[13];
+                mbar_wait_or_trap(mDP, pDP);                   // (also what makes F's scratch writes of this tile visible)
+                umma::fence_after();
+                if (k > 0) {
+#pragma unroll
+                    for (int c = 0; c < 13; ++c) rv4[c] = sb[(size_t)((k - 1) * 14 + c) * 128];
+                }
+                {
+                    float v[KP];
+                    umma::tmem_ld56(lane_addr + P3_AR, v);
+                    if (pending) { mbar_wait_or_trap(mP, pP); pending = false; }     // the images are free again
+#pragma unroll
+                    for (int o = 0; o < HV; ++o) dT_hi[t_off(o, j)] = v[o];
+                    umma::tmem_ld56(lane_addr + P3_AR + KP, v);
+                    umma::fence_before();
+                    umma::mbar_arrive(mPR);
+#pragma unroll
+                    for (int o = 0; o < HV; ++o) dT_lo[t_off(o, j)] = v[o];
+                }
+                if (k > 0) {
+#pragma unroll
+                    for (int c = 0; c < 13; ++c) {
+                        const float rv[4] = {rv4[c].x, rv4[c].y, rv4[c].z, rv4[c].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int o = 4 * c + e;
+                            if (o < HV) {
+                                const float hi = umma::tf32_hi(rv[e]);
+                                rT_hi[t_off(o, j)] = hi;
+                                rT_lo[t_off(o, j)] = rv[e] - hi;
+                            }
+                        }
+                    }
+                    rT_hi[t_off(BIASC, j)] = 1.f; rT_lo[t_off(BIASC, j)] = 0.f;
+#pragma unroll
+                    for (int o = BIASC + 1; o < KP; ++o) { rT_hi[t_off(o, j)] = 0.f; rT_lo[t_off(o, j)] = 0.f; }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < kin; ++c) {
+                        float v = 0.f;
+                        if (valid) v = c == 0 ? tval : (c <= a.d ? xr[c - 1] : (c == C ? 1.f : 0.f));
+                        const float hi = umma::tf32_hi(v);
+                        rT_hi[t_off(c, j)] = hi;
+                        rT_lo[t_off(c, j)] = v - hi;
+                    }
+                }
+                umma::fence_smem_to_async();
+                umma::group_sync(3);
+                if (j == 0) {
+                    umma::fence_after();
+                    if (k > 0) issue_pop(tbase + P3_WH, dT_hi, dT_lo, rT_hi, rT_lo, idesc, k < nv ? 1u : 0u);
+                    else issue_pop(tbase + P3_WI, dT_hi, dT_lo, rT_hi, rT_lo, idesc_in, 0u);
+                    umma::commit(mP);
+                }
+                pending = true;
+            }
+            mbar_wait_or_trap(mP, pP);
+            pending = false;
+            umma::fence_after();
+            if ((warp & 3) < 2) {                                 // accumulator rows o = j < 56
+                float* grow = gimg + (j < KP ? j : 0) * GS;
+                if (nv > 0) {
+                    float acc[KP];
+                    umma::tmem_ld56(lane_addr + P3_WH, acc);
+                    if (j < KP) {
+#pragma unroll
+                        for (int i = 0; i < KP; ++i) grow[i] += acc[i];
+                    }
+                }
+#pragma unroll 1
+                for (int c8 = 0; c8 < kin; c8 += 8) {
+                    float acc[8];
+                    umma::tmem_ld8(lane_addr + P3_WI + c8, acc);
+                    if (j < KP) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) grow[KP + c8 + e] += acc[e];
+                    }
+                }
+            }
+            umma::fence_before();
+        }
+    }
+    umma::fence_before();
+    __syncthreads();
+    // ------------------------------------------------------------------------ write the CTA's partial
+    float* out = a.gpart + (size_t)blockIdx.x * g.size;
+    const int Hvr = a.Hvr;
+    for (int e = tid; e < Hvr * C; e += blockDim.x) { const int o = e / C, c = e - o * C; out[g.Wi + e] = gimg[o * GS + KP + c]; }
+    for (int e = tid; e < Hvr * Hvr; e += blockDim.x) { const int o = e / Hvr, i = e - o * Hvr; out[g.Wh + e] = gimg[o * GS + i]; }
+    for (int o = tid; o < Hvr; o += blockDim.x) {
+        out[g.bi + o] = gimg[o * GS + KP + C];
+        out[g.bh + o] = gimg[o * GS + BIASC];
+        out[g.Wz + o] = zacc[o];
+    }
+    if (tid == 0) out[g.bz] = zacc[KP];
     __syncthreads();
     if (warp == 0) umma::tmem_free(tbase, 512);
 }
