@@ -435,15 +435,14 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     if (use_tc_kernels() && xw::tc::kin_of(m->d) <= 224) {
         // generation 3: hidden-layer contractions on the tensor cores (tcgen05, 3xTF32), 64 points per tile
         const int kin = xw::tc::kin_of(m->d), KA = std::max(kin, xw::tc::KP);
-        const int need = xw::tc::A_COL + 2 * KA, cols = need <= 256 ? 256 : 512;
-        size_t sm = (size_t)(2 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64) * 4 + 4 * 32 * 8 + 64;
-        // tensor memory holds 512 columns per SM: keep the resident CTAs at 512 / cols by sizing shared memory
-        const int per_sm = 512 / cols;
-        sm = std::max(sm, (size_t)(device()->smem_optin / (per_sm + 1) + 1024));
+        // one CTA per SM owns the 512 tensor-memory columns; each warpgroup needs 56 + 2 KA of them
+        const int ng = std::max(1, std::min(3, 512 / (xw::tc::NP + 2 * KA)));
+        size_t sm = (size_t)(2 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64) * 4 + 4 * 32 * 8 + 128;
+        sm = std::max(sm, (size_t)(device()->smem_optin / 2 + 1024));          // (keeps a second CTA off the SM)
         if (XW_SET_SMEM(xw::tc::k_vnet_tc_fwd, sm)) return 1;
         const long long nt = ((long long)n * L + 63) / 64;
-        const int g3 = (int)std::max<long long>(1, std::min<long long>(nt, (long long)device()->sms * per_sm));
-        xw::tc::k_vnet_tc_fwd<<<g3, 128, sm, (cudaStream_t)stream>>>(t, cols);
+        const int g3 = (int)std::max<long long>(1, std::min<long long>((nt + ng - 1) / ng, (long long)device()->sms));
+        xw::tc::k_vnet_tc_fwd<<<g3, 128 * ng, sm, (cudaStream_t)stream>>>(t, ng);
         return XW_CHECK_LAUNCH("k_vnet_tc_fwd");
     }
 #endif

@@ -120,12 +120,22 @@ __device__ __forceinline__ void store_a_row(uint32_t lane_addr, int KA, const fl
     umma::tmem_st56(lane_addr + A_COL + KA, r);
 }
 
+__device__ __forceinline__ void store_a_row_at(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[KP]) {
+    uint32_t r[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
+    umma::tmem_st56(addr_hi, r);
+#pragma unroll
+    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i] - __uint_as_float(r[i]));
+    umma::tmem_st56(addr_lo, r);
+}
+
 // =============================================================================================
 // interior forward over all points: v, dv/dt (forward-mode tangent), weak-form integrands, seeds.
 // A tile is 64 points = 128 rows: lanes 0..15 of warp w own the VALUE rows of points 16w..16w+15,
 // lanes 16..31 the TANGENT rows of the same points (relu masks travel by warp shuffle).
 // =============================================================================================
-__global__ void __launch_bounds__(128) k_vnet_tc_fwd(VtileFwdArgs a, int tmem_cols) {
+__global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = a.d + 1, kin = kin_of(a.d), KA = kin > KP ? kin : KP;
     WImages w;
@@ -136,26 +146,31 @@ __global__ void __launch_bounds__(128) k_vnet_tc_fwd(VtileFwdArgs a, int tmem_co
     w.wi_lo = w.wi_hi + kin * NP;
     w.wz = w.wi_lo + kin * NP;
     double* red = reinterpret_cast<double*>(w.wz + 64);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 4 * 32);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(red + 4 * 32);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid >> 7, wq = warp & 3;
     const bool is_tan = lane >= 16;
     stage_images(w, a.theta, a.d, a.Hvr, kin);
-    if (tid == 0) umma::mbar_init(mbar, 1);
-    if (warp == 0) umma::tmem_alloc(slot, tmem_cols);
+    if (tid < 4) umma::mbar_init(mbars + tid, 1);
+    if (warp == 0) umma::tmem_alloc(slot, 512);
     umma::fence_before();
     __syncthreads();
     umma::fence_after();
-    const uint32_t tbase = *slot;
-    const uint32_t lane_addr = tbase + ((uint32_t)(32 * warp) << 16);
+    // every warpgroup runs its own stream of tiles in its own tensor-memory columns (D: 56, A hi/lo: 2 KA):
+    // up to three independent layer chains keep the tensor pipe fed while the others are in their epilogues
+    const uint32_t tbase = *slot + (uint32_t)(wg * (NP + 2 * KA));
+    const uint32_t colD = 0, colA = NP;
+    const uint32_t lane_addr = tbase + ((uint32_t)(32 * wq) << 16);
+    uint64_t* mbar = mbars + wg;
+    const bool issuer = (tid & 127) == 0;
     const uint32_t idesc = umma::idesc_tf32(128, NP);
     uint32_t parity = 0;
     const long long npts = (long long)a.n * a.L;
     const long long ntiles = (npts + 63) / 64;
     const int L = a.L;
     double accs[4] = {0.0, 0.0, 0.0, 0.0};
-    for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
-        const long long p = tix * 64 + 16 * warp + (lane & 15);
+    for (long long tix = (long long)blockIdx.x * ngroups + wg; tix < ntiles; tix += (long long)gridDim.x * ngroups) {
+        const long long p = tix * 64 + 16 * wq + (lane & 15);
         const bool valid = p < npts;
         const long long n = valid ? p / L : 0;
         const int l = (int)(p - n * L);
@@ -174,21 +189,21 @@ __global__ void __launch_bounds__(128) k_vnet_tc_fwd(VtileFwdArgs a, int tmem_co
                 hi[e] = umma::tf32_hi(v);
                 lo[e] = v - hi[e];
             }
-            umma::tmem_st8(lane_addr + A_COL + c8, hi);
-            umma::tmem_st8(lane_addr + A_COL + KA + c8, lo);
+            umma::tmem_st8(lane_addr + colA + c8, hi);
+            umma::tmem_st8(lane_addr + colA + KA + c8, lo);
         }
         umma::tmem_wait_st();
         umma::fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        umma::group_sync(1 + wg);
+        if (issuer) {
             umma::fence_after();
-            issue_3xtf32<0>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
+            issue_3xtf32<0>(tbase + colD, tbase + colA, tbase + colA + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
             umma::commit(mbar);
         }
         float h[KP];
         mbar_wait_or_trap(mbar, parity);
         umma::fence_after();
-        umma::tmem_ld56(lane_addr + D_COL, h);
+        umma::tmem_ld56(lane_addr + colD, h);
         // ---- hidden layers -------------------------------------------------------------------
 #pragma unroll 1
         for (int layer = 0; layer < a.nv; ++layer) {
@@ -206,18 +221,18 @@ __global__ void __launch_bounds__(128) k_vnet_tc_fwd(VtileFwdArgs a, int tmem_co
             h[BIASC] = is_tan ? 0.f : 1.f;
 #pragma unroll
             for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
-            store_a_row(lane_addr, KA, h);
+            store_a_row_at(lane_addr + colA, lane_addr + colA + KA, h);
             umma::tmem_wait_st();
             umma::fence_before();
-            __syncthreads();
-            if (tid == 0) {
+            umma::group_sync(1 + wg);
+            if (issuer) {
                 umma::fence_after();
-                issue_3xtf32<KP / 8>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wh_hi, w.wh_lo, 0, idesc);
+                issue_3xtf32<KP / 8>(tbase + colD, tbase + colA, tbase + colA + KA, w.wh_hi, w.wh_lo, 0, idesc);
                 umma::commit(mbar);
             }
             mbar_wait_or_trap(mbar, parity);
             umma::fence_after();
-            umma::tmem_ld56(lane_addr + D_COL, h);
+            umma::tmem_ld56(lane_addr + colD, h);
         }
         // ---- tanh + output layer ---------------------------------------------------------------
         float pv = 0.f, pt = 0.f;
@@ -245,9 +260,8 @@ __global__ void __launch_bounds__(128) k_vnet_tc_fwd(VtileFwdArgs a, int tmem_co
     block_sum_to_global<4>(accs, red, a.sums, idx);
     umma::fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_free(tbase, tmem_cols);
+    if (warp == 0) umma::tmem_free(*slot, 512);
 }
-
 
 // =============================================================================================
 // v net backward on the tensor cores:  parameter gradients of sum_p G[p] v[p],  G = k0*cot_v + k1*v + k2*w
@@ -553,15 +567,6 @@ __global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
 // =============================================================================================
 constexpr int P3_DF = 0, P3_AF = 64, P3_DR = 176, P3_AR = 240, P3_WH = 352, P3_WI = 416;
 
-__device__ __forceinline__ void store_a_row_at(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[KP]) {
-    uint32_t r[KP];
-#pragma unroll
-    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
-    umma::tmem_st56(addr_hi, r);
-#pragma unroll
-    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i] - __uint_as_float(r[i]));
-    umma::tmem_st56(addr_lo, r);
-}
 
 __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
