@@ -1,0 +1,102 @@
+"""GPU (-m gpu): the tcgen05 (5th-generation tensor core) path of the test-function net.
+* the 3xTF32 building block (C-ABI `xw_umma_probe`) against fp64 numpy: plain TF32 is NOT accurate enough
+  for the 1e-4 / 1e-3 tolerances of the path, the error-compensated form is;
+* the kernel variants (tensor-core pipeline, serial tensor-core backward, FP32 tile engine, one thread per
+  point) all reproduce the golden vectors of the unmodified reference and agree with each other."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import xnode_wan_b200 as xw
+from tests import _golden as G
+from tests import _lowlevel as LL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return xw._lib.get()
+
+
+def _probe(lib, A, B, K, N, terms):
+    dev = torch.device("cuda:0")
+    D = torch.full((128, N), float("nan"), device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    Ad, Bd = A.to(dev), B.to(dev)            # (kept alive: a temporary would be recycled before the launch)
+    lib.call("xw_umma_probe", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, N, terms, err.data_ptr(),
+             torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0, "a bounded mbarrier wait expired"
+    return D.cpu().double().numpy()
+
+
+@pytest.mark.parametrize("K,N", [(8, 16), (24, 56), (56, 56), (64, 64)])
+def test_umma_probe_3xtf32_accuracy(lib, K, N):
+    g = torch.Generator().manual_seed(K * 100 + N)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    ref = A.double().numpy() @ B.double().numpy().T
+    scale = np.abs(ref).max()
+    for ts in (0, 10):          # A from shared memory / A from tensor memory
+        e1 = np.abs(_probe(lib, A, B, K, N, 1 + ts) - ref).max() / scale
+        e3 = np.abs(_probe(lib, A, B, K, N, 3 + ts) - ref).max() / scale
+        assert 1e-5 < e1 < 5e-3, e1          # one TF32 MMA: 10-bit mantissas
+        assert e3 < 5e-6, e3                 # 3xTF32: fp32 level
+
+
+def test_umma_probe_rejects_bad_shapes(lib):
+    z = torch.zeros(128 * 64, device="cuda:0")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    with pytest.raises(xw._lib.XwError):
+        lib.call("xw_umma_probe", z.data_ptr(), z.data_ptr(), z.data_ptr(), 12, 16, 3, err.data_ptr(), None)
+    with pytest.raises(xw._lib.XwError):
+        lib.call("xw_umma_probe", z.data_ptr(), z.data_ptr(), z.data_ptr(), 8, 16, 2, err.data_ptr(), None)
+
+
+VARIANTS = [("tc", None), ("tc", "serial"), ("tile", None)]
+
+
+@pytest.mark.parametrize("name", ["cube_d20_ex41", "cube_d3_rk4", "cone_d5_g2", "hourglass_d5_g4_reentry"])
+def test_kernel_variants_agree_and_match_golden(lib, name):
+    c = G.load(name)
+    z = c["z"]
+    out = {}
+    old = {k: os.environ.get(k) for k in ("XW_VNET_IMPL", "XW_VNET_BWD")}
+    try:
+        for impl, bwd in VARIANTS:
+            os.environ["XW_VNET_IMPL"] = impl
+            if bwd:
+                os.environ["XW_VNET_BWD"] = bwd
+            else:
+                os.environ.pop("XW_VNET_BWD", None)
+            out[(impl, bwd)] = LL.run_case(lib, LL.TorchBackend(), c)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for key, r in out.items():
+        for k in ("I", "S"):
+            assert abs(r[k] - float(z[k])) <= 1e-4 * abs(float(z[k])) + 1e-9, (key, k)
+        for i, (a, b) in enumerate(zip(r["grads_v"], c["gv"])):
+            assert G.rel(a, b) < 1e-3, (key, "grad_v", i, G.rel(a, b))
+    # generation 1 (one thread per point) has no test-function cache: asking for it fails loudly
+    os.environ["XW_VNET_IMPL"] = "points"
+    try:
+        with pytest.raises(xw._lib.XwError):
+            LL.run_case(lib, LL.TorchBackend(), c)
+    finally:
+        os.environ.pop("XW_VNET_IMPL", None)
+        if old["XW_VNET_IMPL"] is not None:
+            os.environ["XW_VNET_IMPL"] = old["XW_VNET_IMPL"]
+    base = out[("tile", None)]
+    for key, r in out.items():
+        # (I is a difference of Monte-Carlo sums: on the small sphere groups it cancels to ~1e-2 of its terms)
+        assert abs(r["I"] - base["I"]) <= 2e-4 * abs(base["I"]) + 1e-9, key
+        assert abs(r["loss_v"] - base["loss_v"]) <= 2e-4 * abs(base["loss_v"]) + 1e-6, key
+        for a, b in zip(r["grads_v"], base["grads_v"]):
+            assert G.rel(a, b) < 3e-4, (key, G.rel(a, b))

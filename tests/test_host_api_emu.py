@@ -3,6 +3,8 @@ autograd.Function) driven end to end with the CPU EMULATION build of the kernels
 the golden vectors of the unmodified reference.  Checks host logic only (packing, strides,
 normalisers, side-effect terms, state-dict names, sampler RNG order); the real sm_100a library is
 checked by the `-m gpu` tests."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -258,3 +260,17 @@ def test_training_iteration_on_cone_domain(emu):
     after = list(s.u_net.parameters()) + list(s.v_net.parameters())
     assert all(torch.isfinite(a).all() for a in after)
     assert any(not torch.equal(a, b) for a, b in zip(before, after))
+
+
+def test_product_library_carries_tcgen05_code():
+    """the shipped .so holds tensor-core (tcgen05) SASS for the test-function kernels: UTCHMMA = tcgen05.mma,
+    LDTM / STTM = tcgen05.ld / st (B200_PROFILING.md).  Checked with cuobjdump on the build box (no GPU needed)."""
+    import shutil
+    import subprocess
+    from xnode_wan_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the product library is not available")
+    sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM"):
+        assert mnemonic in sass, mnemonic

@@ -11,7 +11,8 @@ A = torch.randn(128, K, generator=g); B = torch.randn(N, K, generator=g)
 ref = A.double().numpy() @ B.double().numpy().T
 D = torch.full((128, N), 777.0, device=dev); err = torch.zeros(1, dtype=torch.int32, device=dev)
 # pre-fill tensor memory lanes with a marker by a plain M=128 run of zeros first is not possible; just read
-lib.call("xw_umma_probe", A.to(dev).data_ptr(), B.to(dev).data_ptr(), D.data_ptr(), K, N, 3, err.data_ptr(), torch.cuda.current_stream().cuda_stream)
+Ad, Bd = A.to(dev), B.to(dev)
+lib.call("xw_umma_probe", Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, N, 3, err.data_ptr(), torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 d = D.cpu().double().numpy()
 for lane in range(128):

@@ -27,7 +27,8 @@ for MO, NI in ((56, 56), (52, 24), (8, 8), (128, 64)):
     ref = P.double().numpy().T @ Q.double().numpy()
     for terms in (1, 3):
         D = torch.full((128, NI), float("nan"), device=dev); err = torch.zeros(1, dtype=torch.int32, device=dev)
-        lib.call("xw_umma_probe", P.to(dev).data_ptr(), Q.to(dev).data_ptr(), D.data_ptr(), MO, NI, -terms, err.data_ptr(),
+        Pd, Qd = P.to(dev), Q.to(dev)
+        lib.call("xw_umma_probe", Pd.data_ptr(), Qd.data_ptr(), D.data_ptr(), MO, NI, -terms, err.data_ptr(),
                  torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         d = D.cpu().double().numpy()

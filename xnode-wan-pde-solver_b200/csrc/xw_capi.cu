@@ -418,6 +418,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     }
     const size_t smem = smem_vnet_fwd(m->d);
     if (use_point_kernels()) {
+        if (vcache_mode != 0) return fail("XW_VNET_IMPL=points (generation-1 kernels) has no test-function cache: call with vcache_mode 0");
         if (XW_SET_SMEM((xw::k_vnet_points<kHV, 1>), smem)) return 1;
         XW_LAUNCH((xw::k_vnet_points<kHV, 1>), grid_for((long long)n * L, 128, 8), 128, smem, stream, b);
         return XW_CHECK_LAUNCH("k_vnet_points<interior>");
