@@ -80,6 +80,25 @@ __device__ void stage_images(const WImages& w, const float* XW_RESTRICT th, int 
     __syncthreads();
 }
 
+
+// relu masks as SIGN bits, one funnel shift per element: after the loop bit (31 - o) of s0 is the sign of v[o]
+// (o < 32), bit (31 - (o - 32)) of s1 the sign of v[o] (o >= 32).  A set bit means "relu output is 0" (-0.0 counts
+// as negative, +0.0 as positive: both give 0 either way).
+__device__ __forceinline__ void sign_masks(const float (&v)[KP], uint32_t& s0, uint32_t& s1) {
+    s0 = 0u; s1 = 0u;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) s0 = __funnelshift_l(__float_as_uint(v[o]), s0, 1);
+#pragma unroll
+    for (int o = 32; o < HV; ++o) s1 = __funnelshift_l(__float_as_uint(v[o]), s1, 1);
+    s1 <<= (64 - HV);                       // left-align: unit o >= 32 sits at bit 31 - (o - 32)
+}
+__device__ __forceinline__ void apply_sign_masks(float (&v)[KP], uint32_t s0, uint32_t s1) {
+#pragma unroll
+    for (int o = 0; o < 32; ++o) v[o] = ((s0 >> (31 - o)) & 1u) ? 0.f : v[o];
+#pragma unroll
+    for (int o = 32; o < HV; ++o) v[o] = ((s1 >> (31 - (o - 32))) & 1u) ? 0.f : v[o];
+}
+
 // D[128 x NP] = A[128 x 8*ksteps] * B^T, A from tensor memory (hi / lo column blocks), B images in smem.
 // KS > 0: compile-time k-step count (straight-line issue: one IADD on the descriptor per MMA)
 template <int KS>
@@ -207,17 +226,11 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
         // ---- hidden layers -------------------------------------------------------------------
 #pragma unroll 1
         for (int layer = 0; layer < a.nv; ++layer) {
-            uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll
-            for (int o = 0; o < 32; ++o) m0 |= (h[o] > 0.f ? 1u : 0u) << o;
-#pragma unroll
-            for (int o = 32; o < HV; ++o) m1 |= (h[o] > 0.f ? 1u : 0u) << (o - 32);
+            uint32_t m0, m1;
+            sign_masks(h, m0, m1);
             m0 = __shfl_sync(0xffffffffu, m0, lane & 15);      // the value row's mask, for both rows of the point
             m1 = __shfl_sync(0xffffffffu, m1, lane & 15);
-#pragma unroll
-            for (int o = 0; o < 32; ++o) h[o] = ((m0 >> o) & 1u) ? h[o] : 0.f;
-#pragma unroll
-            for (int o = 32; o < HV; ++o) h[o] = ((m1 >> (o - 32)) & 1u) ? h[o] : 0.f;
+            apply_sign_masks(h, m0, m1);
             h[BIASC] = is_tan ? 0.f : 1.f;
 #pragma unroll
             for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
@@ -557,9 +570,10 @@ __global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
 // =============================================================================================
 // The same backward as a three-stage warp-specialised pipeline (384 threads, one CTA per SM):
 //   F (warps 0-3)  : forward recompute of tile t+1, output layer, cotangent G, dWz, delta_nv -> mailbox (D_f)
-//   R (warps 4-7)  : the delta chain of tile t: delta_k -> A_r (tensor memory), R-op, relu mask
-//   P (warps 8-11) : reads delta_k back from A_r, builds the transposed images of delta_k and r_{k-1},
-//                    issues the weight-gradient MMAs (P-op), flushes the accumulators per tile
+//   R (warps 4-7)  : the delta chain of tile t: delta_k -> A_r (tensor memory) and its transposed hi/lo image
+//                    (shared memory), R-op, relu mask
+//   P (warps 8-11) : builds the transposed image of (r_{k-1} | 1), issues the weight-gradient MMAs (P-op,
+//                    M = 64) as soon as both images stand, flushes the accumulators per tile
 // Thread j of every group owns point row j = TMEM lane j (a warp reaches lane quadrant warp % 4).
 // The tensor pipe then always has queued work from three independent issuers.  Every cross-group
 // hand-off is an mbarrier with a bounded wait; F's activations and relu masks travel through a
@@ -587,14 +601,14 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     float* gimg = rT_lo + TIMG;                                  // [56][GS] (+512: overrun pad of the M = 128 reads)
     float* zacc = gimg + KP * GS + 512;                          // [64] dWz | dbz
     uint64_t* mb = reinterpret_cast<uint64_t*>(zacc + 64);
-    uint64_t *mF = mb, *mR = mb + 1, *mP = mb + 2, *mFD = mb + 3, *mFC = mb + 4, *mDP = mb + 5, *mPR = mb + 6;
+    uint64_t *mF = mb, *mR = mb + 1, *mP = mb + 2, *mFD = mb + 3, *mFC = mb + 4, *mDP = mb + 5, *mPC = mb + 6;
     uint32_t* slot = reinterpret_cast<uint32_t*>(mb + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid >> 7, j = tid & 127;
     for (int i = tid; i < 4 * TIMG + KP * GS + 512 + 64; i += blockDim.x) dT_hi[i] = 0.f;
     stage_images(w, a.theta, a.d, a.Hvr, kin);
     if (tid == 0) {
         umma::mbar_init(mF, 1); umma::mbar_init(mR, 1); umma::mbar_init(mP, 1);
-        umma::mbar_init(mFD, 128); umma::mbar_init(mFC, 128); umma::mbar_init(mDP, 128); umma::mbar_init(mPR, 128);
+        umma::mbar_init(mFD, 128); umma::mbar_init(mFC, 128); umma::mbar_init(mDP, 128); umma::mbar_init(mPC, 128);
     }
     if (warp == 0) umma::tmem_alloc(slot, 512);
     umma::fence_before();
@@ -602,7 +616,10 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     umma::fence_after();
     const uint32_t tbase = *slot;
     const uint32_t lane_addr = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
-    const uint32_t idesc = umma::idesc_tf32(128, NP), idesc_in = umma::idesc_tf32(128, kin);
+    const uint32_t idesc = umma::idesc_tf32(128, NP);
+    // weight-gradient MMAs: M = 64 (56 output units): half the shared-memory operand reads of M = 128;
+    // accumulator row o lands in tensor-memory lane 32 * (o / 16) + o % 16
+    const uint32_t idesc_p = umma::idesc_tf32(64, NP), idesc_pin = umma::idesc_tf32(64, kin);
     const long long npts = (long long)a.n * a.L;
     const long long ntiles = (npts + 127) / 128;
     const int L = a.L, nv = a.nv, nvs = nv > 0 ? nv : 1;
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     if (wg == 0) {
         // ======================================================================== F: forward of every tile
         const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
-        uint32_t pF = 0, pFC = 0;
+        uint32_t pF = 0, pFC = 0, pPC = 0;
         int it = 0;
         for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
             const long long p = tix * 128 + j;
@@ -637,7 +654,10 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
             }
             umma::tmem_wait_st();
             umma::fence_before();
-            if (it > 0) mbar_wait_or_trap(mFC, pFC);              // R has taken the previous tile out of the mailbox
+            if (it > 0) {                                         // R has taken the previous tile out of the mailbox,
+                mbar_wait_or_trap(mFC, pFC);                      // and P has seen its activations land
+                mbar_wait_or_trap(mPC, pPC);
+            }
             umma::group_sync(1);
             if (j == 0) {
                 umma::fence_after();
@@ -650,11 +670,8 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
             umma::tmem_ld56(lane_addr + P3_DF, h);
 #pragma unroll 1
             for (int layer = 0; layer < nv; ++layer) {
-                uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll
-                for (int o = 0; o < 32; ++o) m0 |= (h[o] > 0.f ? 1u : 0u) << o;
-#pragma unroll
-                for (int o = 32; o < HV; ++o) m1 |= (h[o] > 0.f ? 1u : 0u) << (o - 32);
+                uint32_t m0, m1;
+                sign_masks(h, m0, m1);
 #pragma unroll
                 for (int o = 0; o < HV; ++o) h[o] = fmaxf(h[o], 0.f);
                 h[BIASC] = 0.f; h[BIASC + 1] = 0.f;
@@ -715,8 +732,10 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
         }
     } else if (wg == 1) {
         // ======================================================================== R: the delta chain
-        uint32_t pR = 0, pFD = 0, pPR = 0;
-        bool wrote = false;
+        // R also writes the transposed hi/lo images of delta_k (it holds the split values anyway); they may
+        // only be overwritten once the P-op that read the previous delta has completed (mP)
+        uint32_t pR = 0, pFD = 0, pPr = 0;
+        bool published = false;
         int it = 0;
         for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
             const f4* sb = scr + (size_t)(it & 1) * nvs * 14 * 128;
@@ -728,35 +747,42 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
             umma::mbar_arrive(mFC);
 #pragma unroll 1
             for (int k = nv; k >= 0; --k) {
-                if (wrote) mbar_wait_or_trap(mPR, pPR);          // P has read the previous delta out of A_r
-                store_a_row_at(lane_addr + P3_AR, lane_addr + P3_AR + KP, h);
-                umma::tmem_wait_st();
-                umma::fence_before();
-                umma::mbar_arrive(mDP);
-                wrote = true;
-                if (k == 0) break;
-                umma::group_sync(2);
-                if (j == 0) {
-                    umma::fence_after();
-                    issue_3xtf32<KP / 8>(tbase + P3_DR, tbase + P3_AR, tbase + P3_AR + KP, w.wht_hi, w.wht_lo, 0, idesc);
-                    umma::commit(mR);
+                if (k > 0) {                                     // R-op first: it does not depend on the images
+                    store_a_row_at(lane_addr + P3_AR, lane_addr + P3_AR + KP, h);
+                    umma::tmem_wait_st();
+                    umma::fence_before();
+                    umma::group_sync(2);
+                    if (j == 0) {
+                        umma::fence_after();
+                        issue_3xtf32<KP / 8>(tbase + P3_DR, tbase + P3_AR, tbase + P3_AR + KP, w.wht_hi, w.wht_lo, 0, idesc);
+                        umma::commit(mR);
+                    }
                 }
+                if (published) mbar_wait_or_trap(mP, pPr);       // the P-op that read the previous delta image is done
+#pragma unroll
+                for (int o = 0; o < HV; ++o) {
+                    const float hi = umma::tf32_hi(h[o]);
+                    dT_hi[t_off(o, j)] = hi;
+                    dT_lo[t_off(o, j)] = h[o] - hi;
+                }
+                umma::fence_smem_to_async();
+                umma::mbar_arrive(mDP);
+                published = true;
+                if (k == 0) break;
                 const f4 mv = sb[(size_t)((k - 1) * 14 + 13) * 128];
                 const uint32_t m0 = __float_as_uint(mv.x), m1 = __float_as_uint(mv.y);
                 mbar_wait_or_trap(mR, pR);
                 umma::fence_after();
                 umma::tmem_ld56(lane_addr + P3_DR, h);
-#pragma unroll
-                for (int o = 0; o < 32; ++o) h[o] = ((m0 >> o) & 1u) ? h[o] : 0.f;
-#pragma unroll
-                for (int o = 32; o < HV; ++o) h[o] = ((m1 >> (o - 32)) & 1u) ? h[o] : 0.f;
+                umma::fence_before();
+                apply_sign_masks(h, m0, m1);
 #pragma unroll
                 for (int o = HV; o < KP; ++o) h[o] = 0.f;
             }
         }
     } else {
         // ======================================================================== P: weight gradients
-        uint32_t pP = 0, pDP = 0;
+        uint32_t pP = 0, pDP = 0, pFDp = 0;
         bool pending = false;
         int it = 0;
         for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
@@ -767,28 +793,17 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
             const float* xr = a.p.x + n * a.p.x_sn + (long long)l * a.p.x_sl;
             const float tval = valid ? a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl] : 0.f;
             const f4* sb = scr + (size_t)(it & 1) * nvs * 14 * 128;
+            mbar_wait_or_trap(mFD, pFDp);                      // F's scratch writes of this tile are visible from here on
+            umma::mbar_arrive(mPC);                            // (F may not finish the NEXT tile before P has seen this one)
 #pragma unroll 1
             for (int k = nv; k >= 0; --k) {
-                // r_{k-1} and delta_k are fetched while the previous P-op still runs; only the image stores wait for it
+                // r_{k-1} is fetched while the previous P-op still runs; only the image stores wait for it
                 f4 rv4[13];
-                mbar_wait_or_trap(mDP, pDP);                   // (also what makes F's scratch writes of this tile visible)
-                umma::fence_after();
                 if (k > 0) {
 #pragma unroll
                     for (int c = 0; c < 13; ++c) rv4[c] = sb[(size_t)((k - 1) * 14 + c) * 128];
                 }
-                {
-                    float v[KP];
-                    umma::tmem_ld56(lane_addr + P3_AR, v);
-                    if (pending) { mbar_wait_or_trap(mP, pP); pending = false; }     // the images are free again
-#pragma unroll
-                    for (int o = 0; o < HV; ++o) dT_hi[t_off(o, j)] = v[o];
-                    umma::tmem_ld56(lane_addr + P3_AR + KP, v);
-                    umma::fence_before();
-                    umma::mbar_arrive(mPR);
-#pragma unroll
-                    for (int o = 0; o < HV; ++o) dT_lo[t_off(o, j)] = v[o];
-                }
+                if (pending) { mbar_wait_or_trap(mP, pP); pending = false; }     // the images are free again
                 if (k > 0) {
 #pragma unroll
                     for (int c = 0; c < 13; ++c) {
@@ -817,11 +832,12 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     }
                 }
                 umma::fence_smem_to_async();
+                mbar_wait_or_trap(mDP, pDP);                   // R has written the delta_k images
                 umma::group_sync(3);
                 if (j == 0) {
                     umma::fence_after();
-                    if (k > 0) issue_pop(tbase + P3_WH, dT_hi, dT_lo, rT_hi, rT_lo, idesc, k < nv ? 1u : 0u);
-                    else issue_pop(tbase + P3_WI, dT_hi, dT_lo, rT_hi, rT_lo, idesc_in, 0u);
+                    if (k > 0) issue_pop(tbase + P3_WH, dT_hi, dT_lo, rT_hi, rT_lo, idesc_p, k < nv ? 1u : 0u);
+                    else issue_pop(tbase + P3_WI, dT_hi, dT_lo, rT_hi, rT_lo, idesc_pin, 0u);
                     umma::commit(mP);
                 }
                 pending = true;
@@ -829,12 +845,14 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
             mbar_wait_or_trap(mP, pP);
             pending = false;
             umma::fence_after();
-            if ((warp & 3) < 2) {                                 // accumulator rows o = j < 56
-                float* grow = gimg + (j < KP ? j : 0) * GS;
+            {                                                     // lanes 0..15 of warp q hold accumulator rows 16 q + lane
+                const int orow = 16 * (warp & 3) + lane;
+                const bool has = lane < 16 && orow < KP;
+                float* grow = gimg + (has ? orow : 0) * GS;
                 if (nv > 0) {
                     float acc[KP];
                     umma::tmem_ld56(lane_addr + P3_WH, acc);
-                    if (j < KP) {
+                    if (has) {
 #pragma unroll
                         for (int i = 0; i < KP; ++i) grow[i] += acc[i];
                     }
@@ -843,7 +861,7 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 for (int c8 = 0; c8 < kin; c8 += 8) {
                     float acc[8];
                     umma::tmem_ld8(lane_addr + P3_WI + c8, acc);
-                    if (j < KP) {
+                    if (has) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) grow[KP + c8 + e] += acc[e];
                     }
