@@ -410,6 +410,13 @@ template <int O, int I, int ROFF, class Dst>
 XW_DEV void outer_auto(const float (&dl)[O], const float (&r)[I], float* stg, Dst dst) {
     using Sh = OuterShape<O, I>;
     static_assert(Sh::rows_d <= ROFF, "d-side staging rows");
+#ifndef XW_EMU
+    // XNODE staging (32 + 24 rows): tensor-core fragments fit when O <= 32 and I <= 24
+    if constexpr (ROFF == 32 && O <= 32 && I <= 24 && O >= 8) {
+        warp_outer_mma<O, I>(dl, r, stg, stg + ROFF * kStgLd, dst);
+        return;
+    }
+#endif
     warp_outer<O, I, Sh::BO, Sh::NBO, Sh::BI, Sh::NBI>(dl, r, stg, stg + ROFF * kStgLd, dst);
 }
 constexpr int kStgRowsU = 32 + 24;     // XNODE: d-side <= 32 rows, r-side <= 24 rows (warp_outer_dyn chunks of 16)

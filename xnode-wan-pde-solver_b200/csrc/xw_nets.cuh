@@ -379,6 +379,83 @@ XW_DEV void warp_outer(const float (&dl)[O], const float (&r)[I], float* stg_d, 
     XW_SYNCWARP();
 }
 
+
+#ifndef XW_EMU
+// ---------------------------------------------------------------------------------------------
+// the same contraction on the warp-level tensor-core path (mma.sync m16n8k8, TF32 with 3xTF32 error
+// compensation: fp32-level result): M = o, N = i, K = the 32 lanes.  The fragments come straight out of
+// the lane-contiguous staging rows (row stride 36 floats: the 8 x 4 threads of a fragment load hit 32
+// different banks), so one 16 x 8 x 32 block costs 24 scalar shared-memory loads instead of the
+// (BO + BI) x 8 LDS.128 of the FFMA version -- the XNODE backward is LSU bound, not FMA bound.
+// Rows / columns beyond O / I read stale staging rows; they only reach outputs that are discarded.
+// ---------------------------------------------------------------------------------------------
+XW_DEV void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+XW_DEV void split_tf32(float v, unsigned& hi, unsigned& lo) {
+    hi = __float_as_uint(v) & 0xFFFFE000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+template <int O, int I, class Dst>
+XW_DEV void warp_outer_mma(const float (&dl)[O], const float (&r)[I], float* stg_d, float* stg_r, Dst dst) {
+    constexpr int MT = (O + 15) / 16, NT = (I + 7) / 8;
+    const int lane = XW_TID & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int o = 0; o < O; ++o) stg_d[o * kStgLd + lane] = dl[o];
+#pragma unroll
+    for (int i = 0; i < I; ++i) stg_r[i * kStgLd + lane] = r[i];
+    XW_SYNCWARP();
+    float c[MT][NT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c[m][n][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        unsigned ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const float* pa = stg_d + (16 * m + g) * kStgLd + 8 * ks + t;
+            split_tf32(pa[0], ah[m][0], al[m][0]);
+            split_tf32(pa[8 * kStgLd], ah[m][1], al[m][1]);
+            split_tf32(pa[4], ah[m][2], al[m][2]);
+            split_tf32(pa[8 * kStgLd + 4], ah[m][3], al[m][3]);
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const float* pb = stg_r + (8 * n + g) * kStgLd + 8 * ks + t;
+            split_tf32(pb[0], bh[n][0], bl[n][0]);
+            split_tf32(pb[4], bh[n][1], bl[n][1]);
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                mma_tf32_16x8x8(c[m][n], al[m], bh[n]);       // small terms first
+                mma_tf32_16x8x8(c[m][n], ah[m], bl[n]);
+                mma_tf32_16x8x8(c[m][n], ah[m], bh[n]);
+            }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int o = 16 * m + g + (e >> 1) * 8, i = 8 * n + 2 * t + (e & 1);
+                if (o < O && i < I) {
+                    float* p = dst(o, i);
+                    if (p) *p += c[m][n][e];
+                }
+            }
+    XW_SYNCWARP();
+}
+#endif
+
 // same for a RUNTIME number of columns (e.g. the d spatial inputs): colval(i) returns this lane's
 // i-th column value; columns are processed in chunks of 8*BI (r-side staging rows), rows in passes of 4*BO.
 template <int O, int BO, int BI, class ColVal, class Dst>
