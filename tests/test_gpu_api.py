@@ -62,10 +62,13 @@ def _loss_and_grads(s, dom, X, XV, BX, phase):
     return val, [q.grad.detach().clone() for q in net.parameters()]
 
 
-@pytest.mark.parametrize("d,N,Nb", [(20, 2048 + 37, 1024 + 5), (100, 300 + 7, 200 + 3)])
+@pytest.mark.parametrize("d,N,Nb", [(20, 2048 + 37, 1024 + 5), (100, 300 + 7, 200 + 3), (53, 500 + 3, 200 + 1), (55, 500 + 3, 200 + 1),
+                                    (30, 700 + 9, 300 + 7)])
 def test_mid_size_against_oracle(d, N, Nb):
     """d=20, N=2085 (several CTAs per kernel, ragged tail tiles) and d=100 (BASELINE configs[4]: V = 2^100,
-    float shape_param) vs the fp64 closed-form oracle"""
+    float shape_param) vs the fp64 closed-form oracle; d=53 / d=55 straddle the largest input width of the
+    tensor-core backward (k-padded input 56 -> 64: FP32 tile backward, two tile streams in the forward), d=30 is
+    a 32-wide input"""
     s, prob = _rand_case(d, N, Nb, 3)
     dom = s.new_domain()
     pts = xw.Comb_loader(N, Nb, dom, DEV)
