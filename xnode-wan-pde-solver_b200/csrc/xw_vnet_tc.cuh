@@ -582,6 +582,33 @@ __global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
 constexpr int P3_DF = 0, P3_AF = 64, P3_DR = 176, P3_AR = 240, P3_WH = 352, P3_WI = 416;
 
 
+// one HALF of a P-op: the 64 points of half h (8 k-steps of 8 points), all three terms.  The two halves have their own
+// images, barriers and issuing threads: while one half's MMAs run, the other half's images are being rewritten.
+__device__ __forceinline__ void issue_pop_half(uint32_t tD, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
+                                               uint32_t idesc) {
+    constexpr uint64_t kStep = (2 * TCS * 4) >> 4;
+    const uint64_t ah = umma::smem_desc(a_hi, TCS * 4, 128), al = umma::smem_desc(a_lo, TCS * 4, 128);
+    const uint64_t bh = umma::smem_desc(b_hi, TCS * 4, 128), bl = umma::smem_desc(b_lo, TCS * 4, 128);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+            umma::mma_tf32(tD, (t == 0 ? al : ah) + kStep * ks, (t == 1 ? bl : bh) + kStep * ks, idesc, 1u);
+    }
+}
+// clears this thread's lane of the dWh / dWi accumulator columns
+__device__ __forceinline__ void zero_acc(uint32_t lane_addr, int kin) {
+    uint32_t z[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) z[i] = 0u;
+    umma::tmem_st56(lane_addr + 352, z);
+    float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c8 = 0; c8 < kin; c8 += 8) umma::tmem_st8(lane_addr + 416 + c8, z8);
+}
+constexpr int THALF = 16 * TCS;              // floats of one half image (64 points = 16 chunks)
+// element (row, point r) of half (r >> 6) of an image
+__device__ __forceinline__ int th_off(int row, int r) { return (r >> 6) * THALF + ((r & 63) >> 2) * TCS + (row >> 3) * 32 + (row & 7) * 4 + (r & 3); }
+
 __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = a.d + 1, kin = kin_of(a.d), GS = KP + kin;
@@ -601,14 +628,16 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     float* gimg = rT_lo + TIMG;                                  // [56][GS] (+512: overrun pad of the M = 128 reads)
     float* zacc = gimg + KP * GS + 512;                          // [64] dWz | dbz
     uint64_t* mb = reinterpret_cast<uint64_t*>(zacc + 64);
-    uint64_t *mF = mb, *mR = mb + 1, *mP = mb + 2, *mFD = mb + 3, *mFC = mb + 4, *mDP = mb + 5, *mPC = mb + 6;
-    uint32_t* slot = reinterpret_cast<uint32_t*>(mb + 8);
+    uint64_t *mF = mb, *mR = mb + 1, *mFD = mb + 3, *mFC = mb + 4, *mPC = mb + 6;
+    uint64_t* mPh = mb + 8;          // [2] P-op of half h complete
+    uint64_t* mDPh = mb + 10;        // [2] delta image of half h written (64 arrivals)
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mb + 12);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid >> 7, j = tid & 127;
     for (int i = tid; i < 4 * TIMG + KP * GS + 512 + 64; i += blockDim.x) dT_hi[i] = 0.f;
     stage_images(w, a.theta, a.d, a.Hvr, kin);
     if (tid == 0) {
-        umma::mbar_init(mF, 1); umma::mbar_init(mR, 1); umma::mbar_init(mP, 1);
-        umma::mbar_init(mFD, 128); umma::mbar_init(mFC, 128); umma::mbar_init(mDP, 128); umma::mbar_init(mPC, 128);
+        umma::mbar_init(mF, 1); umma::mbar_init(mR, 1); umma::mbar_init(mPh, 1); umma::mbar_init(mPh + 1, 1);
+        umma::mbar_init(mFD, 128); umma::mbar_init(mFC, 128); umma::mbar_init(mDPh, 64); umma::mbar_init(mDPh + 1, 64); umma::mbar_init(mPC, 128);
     }
     if (warp == 0) umma::tmem_alloc(slot, 512);
     umma::fence_before();
@@ -617,6 +646,7 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     const uint32_t tbase = *slot;
     const uint32_t lane_addr = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
     const uint32_t idesc = umma::idesc_tf32(128, NP);
+    const int hh_ = j >> 6;                                      // which 64-point half this thread's row belongs to
     // weight-gradient MMAs: M = 64 (56 output units): half the shared-memory operand reads of M = 128;
     // accumulator row o lands in tensor-memory lane 32 * (o / 16) + o % 16
     const uint32_t idesc_p = umma::idesc_tf32(64, NP), idesc_pin = umma::idesc_tf32(64, kin);
@@ -758,15 +788,15 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                         umma::commit(mR);
                     }
                 }
-                if (published) mbar_wait_or_trap(mP, pPr);       // the P-op that read the previous delta image is done
+                if (published) mbar_wait_or_trap(mPh + hh_, pPr);   // this half's P-op on the previous delta image is done
 #pragma unroll
                 for (int o = 0; o < HV; ++o) {
                     const float hi = umma::tf32_hi(h[o]);
-                    dT_hi[t_off(o, j)] = hi;
-                    dT_lo[t_off(o, j)] = h[o] - hi;
+                    dT_hi[th_off(o, j)] = hi;
+                    dT_lo[th_off(o, j)] = h[o] - hi;
                 }
                 umma::fence_smem_to_async();
-                umma::mbar_arrive(mDP);
+                umma::mbar_arrive(mDPh + hh_);
                 published = true;
                 if (k == 0) break;
                 const f4 mv = sb[(size_t)((k - 1) * 14 + 13) * 128];
@@ -785,6 +815,10 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
         uint32_t pP = 0, pDP = 0, pFDp = 0;
         bool pending = false;
         int it = 0;
+        zero_acc(lane_addr, kin);
+        umma::tmem_wait_st();
+        umma::fence_before();
+        umma::group_sync(3);
         for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
             const long long p = tix * 128 + j;
             const bool valid = p < npts;
@@ -803,7 +837,7 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
 #pragma unroll
                     for (int c = 0; c < 13; ++c) rv4[c] = sb[(size_t)((k - 1) * 14 + c) * 128];
                 }
-                if (pending) { mbar_wait_or_trap(mP, pP); pending = false; }     // the images are free again
+                if (pending) { mbar_wait_or_trap(mPh + hh_, pP); pending = false; }     // this half's images are free again
                 if (k > 0) {
 #pragma unroll
                     for (int c = 0; c < 13; ++c) {
@@ -813,60 +847,64 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                             const int o = 4 * c + e;
                             if (o < HV) {
                                 const float hi = umma::tf32_hi(rv[e]);
-                                rT_hi[t_off(o, j)] = hi;
-                                rT_lo[t_off(o, j)] = rv[e] - hi;
+                                rT_hi[th_off(o, j)] = hi;
+                                rT_lo[th_off(o, j)] = rv[e] - hi;
                             }
                         }
                     }
-                    rT_hi[t_off(BIASC, j)] = 1.f; rT_lo[t_off(BIASC, j)] = 0.f;
+                    rT_hi[th_off(BIASC, j)] = 1.f; rT_lo[th_off(BIASC, j)] = 0.f;
 #pragma unroll
-                    for (int o = BIASC + 1; o < KP; ++o) { rT_hi[t_off(o, j)] = 0.f; rT_lo[t_off(o, j)] = 0.f; }
+                    for (int o = BIASC + 1; o < KP; ++o) { rT_hi[th_off(o, j)] = 0.f; rT_lo[th_off(o, j)] = 0.f; }
                 } else {
 #pragma unroll 1
                     for (int c = 0; c < kin; ++c) {
                         float v = 0.f;
                         if (valid) v = c == 0 ? tval : (c <= a.d ? xr[c - 1] : (c == C ? 1.f : 0.f));
                         const float hi = umma::tf32_hi(v);
-                        rT_hi[t_off(c, j)] = hi;
-                        rT_lo[t_off(c, j)] = v - hi;
+                        rT_hi[th_off(c, j)] = hi;
+                        rT_lo[th_off(c, j)] = v - hi;
                     }
                 }
                 umma::fence_smem_to_async();
-                mbar_wait_or_trap(mDP, pDP);                   // R has written the delta_k images
-                umma::group_sync(3);
-                if (j == 0) {
+                mbar_wait_or_trap(mDPh + hh_, pDP);            // R has written this half's delta_k image
+                asm volatile("bar.sync %0, 64;" ::"r"(4 + hh_) : "memory");       // the 64 threads of this half
+                if ((j & 63) == 0) {
                     umma::fence_after();
-                    if (k > 0) issue_pop(tbase + P3_WH, dT_hi, dT_lo, rT_hi, rT_lo, idesc_p, k < nv ? 1u : 0u);
-                    else issue_pop(tbase + P3_WI, dT_hi, dT_lo, rT_hi, rT_lo, idesc_pin, 0u);
-                    umma::commit(mP);
+                    const int ho = hh_ * THALF;
+                    issue_pop_half(tbase + (k > 0 ? P3_WH : P3_WI), dT_hi + ho, dT_lo + ho, rT_hi + ho, rT_lo + ho, k > 0 ? idesc_p : idesc_pin);
+                    umma::commit(mPh + hh_);
                 }
                 pending = true;
             }
-            mbar_wait_or_trap(mP, pP);
+            mbar_wait_or_trap(mPh + hh_, pP);
             pending = false;
+            umma::group_sync(3);                                  // both halves' last P-ops are complete
             umma::fence_after();
             {                                                     // lanes 0..15 of warp q hold accumulator rows 16 q + lane
                 const int orow = 16 * (warp & 3) + lane;
                 const bool has = lane < 16 && orow < KP;
                 float* grow = gimg + (has ? orow : 0) * GS;
-                if (nv > 0) {
-                    float acc[KP];
-                    umma::tmem_ld56(lane_addr + P3_WH, acc);
-                    if (has) {
+                float acc[KP];
+                umma::tmem_ld56(lane_addr + P3_WH, acc);
+                if (has && nv > 0) {
 #pragma unroll
-                        for (int i = 0; i < KP; ++i) grow[i] += acc[i];
-                    }
+                    for (int i = 0; i < KP; ++i) grow[i] += acc[i];
                 }
 #pragma unroll 1
                 for (int c8 = 0; c8 < kin; c8 += 8) {
-                    float acc[8];
-                    umma::tmem_ld8(lane_addr + P3_WI + c8, acc);
+                    float a8[8];
+                    umma::tmem_ld8(lane_addr + P3_WI + c8, a8);
                     if (has) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) grow[KP + c8 + e] += acc[e];
+                        for (int e = 0; e < 8; ++e) grow[KP + c8 + e] += a8[e];
                     }
                 }
+                // every P-op accumulates (two issuers, no defined first MMA): clear the accumulators for the next tile
+                zero_acc(lane_addr, kin);
             }
+            umma::tmem_wait_st();
+            umma::fence_before();
+            umma::group_sync(3);
             umma::fence_before();
         }
     }
