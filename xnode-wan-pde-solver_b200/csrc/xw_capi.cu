@@ -168,7 +168,7 @@ bool use_point_kernels() {
 bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
 int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
     const int kin = xw::tc::kin_of(m->d);
-    p->smem = (size_t)(4 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64 + 4 * xw::tc::TIMG + xw::tc::KP * (xw::tc::KP + kin) + 512 + 64) * 4 + 128;
+    p->smem = (size_t)(4 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64 + 4 * xw::tc::TIMG + xw::tc::KP * (xw::tc::KP + kin) + 512 + 64 + 256) * 4 + 128;
     if (p->smem > device()->smem_optin) return fail("tensor-core v-net backward needs %zu B shared memory (> %zu)", p->smem, device()->smem_optin);
     const long long ntiles = ((long long)n * L + 127) / 128;
     p->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms));
@@ -519,7 +519,7 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
             if (XW_CHECK_LAUNCH("k_vnet_tc_bwd")) return 1;
         } else {
             if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, pl.smem)) return 1;
-            xw::tc::k_vnet_tc_bwd3<<<pl.grid, 384, pl.smem, (cudaStream_t)stream>>>(t);
+            xw::tc::k_vnet_tc_bwd3<<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
             if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
         }
         return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);

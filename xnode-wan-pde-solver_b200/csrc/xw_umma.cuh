@@ -120,6 +120,26 @@ __device__ __forceinline__ void tmem_st56(uint32_t taddr, const uint32_t (&r)[56
                  "r"(taddr), "r"(taddr + 32), "r"(taddr + 48) : "memory");
 }
 
+// 28 consecutive columns (half a 56-wide row) of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld28(uint32_t taddr, float (&v)[28]) {
+    uint32_t r[28];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%28];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16, %17, %18, %19, %20, %21, %22, %23}, [%29];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%24, %25, %26, %27}, [%30];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27])
+                 : "r"(taddr), "r"(taddr + 16), "r"(taddr + 24) : "memory");
+#pragma unroll
+    for (int i = 0; i < 28; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st28(uint32_t taddr, const uint32_t (&r)[28]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%28], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};\n\t"
+                 "tcgen05.st.sync.aligned.32x32b.x8.b32 [%29], {%16, %17, %18, %19, %20, %21, %22, %23};\n\t"
+                 "tcgen05.st.sync.aligned.32x32b.x4.b32 [%30], {%24, %25, %26, %27};"
+                 :: "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+                 "r"(taddr), "r"(taddr + 16), "r"(taddr + 24) : "memory");
+}
+
 // 8 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];

@@ -609,7 +609,33 @@ constexpr int THALF = 16 * TCS;              // floats of one half image (64 poi
 // element (row, point r) of half (r >> 6) of an image
 __device__ __forceinline__ int th_off(int row, int r) { return (r >> 6) * THALF + ((r & 63) >> 2) * TCS + (row >> 3) * 32 + (row & 7) * 4 + (r & 3); }
 
-__global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
+// relu masks of half a row (28 units) as sign bits: bit (31 - i) = sign of v[i]
+__device__ __forceinline__ uint32_t sign_mask28(const float (&v)[28]) {
+    uint32_t m = 0u;
+#pragma unroll
+    for (int i = 0; i < 28; ++i) m = __funnelshift_l(__float_as_uint(v[i]), m, 1);
+    return m << 4;
+}
+// w0: units 0..27, w1: units 28..55 (bit 31 - (o mod 28)); a set bit zeroes the unit
+__device__ __forceinline__ void apply_sign_masks_2x28(float (&v)[KP], uint32_t w0, uint32_t w1) {
+#pragma unroll
+    for (int o = 0; o < 28; ++o) v[o] = ((w0 >> (31 - o)) & 1u) ? 0.f : v[o];
+#pragma unroll
+    for (int o = 28; o < HV; ++o) v[o] = ((w1 >> (31 - (o - 28))) & 1u) ? 0.f : v[o];
+}
+// split a 56-wide row into the hi / lo A operand, 8 columns at a time (few live registers)
+__device__ __forceinline__ void store_a_row_chunked(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[KP]) {
+#pragma unroll
+    for (int c8 = 0; c8 < KP; c8 += 8) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { hi[e] = umma::tf32_hi(v[c8 + e]); lo[e] = v[c8 + e] - hi[e]; }
+        umma::tmem_st8(addr_hi + c8, hi);
+        umma::tmem_st8(addr_lo + c8, lo);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = a.d + 1, kin = kin_of(a.d), GS = KP + kin;
     const VLayout g(a.d, a.Hvr);
@@ -627,17 +653,19 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     float* rT_lo = rT_hi + TIMG;
     float* gimg = rT_lo + TIMG;                                  // [56][GS] (+512: overrun pad of the M = 128 reads)
     float* zacc = gimg + KP * GS + 512;                          // [64] dWz | dbz
-    uint64_t* mb = reinterpret_cast<uint64_t*>(zacc + 64);
+    float* vex = zacc + 64;                                      // [2][128] partial output dot products of the two F column halves
+    uint64_t* mb = reinterpret_cast<uint64_t*>(vex + 256);
     uint64_t *mF = mb, *mR = mb + 1, *mFD = mb + 3, *mFC = mb + 4, *mPC = mb + 6;
     uint64_t* mPh = mb + 8;          // [2] P-op of half h complete
     uint64_t* mDPh = mb + 10;        // [2] delta image of half h written (64 arrivals)
     uint32_t* slot = reinterpret_cast<uint32_t*>(mb + 12);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid >> 7, j = tid & 127;
+    // roles: F = warps 0-7 (two warps per lane quadrant, 28 columns each), R = warps 8-11, P = warps 12-15
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid < 256 ? 0 : (tid >> 7) - 1, j = tid & 127;
     for (int i = tid; i < 4 * TIMG + KP * GS + 512 + 64; i += blockDim.x) dT_hi[i] = 0.f;
     stage_images(w, a.theta, a.d, a.Hvr, kin);
     if (tid == 0) {
         umma::mbar_init(mF, 1); umma::mbar_init(mR, 1); umma::mbar_init(mPh, 1); umma::mbar_init(mPh + 1, 1);
-        umma::mbar_init(mFD, 128); umma::mbar_init(mFC, 128); umma::mbar_init(mDPh, 64); umma::mbar_init(mDPh + 1, 64); umma::mbar_init(mPC, 128);
+        umma::mbar_init(mFD, 256); umma::mbar_init(mFC, 128); umma::mbar_init(mDPh, 64); umma::mbar_init(mDPh + 1, 64); umma::mbar_init(mPC, 128);
     }
     if (warp == 0) umma::tmem_alloc(slot, 512);
     umma::fence_before();
@@ -657,6 +685,8 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
 
     if (wg == 0) {
         // ======================================================================== F: forward of every tile
+        // 256 threads: thread (ch, j) owns columns [28 ch, 28 ch + 28) of row j
+        const int ch = (tid >> 7) & 1, cb = 28 * ch;
         const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
         uint32_t pF = 0, pFC = 0, pPC = 0;
         int it = 0;
@@ -669,7 +699,7 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
             const float tval = valid ? a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl] : 0.f;
             f4* sb = scr + (size_t)(it & 1) * nvs * 14 * 128;
 #pragma unroll 1
-            for (int c8 = 0; c8 < kin; c8 += 8) {
+            for (int c8 = 8 * ch; c8 < kin; c8 += 16) {           // the two halves alternate over the 8-column chunks
                 float hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -688,73 +718,92 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 mbar_wait_or_trap(mFC, pFC);                      // and P has seen its activations land
                 mbar_wait_or_trap(mPC, pPC);
             }
-            umma::group_sync(1);
-            if (j == 0) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid == 0) {
                 umma::fence_after();
                 issue_3xtf32<0>(tbase + P3_DF, tbase + P3_AF, tbase + P3_AF + KP, w.wi_hi, w.wi_lo, kin / 8, idesc);
                 umma::commit(mF);
             }
-            float h[KP];
+            float h[28];
             mbar_wait_or_trap(mF, pF);
             umma::fence_after();
-            umma::tmem_ld56(lane_addr + P3_DF, h);
+            umma::tmem_ld28(lane_addr + P3_DF + cb, h);
 #pragma unroll 1
             for (int layer = 0; layer < nv; ++layer) {
-                uint32_t m0, m1;
-                sign_masks(h, m0, m1);
+                const uint32_t m = sign_mask28(h);
 #pragma unroll
-                for (int o = 0; o < HV; ++o) h[o] = fmaxf(h[o], 0.f);
-                h[BIASC] = 0.f; h[BIASC + 1] = 0.f;
+                for (int i = 0; i < 28; ++i) h[i] = fmaxf(h[i], 0.f);     // (accumulator columns 50..55 are exactly 0)
+                if (ch == 0) {
 #pragma unroll
-                for (int c = 0; c < 13; ++c) {
-                    f4 v; v.x = h[4 * c]; v.y = h[4 * c + 1]; v.z = h[4 * c + 2]; v.w = h[4 * c + 3];
-                    sb[(size_t)(layer * 14 + c) * 128] = v;
+                    for (int c = 0; c < 7; ++c) {
+                        f4 v; v.x = h[4 * c]; v.y = h[4 * c + 1]; v.z = h[4 * c + 2]; v.w = h[4 * c + 3];
+                        sb[(size_t)(layer * 14 + c) * 128] = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {                         // units 28..51
+                        f4 v; v.x = h[4 * c]; v.y = h[4 * c + 1]; v.z = h[4 * c + 2]; v.w = h[4 * c + 3];
+                        sb[(size_t)(layer * 14 + 7 + c) * 128] = v;
+                    }
                 }
-                { f4 v; v.x = __uint_as_float(m0); v.y = __uint_as_float(m1); v.z = 0.f; v.w = 0.f; sb[(size_t)(layer * 14 + 13) * 128] = v; }
-                h[BIASC] = 1.f;
+                reinterpret_cast<float*>(sb + (size_t)(layer * 14 + 13) * 128)[ch] = __uint_as_float(m);
+                uint32_t rh[28], rl[28];
 #pragma unroll
-                for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
-                store_a_row_at(lane_addr + P3_AF, lane_addr + P3_AF + KP, h);
+                for (int i = 0; i < 28; ++i) {
+                    float v = h[i];
+                    if (ch == 1 && i == BIASC - 28) v = 1.f;              // the bias column
+                    if (ch == 1 && i > BIASC - 28) v = 0.f;
+                    rh[i] = __float_as_uint(v) & 0xFFFFE000u;
+                    rl[i] = __float_as_uint(v - __uint_as_float(rh[i]));
+                }
+                umma::tmem_st28(lane_addr + P3_AF + cb, rh);
+                umma::tmem_st28(lane_addr + P3_AF + KP + cb, rl);
                 umma::tmem_wait_st();
                 umma::fence_before();
-                umma::group_sync(1);
-                if (j == 0) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid == 0) {
                     umma::fence_after();
                     issue_3xtf32<KP / 8>(tbase + P3_DF, tbase + P3_AF, tbase + P3_AF + KP, w.wh_hi, w.wh_lo, 0, idesc);
                     umma::commit(mF);
                 }
                 mbar_wait_or_trap(mF, pF);
                 umma::fence_after();
-                umma::tmem_ld56(lane_addr + P3_DF, h);
+                umma::tmem_ld28(lane_addr + P3_DF + cb, h);
             }
             // output layer, cotangent G, dWz | dbz, delta_nv -> mailbox
             {
-                float v = w.wz[KP];
+                float vp = 0.f;
 #pragma unroll
-                for (int o = 0; o < HV; ++o) {
-                    h[o] = tanh_fast(h[o]);
-                    v = fmaf(w.wz[o], h[o], v);
+                for (int i = 0; i < 28; ++i) {
+                    if (cb + i < HV) {
+                        h[i] = tanh_fast(h[i]);
+                        vp = fmaf(w.wz[cb + i], h[i], vp);
+                    }
                 }
+                vex[ch * 128 + j] = vp;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float v = vex[j] + vex[128 + j] + w.wz[KP];
                 float G = 0.f;
                 if (valid) {
                     const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
                     G = fmaf(k0, a.cot[p], fmaf(k1, v, k2 * W.w));
                 }
-                {
+                if (ch == 0) {
                     const float sb2 = warp_sum(G);
                     if (lane == 0) atomicAdd(zacc + KP, sb2);
                 }
+                uint32_t r[28];
 #pragma unroll
-                for (int o = 0; o < HV; ++o) {
-                    const float t = h[o];
-                    const float sz = warp_sum(G * t);
-                    if (lane == 0) atomicAdd(zacc + o, sz);
-                    h[o] = G * w.wz[o] * (1.f - t * t);
+                for (int i = 0; i < 28; ++i) {
+                    r[i] = 0u;
+                    if (cb + i < HV) {
+                        const float t = h[i];
+                        const float sz = warp_sum(G * t);
+                        if (lane == 0) atomicAdd(zacc + cb + i, sz);
+                        r[i] = __float_as_uint(G * w.wz[cb + i] * (1.f - t * t));
+                    }
                 }
-                uint32_t r[KP];
-#pragma unroll
-                for (int o = 0; o < KP; ++o) r[o] = o < HV ? __float_as_uint(h[o]) : 0u;
-                umma::tmem_st56(lane_addr + P3_DF, r);
+                umma::tmem_st28(lane_addr + P3_DF + cb, r);
                 umma::tmem_wait_st();
                 umma::fence_before();
                 umma::mbar_arrive(mFD);
@@ -778,7 +827,7 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
 #pragma unroll 1
             for (int k = nv; k >= 0; --k) {
                 if (k > 0) {                                     // R-op first: it does not depend on the images
-                    store_a_row_at(lane_addr + P3_AR, lane_addr + P3_AR + KP, h);
+                    store_a_row_chunked(lane_addr + P3_AR, lane_addr + P3_AR + KP, h);
                     umma::tmem_wait_st();
                     umma::fence_before();
                     umma::group_sync(2);
@@ -805,7 +854,7 @@ __global__ void __launch_bounds__(384, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 umma::fence_after();
                 umma::tmem_ld56(lane_addr + P3_DR, h);
                 umma::fence_before();
-                apply_sign_masks(h, m0, m1);
+                apply_sign_masks_2x28(h, m0, m1);
 #pragma unroll
                 for (int o = HV; o < KP; ++o) h[o] = 0.f;
             }
