@@ -690,6 +690,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
         const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
         uint32_t pF = 0, pFC = 0, pPC = 0;
         int it = 0;
+        float gwz[28], gbz = 0.f;                                 // dWz | dbz of this thread's row and units, over all its tiles
+#pragma unroll
+        for (int i = 0; i < 28; ++i) gwz[i] = 0.f;
         for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
             const long long p = tix * 128 + j;
             const bool valid = p < npts;
@@ -788,18 +791,14 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
                     G = fmaf(k0, a.cot[p], fmaf(k1, v, k2 * W.w));
                 }
-                if (ch == 0) {
-                    const float sb2 = warp_sum(G);
-                    if (lane == 0) atomicAdd(zacc + KP, sb2);
-                }
+                gbz += G;
                 uint32_t r[28];
 #pragma unroll
                 for (int i = 0; i < 28; ++i) {
                     r[i] = 0u;
                     if (cb + i < HV) {
                         const float t = h[i];
-                        const float sz = warp_sum(G * t);
-                        if (lane == 0) atomicAdd(zacc + cb + i, sz);
+                        gwz[i] = fmaf(G, t, gwz[i]);
                         r[i] = __float_as_uint(G * w.wz[cb + i] * (1.f - t * t));
                     }
                 }
@@ -808,6 +807,18 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 umma::fence_before();
                 umma::mbar_arrive(mFD);
             }
+        }
+        // per-thread dWz | dbz -> the CTA's accumulators (once per kernel)
+#pragma unroll
+        for (int i = 0; i < 28; ++i) {
+            if (cb + i < HV) {
+                const float sz = warp_sum(gwz[i]);
+                if (lane == 0) atomicAdd(zacc + cb + i, sz);
+            }
+        }
+        if (ch == 0) {
+            const float sb2 = warp_sum(gbz);
+            if (lane == 0) atomicAdd(zacc + KP, sb2);
         }
     } else if (wg == 1) {
         // ======================================================================== R: the delta chain
