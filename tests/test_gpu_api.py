@@ -158,3 +158,15 @@ def test_single_time_group_matches_golden_on_gpu(name):
         assert abs(val.item() - gold_l) <= 1e-6 * abs(gold_l)
         for a, b in zip(grads, gold_g):
             assert G.rel(a, b) < 1e-6 or np.linalg.norm(b) == 0.0
+
+
+@pytest.mark.parametrize("name", ["pad_cube_d3_rk4", "pad_cube_d5_midpoint", "pad_cone_d5"])
+def test_evaluation_from_inside_the_domain_on_gpu(name):
+    """u_net(X) for paths that start inside the domain after T0 (bound_pad / fillt branch of the reference)"""
+    import os
+    z = np.load(os.path.join(G.GOLDEN_DIR, "extra", name + ".npz"))
+    case = G.load(str(z["base"]))
+    s, _ = make_solver(case, DEV)
+    with torch.no_grad():
+        u = s.u_net(torch.from_numpy(z["X"]).to(DEV))
+    assert np.abs(u.cpu().numpy()[..., 0] - z["u"]).max() < 2e-5

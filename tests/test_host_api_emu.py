@@ -274,3 +274,28 @@ def test_product_library_carries_tcgen05_code():
     sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "STTM"):
         assert mnemonic in sass, mnemonic
+
+
+@pytest.mark.parametrize("name", ["pad_cube_d3_rk4", "pad_cube_d5_midpoint", "pad_cone_d5"])
+def test_evaluation_from_inside_the_domain_matches_reference(emu, name):
+    """u_net(X) for paths that start inside the domain after T0: the reference pads the time grid back to T0 and
+    fills the gaps (bound_pad / fillt, src/model.py:92-94, src/dataset.py:13-32); golden vectors from the unmodified
+    reference (tests/golden/make_pad_golden.py)"""
+    z = np.load(os.path.join(G.GOLDEN_DIR, "extra", name + ".npz"))
+    case = G.load(str(z["base"]))
+    s, _ = make_solver(case)
+    with torch.no_grad():
+        u = s.u_net(torch.from_numpy(z["X"]))
+    assert u.shape == z["X"].shape[:2] + (1,)
+    assert np.abs(u.numpy()[..., 0] - z["u"]).max() < 2e-5
+
+
+def test_fillt_grid_properties():
+    from xnode_wan_b200.dataset import fillt
+    t = torch.tensor([0.0, 0.3, 0.35, 0.9])
+    pos, grid = fillt(t, 1.0, 0.0, 20)
+    assert torch.allclose(grid[pos], t)                        # the requested times sit where `pos` says
+    assert bool((grid[1:] > grid[:-1]).all())                  # strictly increasing
+    assert float((grid[1:] - grid[:-1]).max()) <= 0.05 + 1e-6  # no step larger than (T - T0) / min_steps
+    pos1, grid1 = fillt(torch.tensor([0.0, 0.01, 0.02]), 1.0, 0.0, 20)
+    assert grid1.numel() == 1                                  # the reference's degenerate case is reproduced

@@ -16,6 +16,28 @@ import torch
 from .paths import CollapsedPaths
 
 
+def fillt(times: torch.Tensor, T: float, T0: float, min_steps: int = 5):
+    """Time grid for evaluating u at requested times that do not form a usable integration grid
+    (reference src/dataset.py:13-32): wherever two consecutive requested times are more than
+    (T - T0) / min_steps apart, equally spaced steps of about that size are inserted.  Returns
+    (positions of the requested times in the new grid, the new grid).  Like the reference, a request
+    without any such gap yields a one-point grid (the reference then fails on the lookup; so do we,
+    with a clear message, in NeuralODE.evaluate)."""
+    step = (T - T0) / min_steps
+    n_req = times.shape[0]
+    gaps = torch.cat((torch.tensor(step / 2, device=times.device).view(1), (times[:-1] - times[1:]).abs()), 0)
+    starts = torch.nonzero(gaps > step).squeeze(1).tolist() + [n_req]
+    pos = torch.arange(n_req, device=times.device)
+    grid = times[0].view(1)
+    for a, b in zip(starts[:-1], starts[1:]):
+        target, last = times[a].item(), grid[-1].item()
+        n_fill = round((target - 2 * step - last) / step) + 1
+        filler = torch.linspace(last + step, target - step, n_fill).to(times.device)
+        pos[a:] += filler.shape[0]
+        grid = torch.cat((grid, filler, times[a:b].to(times.device)), 0)
+    return pos, grid
+
+
 class Hypercube:
     """cube (bot..top)^dim x [T0, T]; time grid = sorted uniforms with pinned end points"""
 
@@ -68,7 +90,11 @@ class Hypercube:
         return torch.minimum((self.top - s).abs().amin(dim=2), (self.bot - s).abs().amin(dim=2))
 
     def bound_pad(self, x):
-        raise NotImplementedError("bound_pad / fillt (evaluation from inside the domain) is not supported yet")
+        """integration grid for a batch that starts inside the domain after T0 (src/dataset.py:284-287):
+        (None, positions of the requested times, grid starting at T0)"""
+        t = torch.cat((torch.tensor(self.T0, dtype=x.dtype).view(1).to(x.device), x[0, :, 0]), 0)
+        pos, grid = fillt(t, self.T, self.T0, self.N_t)
+        return None, pos[1:], grid
 
     def V(self):
         return (self.top - self.bot) ** self.dim * (self.T - self.T0)
@@ -176,7 +202,8 @@ class _SphereDomain:
         return groups
 
     def bound_pad(self, x):
-        raise NotImplementedError("bound_pad / fillt (evaluation from inside the domain) is not supported yet")
+        raise NotImplementedError("bound_pad for the hourglass (per-path entry times, src/dataset.py:127-152) is not "
+                                  "supported: evaluate from inside the domain on the cube or the cone")
 
 
 class NSphere_TCone(_SphereDomain):
@@ -203,6 +230,12 @@ class NSphere_TCone(_SphereDomain):
 
     def func_w(self, x: torch.Tensor):
         return self.r * (1 - x[:, :, 0]) - x[:, :, 1:].pow(2).sum(2).sqrt()
+
+    def bound_pad(self, x):
+        """src/dataset.py:220-223: as for the cube, every path starts at T0"""
+        t = torch.cat((torch.tensor(self.T0, dtype=x.dtype).view(1).to(x.device), x[0, :, 0]), 0)
+        pos, grid = fillt(t, self.T, self.T0, self.N_t)
+        return None, pos[1:], grid
 
     def V(self):
         tc = (1 - self.T0) ** (self.dim + 1) / (self.dim + 1) - (1 - self.T) ** (self.dim + 1) / (self.dim + 1)

@@ -191,8 +191,7 @@ class NeuralODE(nn.Module):
             h_ = self.h(inputs[:, 0, :]).unsqueeze(1).double()
             return self.final_linear(self.initial_layers(h_))
         if kind == "pad":
-            raise NotImplementedError("batches that start inside the domain (bound_pad / fillt path of "
-                                      "src/model.py:94,104-106) are not supported by the fused kernels yet")
+            return self._evaluate_from_inside(inputs)
         s0 = hotpath.as_f32(self.initial_scalar(inputs.detach(), kind))
         if isinstance(inputs, CollapsedPaths):
             xs, ts = hotpath.as_f32(inputs.x), hotpath.as_f32(inputs.times)
@@ -202,6 +201,26 @@ class NeuralODE(nn.Module):
         N, L, Cc = Xf.shape
         u = hotpath.xnode_eval(self.spec(), self.kernel_parameters(), Xf, 1, L * Cc, Xf[0, :, 0].contiguous(), s0, N)
         return u.double().unsqueeze(2)
+
+    def _evaluate_from_inside(self, inputs):
+        """u at requested times for paths that start inside the domain after T0 (reference src/model.py:92-94,
+        104-106): the domain pads the time grid back to T0 and fills large gaps (`bound_pad` / `fillt`), the XNODE is
+        integrated on that grid from the spatial point of time-row 0, and the requested times are looked up.  As in the
+        reference the initial scalar is g at time-row 0 (`inputs[0,0,0] != T0`, src/model.py:95-96)."""
+        if isinstance(inputs, CollapsedPaths):
+            raise NotImplementedError("evaluation from inside the domain takes the dense [N, L, C] layout")
+        path_i, pos, grid = self.domain.bound_pad(inputs.detach())
+        if path_i is not None:
+            raise NotImplementedError("per-path integration grids (hourglass bound_pad) are not supported")
+        if grid.numel() < 2 or int(pos.max()) >= grid.numel():
+            raise RuntimeError("fillt produced a %d-point grid for the requested times (no gap larger than "
+                               "(T - T0) / N_t between them): the reference fails on this input too" % grid.numel())
+        s0 = hotpath.as_f32(self.initial_scalar(inputs.detach(), "g"))
+        Xf = hotpath.as_f32(inputs)
+        N, L, Cc = Xf.shape
+        ts = hotpath.as_f32(grid.to(Xf.device))
+        u = hotpath.xnode_eval(self.spec(), self.kernel_parameters(), Xf, 1, L * Cc, ts, s0, N)
+        return u[:, pos.to(u.device).long()].double().unsqueeze(2)
 
     def forward(self, inputs: torch.Tensor):
         if torch.is_grad_enabled() and not (inputs.shape[1] == 1):
