@@ -137,6 +137,9 @@ def config_of(args):
             "layout": "collapsed (times[L] + x[N,d]); kernels also take the reference [N,L,C] layout",
             "l2": "inputs_exceed_L2 (3 x %.0f MB of coordinates + 2 x %.0f MB of per-point seeds per step vs 126 MB L2)"
                   % ((1 << args.log2n) * args.dim * 4 / 1e6, (1 << args.log2n) * L_T * 4 / 1e6),
+            "arithmetic": "fp32 results: XNODE kernels FP32 FFMA (+ mma.sync 3xTF32 for the weight-gradient outer products); "
+                          "test-function net on tcgen05 kind::tf32 with 3xTF32 error compensation (1e-6 vs fp64; "
+                          "XW_VNET_IMPL=tile selects the pure-FP32 kernels)",
             "parallelism": "dp%d (paths sharded, 2 small all-reduces per sub-step)" % args.gpus}
 
 
