@@ -424,9 +424,29 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         return XW_CHECK_LAUNCH("k_vnet_points<interior>");
     }
     // generation 2: time-row-0 gradient term (one thread per path) + CTA-tiled pass over all points
-    if (XW_SET_SMEM((xw::k_vnet_points<kHV, 2>), smem)) return 1;
-    XW_LAUNCH((xw::k_vnet_points<kHV, 2>), grid_for(n, 128, 8), 128, smem, stream, b);
-    if (XW_CHECK_LAUNCH("k_vnet_points<row0>")) return 1;
+    bool row0_done = false;
+#ifndef XW_EMU
+    if (use_tc_kernels() && vtc_bwd_ok(m) && m->nv <= xw::kMaxNv) {
+        // time-row 0 on the tensor cores (reverse mode for grad_x v), 128 paths per tile, three tile streams per CTA
+        const int kin = xw::tc::kin_of(m->d), nvs = std::max(m->nv, 1);
+        size_t sm0 = (size_t)(4 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64 + 2 * xw::tc::KP * kin) * 4 +
+                     (size_t)3 * nvs * 128 * 8 + 4 * 32 * 8 + 128;
+        sm0 = std::max(sm0, (size_t)(device()->smem_optin / 2 + 1024));        // (one CTA per SM: it owns the tensor memory)
+        if (sm0 <= device()->smem_optin) {
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_row0, sm0)) return 1;
+            const long long nt0 = ((long long)n + 127) / 128;
+            const int g0 = (int)std::max<long long>(1, std::min<long long>((nt0 + 2) / 3, (long long)device()->sms));
+            xw::tc::k_vnet_tc_row0<<<g0, 384, sm0, (cudaStream_t)stream>>>(b);
+            if (XW_CHECK_LAUNCH("k_vnet_tc_row0")) return 1;
+            row0_done = true;
+        }
+    }
+#endif
+    if (!row0_done) {
+        if (XW_SET_SMEM((xw::k_vnet_points<kHV, 2>), smem)) return 1;
+        XW_LAUNCH((xw::k_vnet_points<kHV, 2>), grid_for(n, 128, 8), 128, smem, stream, b);
+        if (XW_CHECK_LAUNCH("k_vnet_points<row0>")) return 1;
+    }
     xw::VtileFwdArgs t{};
     t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
     t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;

@@ -985,6 +985,203 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     if (warp == 0) umma::tmem_free(tbase, 512);
 }
 
+// =============================================================================================
+// time-row 0 of every path: grad_x v by reverse mode on the tensor cores -> the a grad(phi).du and b.du phi
+// terms of the weak form (src/loss.py:66-69) and the grad_x phi cache.  Replaces k_vnet_points<HV, 2>.
+// Three warpgroups, each with its own stream of 128-path tiles (thread = path = TMEM lane): forward layers
+// (relu masks parked in shared memory), delta chain back to the input layer, then one more MMA
+// grad_(t,x) v = delta_0 . Wi  ([128 x 56] x [56 x kin]) and the per-path dot products in the epilogue.
+// =============================================================================================
+__global__ void __launch_bounds__(384) k_vnet_tc_row0(VnetFwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int kin = kin_of(a.d), nv = a.nv, nvs = nv > 0 ? nv : 1, d = a.d, C = d + 1;
+    WImages w;
+    w.wh_hi = reinterpret_cast<float*>(smem_raw);
+    w.wh_lo = w.wh_hi + KP * NP;
+    w.wht_hi = w.wh_lo + KP * NP;
+    w.wht_lo = w.wht_hi + KP * NP;
+    w.wi_hi = w.wht_lo + KP * NP;
+    w.wi_lo = w.wi_hi + kin * NP;
+    w.wz = w.wi_lo + kin * NP;
+    float* wit_hi = w.wz + 64;                                   // [KP x kin] B[n = c][k = o] = Wi[o][c]
+    float* wit_lo = wit_hi + KP * kin;
+    uint2* smask = reinterpret_cast<uint2*>(wit_lo + KP * kin);   // [3][nvs][128]
+    double* red = reinterpret_cast<double*>(smask + 3 * nvs * 128);
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(red + 4 * 32);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, wq = warp & 3, row = tid & 127;
+    stage_images(w, a.theta, d, a.Hvr, kin);
+    for (int i = tid; i < KP * kin; i += blockDim.x) { wit_hi[i] = 0.f; wit_lo[i] = 0.f; }
+    __syncthreads();
+    {
+        const VLayout g(d, a.Hvr);
+        for (int e = tid; e < a.Hvr * C; e += blockDim.x) {
+            const int o = e / C, c = e - o * C;
+            const int off = (o >> 2) * (kin * 4) + (c >> 3) * 32 + (c & 7) * 4 + (o & 3);
+            put_split(wit_hi, wit_lo, off, a.theta[g.Wi + e]);
+        }
+    }
+    if (tid < 4) umma::mbar_init(mbars + tid, 1);
+    umma::fence_smem_to_async();
+    if (warp == 0) umma::tmem_alloc(slot, 512);
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tbase = *slot + (uint32_t)(wg * (NP + 2 * KP));
+    const uint32_t colD = 0, colA = NP;
+    const uint32_t lane_addr = tbase + ((uint32_t)(32 * wq) << 16);
+    uint64_t* mbar = mbars + wg;
+    uint2* mk = smask + (size_t)wg * nvs * 128 + row;
+    const bool issuer = row == 0;
+    const uint32_t idesc = umma::idesc_tf32(128, NP), idesc_g = umma::idesc_tf32(128, kin);
+    uint32_t parity = 0;
+    const long long ntiles = ((long long)a.n + 127) / 128;
+    double accs[4] = {0.0, 0.0, 0.0, 0.0};
+    auto run_layer = [&](const float* b_hi, const float* b_lo) {   // A rows are stored: one hidden-width contraction
+        umma::tmem_wait_st();
+        umma::fence_before();
+        umma::group_sync(1 + wg);
+        if (issuer) {
+            umma::fence_after();
+            issue_3xtf32<KP / 8>(tbase + colD, tbase + colA, tbase + colA + KP, b_hi, b_lo, 0, idesc);
+            umma::commit(mbar);
+        }
+        mbar_wait_or_trap(mbar, parity);
+        umma::fence_after();
+    };
+    for (long long tix = (long long)blockIdx.x * 3 + wg; tix < ntiles; tix += (long long)gridDim.x * 3) {
+        const long long n = tix * 128 + row;
+        const bool valid = n < a.n;
+        const long long nn = valid ? n : 0;
+        const float* xp = a.p.x + nn * a.p.x_sn;
+        const float tval = valid ? a.p.t[nn * a.p.t_sn] : 0.f;
+        // ---- input row (t, x, 1) ----------------------------------------------------------------
+#pragma unroll 1
+        for (int c8 = 0; c8 < kin; c8 += 8) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = c8 + e;
+                float v = 0.f;
+                if (valid) v = idx == 0 ? tval : (idx <= d ? xp[idx - 1] : (idx == C ? 1.f : 0.f));
+                hi[e] = umma::tf32_hi(v);
+                lo[e] = v - hi[e];
+            }
+            umma::tmem_st8(lane_addr + colA + c8, hi);
+            umma::tmem_st8(lane_addr + colA + KP + c8, lo);
+        }
+        umma::tmem_wait_st();
+        umma::fence_before();
+        umma::group_sync(1 + wg);
+        if (issuer) {
+            umma::fence_after();
+            issue_3xtf32<0>(tbase + colD, tbase + colA, tbase + colA + KP, w.wi_hi, w.wi_lo, kin / 8, idesc);
+            umma::commit(mbar);
+        }
+        float h[KP];
+        mbar_wait_or_trap(mbar, parity);
+        umma::fence_after();
+        umma::tmem_ld56(lane_addr + colD, h);
+        // ---- forward layers, masks kept ------------------------------------------------------------
+#pragma unroll 1
+        for (int layer = 0; layer < nv; ++layer) {
+            uint32_t m0, m1;
+            sign_masks(h, m0, m1);
+            mk[(size_t)layer * 128] = make_uint2(m0, m1);
+#pragma unroll
+            for (int o = 0; o < HV; ++o) h[o] = fmaxf(h[o], 0.f);
+            h[BIASC] = 1.f;
+#pragma unroll
+            for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
+            store_a_row_chunked(lane_addr + colA, lane_addr + colA + KP, h);
+            run_layer(w.wh_hi, w.wh_lo);
+            umma::tmem_ld56(lane_addr + colD, h);
+        }
+        // ---- output layer: v and the cotangent of h_nv for d v ---------------------------------------
+        float v = w.wz[KP];
+#pragma unroll
+        for (int o = 0; o < HV; ++o) {
+            const float tau = tanh_fast(h[o]);
+            v = fmaf(w.wz[o], tau, v);
+            h[o] = w.wz[o] * (1.f - tau * tau);
+        }
+#pragma unroll
+        for (int o = HV; o < KP; ++o) h[o] = 0.f;
+        // ---- delta chain back to the input layer ---------------------------------------------------
+#pragma unroll 1
+        for (int k = nv; k >= 1; --k) {
+            store_a_row_chunked(lane_addr + colA, lane_addr + colA + KP, h);
+            run_layer(w.wht_hi, w.wht_lo);
+            umma::tmem_ld56(lane_addr + colD, h);
+            const uint2 m = mk[(size_t)(k - 1) * 128];
+            apply_sign_masks(h, m.x, m.y);
+#pragma unroll
+            for (int o = HV; o < KP; ++o) h[o] = 0.f;
+        }
+        // ---- grad_(t,x) v = delta_0 . Wi ----------------------------------------------------------
+        store_a_row_chunked(lane_addr + colA, lane_addr + colA + KP, h);
+        umma::tmem_wait_st();
+        umma::fence_before();
+        umma::group_sync(1 + wg);
+        if (issuer) {
+            umma::fence_after();
+            const uint64_t dh = umma::smem_desc(wit_hi, kin * 16, 128), dl = umma::smem_desc(wit_lo, kin * 16, 128);
+            const uint64_t kStep = (uint64_t)((2 * kin * 16) >> 4);
+#pragma unroll 1
+            for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll 1
+                for (int ks = 0; ks < KP / 8; ++ks)
+                    umma::mma_tf32_ts(tbase + colD, tbase + colA + (t3 == 0 ? KP : 0) + 8 * ks, (t3 == 1 ? dl : dh) + kStep * ks, idesc_g,
+                                      (t3 | ks) ? 1u : 0u);
+            umma::commit(mbar);
+        }
+        mbar_wait_or_trap(mbar, parity);
+        umma::fence_after();
+        // ---- per-path terms --------------------------------------------------------------------------
+        const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xp, d);
+        const float phi = v * W.w;
+        const float* dun = a.du + nn * d;
+        float s31 = 0.f;
+#pragma unroll 1
+        for (int c8 = 0; c8 < kin; c8 += 8) {
+            float g8[8];
+            umma::tmem_ld8(lane_addr + colD + c8, g8);
+            if (valid) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int i = c8 + e - 1;               // column 0 is d/dt, columns 1..d the spatial gradient
+                    if (i >= 0 && i < d) {
+                        const float dphi_i = fmaf(W.w, g8[e], v * domain_dw_x(W, i, xp));
+                        if (a.gcache) a.gcache[nn * d + i] = dphi_i;
+                        float q;
+                        if (a.ca) {
+                            q = 0.f;
+                            for (int jj = 0; jj < d; ++jj) q = fmaf(a.ca[i * d + jj], dun[jj], q);
+                        } else {
+                            q = dun[i];
+                        }
+                        s31 = fmaf(dphi_i, q, s31);
+                    }
+                }
+            }
+        }
+        if (valid) {
+            if (a.cb) {
+                float bq = 0.f;
+                for (int jj = 0; jj < d; ++jj) bq = fmaf(a.cb[jj], dun[jj], bq);
+                s31 = fmaf(phi, bq, s31);
+            }
+            accs[2] += (double)s31;
+        }
+        umma::fence_before();
+    }
+    const int idx[4] = {0, 1, 2, 3};
+    block_sum_to_global<4>(accs, red, a.sums, idx);
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(*slot, 512);
+}
+
 }  // namespace tc
 }  // namespace xw
 #endif
