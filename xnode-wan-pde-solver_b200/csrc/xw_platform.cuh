@@ -80,18 +80,7 @@ XW_DEV void load_row(const float* p, float (&w)[N]) {
 }
 
 // out[j] += sum_i M[i*LD + j] * in[i]        (M "in-major": row i holds the OUT weights of input i)
-template <int IN, int OUT, int LD>
-XW_DEV void matvec_acc(const float* M, const float (&in)[IN], float (&out)[OUT]) {
-    XW_FENCE();
-#pragma unroll
-    for (int i = 0; i < IN; ++i) {
-        float w[OUT];
-        load_row<OUT>(M + i * LD, w);
-        const float xi = in[i];
-#pragma unroll
-        for (int j = 0; j < OUT; ++j) out[j] = fmaf(w[j], xi, out[j]);
-    }
-}
+// (matvec_acc: see below, after the packed-pair helpers)
 
 // tanh as 1 - 2/(1 + e^{2x}) on the SFU (ex2 + rcp approximations): absolute error ~1e-7, i.e. the
 // fp32 rounding level of the surrounding FMAs, at ~6 instructions instead of ~30 for tanhf()
@@ -128,6 +117,40 @@ XW_DEV fpair pack2(float lo, float hi) { fpair r; asm("mov.b64 %0, {%1, %2};" : 
 XW_DEV void unpack2(fpair v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 XW_DEV fpair fma2(fpair a, fpair b, fpair c) { fpair d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 #endif
+
+
+// out[j] += sum_i M[i*LD + j] * in[i]        (M "in-major": row i holds the OUT weights of input i)
+// Two adjacent outputs share one packed FFMA2 (fma.rn.f32x2: the weight pair comes straight out of the 128-bit
+// row load, the input is broadcast to both halves): same IEEE results as OUT fmaf() per input at half the issue
+// slots -- the XNODE kernels are issue bound as much as LSU bound (profiles/r01i_xnode_bwd_stalls.txt).
+template <int IN, int OUT, int LD>
+XW_DEV void matvec_acc(const float* M, const float (&in)[IN], float (&out)[OUT]) {
+    XW_FENCE();
+    if constexpr (OUT % 2 == 0) {
+        fpair acc[OUT / 2];
+#pragma unroll
+        for (int j = 0; j < OUT / 2; ++j) acc[j] = pack2(out[2 * j], out[2 * j + 1]);
+#pragma unroll
+        for (int i = 0; i < IN; ++i) {
+            float w[OUT];
+            load_row<OUT>(M + i * LD, w);
+            const fpair xx = pack2(in[i], in[i]);
+#pragma unroll
+            for (int j = 0; j < OUT / 2; ++j) acc[j] = fma2(pack2(w[2 * j], w[2 * j + 1]), xx, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < OUT / 2; ++j) unpack2(acc[j], out[2 * j], out[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < IN; ++i) {
+            float w[OUT];
+            load_row<OUT>(M + i * LD, w);
+            const float xi = in[i];
+#pragma unroll
+            for (int j = 0; j < OUT; ++j) out[j] = fmaf(w[j], xi, out[j]);
+        }
+    }
+}
 
 // 128-bit LIFO of fixed-width bit groups (relu masks of the shared field layers)
 struct BitStack128 {
