@@ -76,6 +76,9 @@ int xw_theta_u_size(const xw_dims* dims);
 int xw_theta_v_size(const xw_dims* dims);
 /* floats in the optional state-history / test-function cache buffers of xw_interior_forward */
 size_t xw_yhist_floats(const xw_dims* dims, int n, int L);
+/* which generation of the XNODE kernels the last XNODE launch of this process used (1 or 2; 0 = none yet):
+ * lets tests and bench.py name the kernel that actually ran instead of assuming it */
+int xw_last_xnode_impl(void);
 size_t xw_vcache_floats(const xw_dims* dims, int n, int L);
 /* upper bound of the scratch any call below needs for n paths of length L */
 size_t xw_workspace_bytes(const xw_dims* dims, int n, int L);

@@ -6,6 +6,7 @@
 #pragma once
 #include <barrier>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -15,8 +16,17 @@
 
 namespace emu {
 
+// named barrier (PTX bar.sync / bar.arrive with an explicit thread count)
+struct NamedBar {
+    std::mutex m;
+    std::condition_variable cv;
+    int count = 0;
+    unsigned gen = 0;
+};
+
 struct Block {
     int bdim = 0;
+    NamedBar nbar[16];
     std::unique_ptr<std::barrier<>> bar;
     std::vector<std::unique_ptr<std::barrier<>>> wbar;
     std::vector<uint64_t> xchg;           // [nwarps][32]
@@ -28,6 +38,20 @@ inline thread_local Block* blk = nullptr;
 inline std::mutex atomic_mu;
 
 inline void warp_sync() { blk->wbar[tid >> 5]->arrive_and_wait(); }
+
+// bar.sync id, n (wait = true) / bar.arrive id, n (wait = false): the barrier completes when n threads have arrived
+inline void named_bar(int id, int n, bool wait) {
+    NamedBar& b = blk->nbar[id];
+    std::unique_lock<std::mutex> lk(b.m);
+    const unsigned g = b.gen;
+    if (++b.count == n) {
+        b.count = 0;
+        ++b.gen;
+        b.cv.notify_all();
+    } else if (wait) {
+        b.cv.wait(lk, [&] { return b.gen != g; });
+    }
+}
 
 template <typename T>
 inline T shfl_idx(T v, int src_lane) {
@@ -90,6 +114,8 @@ inline unsigned char* dyn_smem() {
 
 #define XW_SYNCTHREADS() emu::blk->bar->arrive_and_wait()
 #define XW_SYNCWARP() emu::warp_sync()
+#define XW_BAR_SYNC(id, n) emu::named_bar((id), (n), true)
+#define XW_BAR_ARRIVE(id, n) emu::named_bar((id), (n), false)
 #define XW_SHFL_XOR(v, m) emu::shfl_xor((v), (m))
 #define XW_SHFL_IDX(v, l) emu::shfl_idx((v), (l))
 #define XW_TID (emu::tid)

@@ -5,6 +5,7 @@
 // product package.
 #include "../../include/xnode_wan_b200.h"
 #include "xw_kernels.cuh"
+#include "xw_xnode2.cuh"
 #include "xw_umma.cuh"
 #include "xw_vnet_tc.cuh"
 
@@ -310,6 +311,101 @@ int plan_xnode_bwd(const xw_dims* m, int n, int L, XnodeBwdPlan* p) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// generation-2 XNODE engine (xw_xnode2.cuh): reduced state, shared layer in registers, warp-specialised
+// backward.  Covers u_layers <= 8 (7 shared-layer uses + the tanh slot = the 8 task slots of a tile row);
+// deeper field nets run on the generation-1 kernels.  XW_XNODE_IMPL=v1 forces generation 1 (A/B runs).
+// ---------------------------------------------------------------------------------------------
+bool use_x2(const xw_dims* m) {
+    if (m->nu - 1 > xw::x2::kSlots - 1) return false;
+    const char* e = getenv("XW_XNODE_IMPL");
+    return !(e && strcmp(e, "v1") == 0);
+}
+int g_last_xnode_impl = 0;       // 1 / 2: which generation the last XNODE launch used (xw_last_kernel_info)
+
+size_t x2_smem_fwd(int d, int L) {
+    using S = xw::USmem<kH, kHH>;
+    return (size_t)(xw::pad4(S::size(d)) + xw::x2::R::size + xw::pad4(L) + 4) * 4 + 32 * 8;
+}
+int x2_grid_fwd(int n) { return grid_for(n, xw::x2::kFwdThreads, 1); }
+size_t x2_rec_bytes(const xw_dims* m, int n, int L) {
+    return align_up((size_t)std::max(L, 1) * stages_of(m->solver) * xw::x2::kRecWords2 * x2_grid_fwd(n) * xw::x2::kFwdThreads * 4, 256);
+}
+struct X2BwdPlan { int grid, lgrid, lblock; size_t smem, lsmem, hist_b, pp_b, pa_b, pb_b; };
+int x2_plan_bwd(const xw_dims* m, int n, int L, X2BwdPlan* p) {
+    using S = xw::USmem<kH, kHH>;
+    const Dev* dv = device();
+    p->smem = (size_t)(xw::pad4(S::size(m->d)) + xw::x2::R::size + xw::pad4(L) + 4 + xw::x2::kCW * 3 * xw::x2::kTile + xw::x2::kPartA) * 4 + 32 * 8;
+    if (p->smem > dv->smem_optin)
+        return fail("xnode backward needs %zu B shared memory per CTA (> %zu): N_t/dim too large", p->smem, dv->smem_optin);
+    const int cpaths = 32 * xw::x2::kCW;
+    p->grid = (int)std::max<long long>(1, std::min<long long>(((long long)n + cpaths - 1) / cpaths, dv->sms));
+    p->lblock = 128;
+    const int nw = p->lblock / 32;
+    const int P = xw::ULayout(m->d, m->H, m->hh).size;
+    p->lsmem = (size_t)(xw::pad4(S::size(m->d)) + nw * xw::kStgRowsU * xw::kStgLd + nw * xw::pad4(P)) * 4;
+    if (p->lsmem > dv->smem_optin)
+        return fail("xnode lift backward needs %zu B shared memory per CTA (> %zu): dim too large", p->lsmem, dv->smem_optin);
+    p->lgrid = grid_for(n, p->lblock, ctas_per_sm_for(p->lsmem, 4));
+    p->hist_b = align_up((size_t)L * xw::x2::kZQ * p->grid * cpaths * 4, 256);
+    p->pp_b = align_up((size_t)xw::x2::kPerPath * n * 4, 256);
+    p->pa_b = align_up((size_t)p->grid * xw::x2::kPartA * 4, 256);
+    p->pb_b = align_up((size_t)p->lgrid * P * 4, 256);
+    return 0;
+}
+size_t x2_bwd_bytes(const X2BwdPlan& p) { return p.hist_b + p.pp_b + p.pa_b + p.pb_b; }
+
+template <int MODE>
+int x2_launch_fwd(const xw_dims* m, const xw::x2::FwdArgs& a, void* stream) {
+    using namespace xw::x2;
+    const size_t smem = x2_smem_fwd(a.d, a.L);
+    const int grid = x2_grid_fwd(a.n);
+#define XW_CASE(SOLV)                                                                       \
+    case SOLV: {                                                                            \
+        if (XW_SET_SMEM((k_xnode2_fwd<SOLV, MODE>), smem)) return 1;                        \
+        XW_LAUNCH((k_xnode2_fwd<SOLV, MODE>), grid, kFwdThreads, smem, stream, a);          \
+        break;                                                                              \
+    }
+    switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
+#undef XW_CASE
+    g_last_xnode_impl = 2;
+    return XW_CHECK_LAUNCH("k_xnode2_fwd");
+}
+
+// backward kernel + per-path kernel + finish.  grad_u == NULL: sums only (no lift / finish).
+template <int MODE>
+int x2_run_bwd(const xw_dims* m, xw::x2::BwdArgs a, const X2BwdPlan& p, void* workspace, float* grad_u, int accumulate,
+               void* stream) {
+    using namespace xw::x2;
+    char* ws = (char*)workspace;
+    a.hist = (float*)ws;
+    a.perpath = (float*)(ws + p.hist_b);
+    a.partA = (float*)(ws + p.hist_b + p.pp_b);
+    float* partB = (float*)(ws + p.hist_b + p.pp_b + p.pa_b);
+#define XW_CASE(SOLV)                                                                       \
+    case SOLV: {                                                                            \
+        if (XW_SET_SMEM((k_xnode2_bwd<SOLV, MODE>), p.smem)) return 1;                      \
+        XW_LAUNCH((k_xnode2_bwd<SOLV, MODE>), p.grid, kBwdThreads, p.smem, stream, a);      \
+        break;                                                                              \
+    }
+    switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
+#undef XW_CASE
+    g_last_xnode_impl = 2;
+    if (XW_CHECK_LAUNCH("k_xnode2_bwd")) return 1;
+    if (!grad_u) return 0;
+    LiftArgs l{};
+    l.d = a.d; l.Hr = a.Hr; l.HHr = a.HHr; l.n = a.n; l.theta = a.theta; l.x = a.x; l.x_sn = a.x_sn; l.s0 = a.s0;
+    l.perpath = a.perpath; l.partB = partB;
+    if (XW_SET_SMEM(k_xnode2_lift, p.lsmem)) return 1;
+    XW_LAUNCH(k_xnode2_lift, p.lgrid, p.lblock, p.lsmem, stream, l);
+    if (XW_CHECK_LAUNCH("k_xnode2_lift")) return 1;
+    const int P = xw::ULayout(m->d, m->H, m->hh).size;
+    XW_LAUNCH(k_xnode2_finish, (P + 255) / 256, 256, kPartA * 8, stream, a.partA, p.grid, partB, p.lgrid, a.theta, a.d, a.Hr,
+              a.HHr, grad_u, accumulate);
+    return XW_CHECK_LAUNCH("k_xnode2_finish");
+}
+
 }  // namespace
 
 extern "C" {
@@ -319,7 +415,8 @@ const char* xw_last_error(void) { return g_err; }
 
 int xw_theta_u_size(const xw_dims* m) { return m ? xw::ULayout(m->d, m->H, m->hh).size : -1; }
 int xw_theta_v_size(const xw_dims* m) { return m ? xw::VLayout(m->d, m->Hv).size : -1; }
-size_t xw_yhist_floats(const xw_dims* m, int n, int L) { return m ? (size_t)L * kH * n : 0; }
+size_t xw_yhist_floats(const xw_dims* m, int n, int L) { return m ? (size_t)L * kH * n : 0; }   // (generation 2 uses L*11*n of it)
+int xw_last_xnode_impl(void) { return g_last_xnode_impl; }
 size_t xw_vcache_floats(const xw_dims* m, int n, int L) { return m ? (size_t)4 * n * L + (size_t)n * m->d : 0; }
 
 size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
@@ -331,6 +428,12 @@ size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
     XnodeBwdPlan pb;
     if (plan_xnode_bwd(m, n, L, &pb)) return 0;
     size_t bwd_u = pb.hist_bytes + pb.part_bytes;
+    if (use_x2(m)) {
+        fwd = std::max(fwd, align_up((size_t)n * m->d * 4, 256) + align_up((size_t)n * L * 4, 256) + x2_rec_bytes(m, n, L));
+        X2BwdPlan p2;
+        if (x2_plan_bwd(m, n, L, &p2)) return 0;
+        bwd_u = std::max(bwd_u, x2_bwd_bytes(p2));
+    }
     const int vb = 128;
     int gv = grid_for((long long)n * L, vb, ctas_per_sm_for(smem_vnet_bwd(m, vb), 8));
     size_t bwd_v = align_up((size_t)gv * xw::VLayout(m->d, m->Hv).size * 4, 256);
@@ -352,9 +455,16 @@ int xw_xnode_eval(const xw_dims* m, const float* theta_u, const float* x, long l
     if (!device()) return fail("no CUDA device");
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
     if (!theta_u || !x || !times || !s0 || !u_out) return fail("NULL pointer argument");
+    if (use_x2(m)) {
+        xw::x2::FwdArgs q{};
+        q.d = m->d; q.Hr = m->H; q.HHr = m->hh; q.nsh = m->nu - 1; q.L = L; q.n = n;
+        q.theta = theta_u; q.x = x; q.x_sn = x_sn; q.times = times; q.s0 = s0; q.u_out = u_out;
+        return x2_launch_fwd<0>(m, q, stream);
+    }
     xw::XnodeFwdArgs a{};
     a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
     a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0; a.u_out = u_out;
+    g_last_xnode_impl = 1;
     return launch_xnode_fwd<0>(m, a, grid_for(n, kBlkFwd, 8), smem_xnode_fwd(m->d, L), stream);
 }
 
@@ -387,20 +497,30 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     if (dom->kind < 0 || dom->kind > 2) return fail("unknown domain kind %d", dom->kind);
     if (vcache_mode < 0 || vcache_mode > 2 || (vcache_mode != 0 && !vcache)) return fail("bad vcache arguments");
     float* gcache = vcache ? vcache + (size_t)4 * n * L : nullptr;
+    const bool x2 = use_x2(m);
     const int gf = grid_for(n, kBlkFwd, 8);
     const size_t du_b = align_up((size_t)n * m->d * 4, 256), u_b = align_up((size_t)n * L * 4, 256);
-    const size_t hist_b = align_up(fwd_hist_floats(m, L) * gf * kBlkFwd * 4, 256);
+    const size_t hist_b = x2 ? x2_rec_bytes(m, n, L) : align_up(fwd_hist_floats(m, L) * gf * kBlkFwd * 4, 256);
     if (workspace_bytes < du_b + u_b + hist_b) return fail("workspace too small: %zu < %zu", workspace_bytes, du_b + u_b + hist_b);
     char* ws = (char*)workspace;
     float* du = (float*)ws;
     float* ubuf = u_out ? u_out : (float*)(ws + du_b);
     float* yhist = (float*)(ws + du_b + u_b);
 
-    xw::XnodeFwdArgs a{};
-    a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
-    a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0 ? s0 : h; a.u_out = ubuf;
-    a.grad_h = grad_h; a.du_out = du; a.yhist = yhist; a.sums = sums; a.hloss = h; a.ypath = y_hist;
-    if (launch_xnode_fwd<1>(m, a, gf, smem_xnode_fwd(m->d, L), stream)) return 1;
+    if (x2) {
+        xw::x2::FwdArgs q{};
+        q.d = m->d; q.Hr = m->H; q.HHr = m->hh; q.nsh = m->nu - 1; q.L = L; q.n = n;
+        q.theta = theta_u; q.x = x; q.x_sn = x_sn; q.times = times; q.s0 = s0 ? s0 : h; q.u_out = ubuf;
+        q.grad_h = grad_h; q.du_out = du; q.rec = yhist; q.sums = sums; q.hloss = h; q.zq = y_hist;
+        if (x2_launch_fwd<1>(m, q, stream)) return 1;
+    } else {
+        xw::XnodeFwdArgs a{};
+        a.d = m->d; a.Hr = m->H; a.HHr = m->hh; a.nsh = m->nu - 1; a.L = L; a.n = n;
+        a.theta = theta_u; a.x = x; a.x_sn = x_sn; a.times = times; a.s0 = s0 ? s0 : h; a.u_out = ubuf;
+        a.grad_h = grad_h; a.du_out = du; a.yhist = yhist; a.sums = sums; a.hloss = h; a.ypath = y_hist;
+        g_last_xnode_impl = 1;
+        if (launch_xnode_fwd<1>(m, a, gf, smem_xnode_fwd(m->d, L), stream)) return 1;
+    }
 
     xw::VnetFwdArgs b{};
     b.d = m->d; b.Hvr = m->Hv; b.nv = m->nv; b.n = n; b.L = L; b.theta = theta_v; b.p = view_of(xv);
@@ -484,6 +604,16 @@ int xw_boundary_u(const xw_dims* m, const float* theta_u, const float* xb, long 
     if (!device()) return fail("no CUDA device");
     if (nb < 1 || Lb < 1) return fail("empty batch (n=%d, L=%d)", nb, Lb);
     if (!theta_u || !xb || !times_b || !s0b || !g || !sums || !workspace) return fail("NULL pointer argument");
+    if (use_x2(m)) {
+        X2BwdPlan p2;
+        if (x2_plan_bwd(m, nb, Lb, &p2)) return 1;
+        if (workspace_bytes < x2_bwd_bytes(p2)) return fail("workspace too small: %zu < %zu", workspace_bytes, x2_bwd_bytes(p2));
+        xw::x2::BwdArgs q{};
+        q.d = m->d; q.Hr = m->H; q.HHr = m->hh; q.nsh = m->nu - 1; q.L = Lb; q.n = nb;
+        q.theta = theta_u; q.x = xb; q.x_sn = xb_sn; q.times = times_b; q.s0 = s0b; q.cot = g; q.gscale = gscale; q.sums = sums;
+        return x2_run_bwd<1>(m, q, p2, workspace, grad_u, accumulate, stream);
+    }
+    g_last_xnode_impl = 1;
     XnodeBwdPlan p;
     if (plan_xnode_bwd(m, nb, Lb, &p)) return 1;
     if (workspace_bytes < p.hist_bytes + p.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, p.hist_bytes + p.part_bytes);
@@ -504,6 +634,17 @@ int xw_interior_backward_u(const xw_dims* m, const float* theta_u, const float* 
     if (!device()) return fail("no CUDA device");
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
     if (!theta_u || !x || !times || !h || !cot_u || !coefs_dev || !grad_u || !workspace) return fail("NULL pointer argument");
+    if (use_x2(m)) {
+        X2BwdPlan p2;
+        if (x2_plan_bwd(m, n, L, &p2)) return 1;
+        if (workspace_bytes < x2_bwd_bytes(p2)) return fail("workspace too small: %zu < %zu", workspace_bytes, x2_bwd_bytes(p2));
+        xw::x2::BwdArgs q{};
+        q.d = m->d; q.Hr = m->H; q.HHr = m->hh; q.nsh = m->nu - 1; q.L = L; q.n = n;
+        q.theta = theta_u; q.x = x; q.x_sn = x_sn; q.times = times; q.s0 = s0 ? s0 : h; q.hloss = h; q.cot = cot_u;
+        q.coefs = coefs_dev; q.zq = y_hist;
+        return x2_run_bwd<0>(m, q, p2, workspace, grad_u, accumulate, stream);
+    }
+    g_last_xnode_impl = 1;
     XnodeBwdPlan p;
     if (plan_xnode_bwd(m, n, L, &p)) return 1;
     if (workspace_bytes < p.hist_bytes + p.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, p.hist_bytes + p.part_bytes);

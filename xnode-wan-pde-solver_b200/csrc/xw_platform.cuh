@@ -22,6 +22,9 @@
 #define XW_RESTRICT __restrict__
 #define XW_SYNCTHREADS() __syncthreads()
 #define XW_SYNCWARP() __syncwarp()
+// named barriers (producer / consumer hand-offs between warp roles of one CTA)
+#define XW_BAR_SYNC(id, n) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory")
+#define XW_BAR_ARRIVE(id, n) asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory")
 #define XW_SHFL_XOR(v, m) __shfl_xor_sync(0xffffffffu, (v), (m))
 #define XW_SHFL_IDX(v, l) __shfl_sync(0xffffffffu, (v), (l))
 #define XW_TID ((int)threadIdx.x)
@@ -49,6 +52,10 @@
 #ifdef XW_EMU
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) {
+    sh &= 31u;
+    return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+}
 #endif
 
 namespace xw {

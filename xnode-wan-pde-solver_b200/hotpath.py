@@ -24,7 +24,7 @@ _TEST_ALLOW_HOST = False      # set ONLY by tests that inject the CPU emulation 
 # maps C-ABI entry name -> list of (start_event, end_event) recorded on the launching stream
 PROFILE = None
 CALLS = {}                    # C-ABI entry name -> number of calls (always counted)
-KERNELS_PER_CALL = {"xw_interior_forward": 2, "xw_boundary_u": 2, "xw_interior_backward_u": 2,
+KERNELS_PER_CALL = {"xw_interior_forward": 2, "xw_boundary_u": 3, "xw_interior_backward_u": 3,
                     "xw_interior_backward_v": 2, "xw_xnode_eval": 1, "xw_vnet_eval": 1}
 
 
