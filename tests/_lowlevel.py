@@ -88,6 +88,8 @@ def run_case(lib, be, case, coef_a=None, coef_b=None, use_yhist=True):
     """full u-phase and v-phase evaluation of one golden case through the C ABI.
     returns dict(I,S,init,bdry,loss_u,loss_v,grads_u,grads_v,sums,u)"""
     z, p = case["z"], case["params"]
+    if coef_a is None and "coef_a" in z.files:
+        coef_a = z["coef_a"]
     dims = make_dims(case)
     dom = make_domain(case["meta"]["domain"])
     X, XV, BX = z["X"], z["XV"], z["BX"]

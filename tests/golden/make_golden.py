@@ -31,7 +31,10 @@ CASES = {
     "cube_d3_euler": ({'N_r': 16, 'N_b': 12, 'dim': 3, 'N_t': 5, 'solver': 'euler', 'alpha': 1}, "Ex4_1_funcs", 5, True),
     "cube_d3_rk4": ({'N_r': 16, 'N_b': 12, 'dim': 3, 'N_t': 5, 'solver': 'rk4', 'alpha': 1}, "Ex4_1_funcs", 6, True),
     "cube_d2_L2": ({'N_r': 8, 'N_b': 8, 'dim': 2, 'N_t': 2, 'alpha': 1}, "Ex4_1_funcs", 7, True),
+    # constant a != I, b = 0 (no shipped config has it; the reference CAN run it: src/training.py:32-35, src/loss.py:66-68)
+    "cube_d4_aconst": ({'N_r': 72, 'N_b': 40, 'dim': 4, 'alpha': 10}, "Ex4_3_funcs", 8, True),
 }
+A_CONST = {"cube_d4_aconst": 9}      # case -> seed of the constant matrix a = I + 0.3 * randn(d, d)
 
 
 SPHERE_CASES = {
@@ -102,6 +105,11 @@ def run_case(name, over, funcs_name, seed, rand_bias):
         with torch.no_grad():
             for p in list(solver.u_net.parameters()) + list(solver.v_net.parameters()):
                 p.add_(0.1 * torch.randn(p.shape, generator=g, dtype=p.dtype))
+    coef_a = None
+    if name in A_CONST:
+        d_ = params['dim']
+        coef_a = np.eye(d_) + 0.3 * np.random.default_rng(A_CONST[name]).standard_normal((d_, d_))
+        solver.func_a = lambda X_, i, j: torch.full(X_.shape[:-1], float(np.float32(coef_a[i, j])))
     domain, batches = rr.sample(solver)
     assert len(batches) == 1
     b = batches[0]
@@ -123,6 +131,8 @@ def run_case(name, over, funcs_name, seed, rand_bias):
         u=ou['u'][..., 0], v=ou['v'][..., 0], du=c['du'], dphi=c['dphi'], w=c['w'][..., 0],
         meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8),
     )
+    if coef_a is not None:
+        arrays["coef_a"] = coef_a.astype(np.float32).astype(np.float64)
     for i, p in enumerate(solver.u_net.parameters()):
         arrays["thu_%02d" % i] = p.detach().numpy()
         arrays["gu_%02d" % i] = ou['grads'][i]

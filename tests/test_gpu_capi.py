@@ -33,6 +33,26 @@ def test_capi_matches_reference_golden(lib, name):
         assert G.rel(a, b) < 1e-3, ("grad_v", i, G.rel(a, b))
 
 
+@pytest.mark.parametrize("name", G.big_names())
+def test_capi_matches_full_size_reference_golden(lib, name):
+    """BASELINE configs[0]/[1] at the shipped size (d=5, N_r=N_b=4000, seeds 0/0: SURVEY.md Appendix A.6 anchors) and
+    d=20 with N = 4096 / 8192 paths: outputs of the UNMODIFIED reference (tests/golden/big), inputs re-created with the
+    bit-identical sampler and SHA-1 checked.  Whole waves of tensor-core tiles, not a handful."""
+    c = G.load_big(name)
+    z = c["z"]
+    r = LL.run_case(lib, LL.TorchBackend(), c)
+    assert np.abs(r["u"][:z["u_head"].shape[0]] - z["u_head"]).max() < 2e-5
+    for k in ("I", "S", "init", "bdry"):
+        assert abs(r[k] - float(z[k])) <= 1e-4 * abs(float(z[k])) + 1e-9, (k, r[k], float(z[k]))
+    for k in ("loss_u", "loss_v"):
+        assert abs(r[k] - float(z[k])) <= 1e-4 * abs(float(z[k])) + 1e-6, (k, r[k], float(z[k]))
+    for i, (a, b) in enumerate(zip(r["grads_u"], c["gu"])):
+        assert G.rel(a, b) < 1e-3, ("grad_u", i, G.rel(a, b))
+    for i, (a, b) in enumerate(zip(r["grads_v"], c["gv"])):
+        assert G.rel(a, b) < 1e-3, ("grad_v", i, G.rel(a, b))
+    assert lib.cdll.xw_last_xnode_impl() == 2
+
+
 def test_capi_dense_a_b_matches_oracle(lib):
     c = G.load("cube_d3_small_nets")
     rng = np.random.default_rng(0)

@@ -26,6 +26,9 @@ def make_solver(case, device="cpu"):
     p = dict(case["params"])
     p["domain"] = case["meta"].get("domain_class", "Hypercube")
     prob = xw.problems.by_name(case["meta"]["funcs"], p["dim"])
+    if "coef_a" in case["z"].files:          # the constant a != I this golden was made with
+        A = case["z"]["coef_a"]
+        prob.func_a = lambda X_, i, j: torch.full(X_.shape[:-1], float(A[i, j]))
     s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, device,
                            "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
     with torch.no_grad():
@@ -52,7 +55,7 @@ def eval_phase(s, case, phase, device="cpu"):
 
 
 @pytest.mark.parametrize("name", ["cube_d5_alpha1_randbias", "cube_d3_small_nets", "cube_d4_ex43", "cube_d3_rk4",
-                                  "cone_d5_g2", "hourglass_d5_g2_reentry", "hourglass_d5_g18"])
+                                  "cube_d4_aconst", "cone_d5_g2", "hourglass_d5_g2_reentry", "hourglass_d5_g18"])
 def test_reference_api_matches_golden(emu, name):
     case = G.load(name)
     s, _ = make_solver(case)

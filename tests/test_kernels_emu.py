@@ -37,6 +37,18 @@ def test_emulated_kernels_match_reference_golden(emu, name):
     check_against(r, ref, c["gu"], c["gv"])
 
 
+@pytest.mark.parametrize("name", ["cube_d5_shipped_full", "cube_d20_n4096"])
+def test_emulated_kernels_match_full_size_reference_golden(emu, name):
+    """BASELINE configs[0]/[1] (shipped d=5, N_r=N_b=4000, seeds 0/0) and d=20, N=4096: the UNMODIFIED reference's
+    outputs at full size (tests/golden/big; inputs re-created bit-identically and SHA-1 checked)"""
+    c = G.load_big(name)
+    z = c["z"]
+    r = LL.run_case(emu, LL.NumpyBackend(), c)
+    ref = {k: float(z[k]) for k in ("I", "S", "init", "bdry", "loss_u", "loss_v")}
+    assert np.abs(r["u"][:z["u_head"].shape[0]] - z["u_head"]).max() < 2e-5
+    check_against(r, ref, c["gu"], c["gv"], tol_loss=1e-4)
+
+
 def test_emulated_kernels_dense_a_and_b_match_oracle(emu):
     """constant dense a_ij and b_i (not exercised by any shipped config): compare with the oracle"""
     c = G.load("cube_d3_small_nets")

@@ -154,3 +154,35 @@ def test_torch_port_matches_reference_golden(name):
     assert abs(lv - float(z["loss_v"])) <= 1e-5 * abs(float(z["loss_v"])) + 1e-6
     for q, gref in zip(pv, c["gv"]):
         assert G.rel(q.grad.numpy(), gref) < 1e-5
+
+
+@pytest.mark.parametrize("name", G.big_names())
+def test_closed_form_matches_full_size_reference_golden(name):
+    """the oracle pinned at the BASELINE sizes (shipped d=5 N_r=N_b=4000 with seeds 0/0 -- the SURVEY.md Appendix A.6
+    anchors -- and d=20 with 4096 / 8192 paths): outputs of the UNMODIFIED reference in tests/golden/big"""
+    c = G.load_big(name)
+    z = c["z"]
+    K = z["u_head"].shape[0]
+    for phase, gold_loss, gold_g in (("u", float(z["loss_u"]), c["gu"]), ("v", float(z["loss_v"]), c["gv"])):
+        r = cf.weak_form(c["thu"], c["thv"], z["X"], z["XV"], z["BX"], c["coef"], c["cfg"], phase)
+        assert abs(r["I"] - float(z["I"])) <= 2e-6 * abs(float(z["I"])) + 1e-12
+        assert abs(r["S"] - float(z["S"])) <= 1e-10 * abs(float(z["S"]))
+        assert abs(r["init"] - float(z["init"])) <= 1e-10 * abs(float(z["init"]))
+        assert abs(r["bdry"] - float(z["bdry"])) <= 1e-8 * abs(float(z["bdry"]))
+        assert abs(r["loss_" + phase] - gold_loss) <= 1e-6 * abs(gold_loss) + 1e-6
+        assert np.abs(r["u"][:K] - z["u_head"]).max() < 1e-11
+        assert np.abs(r["v"][:K] - z["v_head"]).max() < 1e-11
+        assert np.abs(r["du"][:K] - z["du_head"]).max() <= 1e-6 * np.abs(z["du_head"]).max() + 1e-9
+        for a, b in zip(r["grads"], gold_g):
+            assert G.rel(a, b) < 5e-6, (phase, G.rel(a, b))
+
+
+def test_shipped_full_golden_is_the_survey_anchor():
+    """seeds 0/0, cube_pde.yaml N_r=N_b=4000, Ex4_1: the values SURVEY.md Appendix A.6 recorded from the reference"""
+    z = np.load(G.os.path.join(G.BIG_DIR, "cube_d5_shipped_full.npz"))
+    assert abs(float(z["I"]) - 0.0726511181) < 1e-9
+    assert abs(float(z["S"]) - 0.00103209205) < 1e-10
+    assert abs(float(z["init"]) - 0.981500739) < 1e-8
+    assert abs(float(z["bdry"]) - 0.500196223) < 1e-8
+    assert abs(float(z["loss_u"]) - 1.4816969779e8) < 1.0
+    assert abs(float(z["loss_v"]) + 1.631994) < 1e-5
