@@ -117,7 +117,8 @@ struct NoRec {
     XW_DEV void layer(int, const float (&)[HH]) {}
     XW_DEV void tanh_out(const float (&)[HH]) {}
     XW_DEV void delta(int, const float (&)[HH]) {}
-    XW_DEV void mask(int, const float (&dn)[HH], float (&dl)[HH]) {
+    XW_DEV void mask_load(int, float (&)[HH]) {}
+    XW_DEV void mask(const float (&)[HH], const float (&dn)[HH], float (&dl)[HH]) {
 #pragma unroll
         for (int i = 0; i < HH; ++i) dl[i] = dn[i];
     }
@@ -136,7 +137,8 @@ struct BitsRec {                       // relu masks (bit set = active) as a bit
         for (int i = 0; i < HH; ++i) tau[i] = t[i];
     }
     XW_DEV void delta(int, const float (&)[HH]) {}
-    XW_DEV void mask(int, const float (&dn)[HH], float (&dl)[HH]) {
+    XW_DEV void mask_load(int, float (&)[HH]) {}
+    XW_DEV void mask(const float (&)[HH], const float (&dn)[HH], float (&dl)[HH]) {
         const unsigned mm = m.template pop<HH>();
 #pragma unroll
         for (int i = 0; i < HH; ++i) dl[i] = ((mm >> (HH - 1 - i)) & 1u) ? dn[i] : 0.f;
@@ -148,9 +150,9 @@ struct TileRec {                       // gradient-task tiles: r_j -> slot j, ta
     XW_DEV void layer(int j, const float (&r)[HH]) { st_vec10(rrow + kSlot * j, r, 1.f); }
     XW_DEV void tanh_out(const float (&t)[HH]) { st_vec10(rrow + kSlot * (kSlots - 1), t, 1.f); }
     XW_DEV void delta(int j, const float (&dl)[HH]) { st_vec10(drow + kSlot * (j - 1), dl, 0.f); }
-    XW_DEV void mask(int jm1, const float (&dn)[HH], float (&dl)[HH]) {
-        float r[HH];
-        ld_vec10(rrow + kSlot * jm1, r);
+    // the relu mask of layer j-1 comes from its recorded output; loaded BEFORE the layer's FFMA2 block, used after it
+    XW_DEV void mask_load(int jm1, float (&r)[HH]) { ld_vec10(rrow + kSlot * jm1, r); }
+    XW_DEV void mask(const float (&r)[HH], const float (&dn)[HH], float (&dl)[HH]) {
 #pragma unroll
         for (int i = 0; i < HH; ++i) dl[i] = r[i] > 0.f ? dn[i] : 0.f;
     }
@@ -188,6 +190,8 @@ XW_DEV void core_rev(const CoreRegs& cr, float (&dl)[HH], int nsh, Rec& rec) {
 #pragma unroll 1
     for (int j = nsh; j > 0; --j) {
         rec.delta(j, dl);
+        float rm[HH];
+        rec.mask_load(j - 1, rm);
         fpair acc[HH];
 #pragma unroll
         for (int i = 0; i < HH; ++i) acc[i] = pack2(0.f, 0.f);
@@ -204,7 +208,7 @@ XW_DEV void core_rev(const CoreRegs& cr, float (&dl)[HH], int nsh, Rec& rec) {
             unpack2(acc[i], lo, hi);
             dn[i] = lo + hi;
         }
-        rec.mask(j - 1, dn, dl);
+        rec.mask(rm, dn, dl);
     }
 }
 
@@ -497,8 +501,8 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kBwdThreads, 1) k_xnode2_bwd(BwdArgs a) {
     const int warp = XW_TID >> 5, lane = XW_TID & 31;
     const int pair = warp & (kCW - 1);
     const bool is_compute = warp < kCW;
-    float* rt[2] = {tiles + (size_t)pair * 3 * kTile, tiles + (size_t)pair * 3 * kTile + kTile};
-    float* dtile = tiles + (size_t)pair * 3 * kTile + 2 * kTile;
+    float* rt0 = tiles + pair * (3 * kTile);               // r-tile 0; r-tile 1 = rt0 + kTile; delta tile = rt0 + 2 kTile
+    float* dtile = rt0 + 2 * kTile;
     const int bar_full = 1 + 2 * pair, bar_empty = 2 + 2 * pair;
     const int L = a.L, nsh = a.nsh;
     const int cpaths = 32 * kCW;
@@ -573,7 +577,7 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kBwdThreads, 1) k_xnode2_bwd(BwdArgs a) {
                 // stages are re-evaluated right before their own reverse -> 2S-1 evaluations of the layer stack)
                 float zin[T::S][HH];
                 TileRec trec;
-                trec.rrow = rt[ecount & 1u] + lane * kRow;
+                trec.rrow = rt0 + ((ecount & 1u) ? kTile : 0) + lane * kRow;
                 trec.drow = dtile + lane * kRow;
                 float tau_last[HH];
                 {
@@ -615,7 +619,7 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kBwdThreads, 1) k_xnode2_bwd(BwdArgs a) {
                     const float ts = fmaf(T::c(s), dt, t0);
                     float tau[HH];
                     if (s + 1 < T::S) {      // re-evaluate this stage, recording its internals in the other r-tile
-                        trec.rrow = rt[ecount & 1u] + lane * kRow;
+                        trec.rrow = rt0 + ((ecount & 1u) ? kTile : 0) + lane * kRow;
                         float av[HH];
                         stage_input(su, ax, ts, zin[s], av);
                         core_fwd(cr, av, nsh, tau, trec);
@@ -685,7 +689,7 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kBwdThreads, 1) k_xnode2_bwd(BwdArgs a) {
         if (total > 0) XW_BAR_ARRIVE(bar_empty, 64);
         for (unsigned e = 0; e < total; ++e) {
             XW_BAR_SYNC(bar_full, 64);
-            const float* rbase = rt[e & 1u] + pg * kRow + slot * kSlot;
+            const float* rbase = rt0 + ((e & 1u) ? kTile : 0) + pg * kRow + slot * kSlot;
             const float* dbase = dtile + pg * kRow + slot * kSlot;
 #pragma unroll 2
             for (int rho = 0; rho < 8; ++rho) {
