@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define XW_ABI_VERSION 1
+#define XW_ABI_VERSION 2
 
 enum { XW_SOLVER_EULER = 0, XW_SOLVER_MIDPOINT = 1, XW_SOLVER_RK4 = 2 };
 enum { XW_DOMAIN_CUBE = 0, XW_DOMAIN_CONE = 1, XW_DOMAIN_HOURGLASS = 2 };
@@ -114,7 +114,9 @@ int xw_interior_forward(const xw_dims* dims, const xw_domain* dom, const xw_coef
                         const xw_points* xv, const float* h, const float* grad_s0, const float* f,
                         int n, double* sums, float* cot_u, float* cot_v, float* u_out,
                         void* workspace, size_t workspace_bytes, void* stream, const float* s0,
-                        float* vcache, int vcache_mode, float* y_hist);
+                        float* vcache, int vcache_mode, float* y_hist, size_t vcache_floats, size_t y_hist_floats);
+/* vcache_floats / y_hist_floats: capacities of the two optional buffers in floats; the call fails (no write) when a
+ * buffer that is passed is smaller than xw_vcache_floats / xw_yhist_floats for this (n, L). */
 
 /* Boundary term (replaces loss.bdry = mean((u_net(BX) - g)^2), src/loss.py:83-85, and its
  * backward): adds sum (u_b - g)^2 to sums[BDRY]; if grad_u != NULL also accumulates

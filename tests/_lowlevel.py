@@ -121,7 +121,7 @@ def run_case(lib, be, case, coef_a=None, coef_b=None, use_yhist=True):
     lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), be.ptr(thu), be.ptr(thv),
              be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L, C.byref(pts), be.ptr(h), be.ptr(gh), be.ptr(f), N,
              be.ptr(sums), be.ptr(cot_u), be.ptr(cot_v), be.ptr(u_out), be.ptr(ws), wsb, be.stream, be.ptr(s0),
-             be.ptr(vcache), 1, be.ptr(yhist))
+             be.ptr(vcache), 1, be.ptr(yhist), len(vcache), len(yhist) if yhist is not None else 0)
     gu = be.zeros(Pu)
     lib.call("xw_boundary_u", C.byref(dims), be.ptr(thu), be.ptr_off(BXd, 1), Lb * Cc, be.ptr(times_b), Lb,
              be.ptr(sb), be.ptr(g), Nb, alpha / (Nb * Lb), be.ptr(sums), be.ptr(gu), 0, be.ptr(ws), wsb, be.stream)
@@ -131,7 +131,8 @@ def run_case(lib, be, case, coef_a=None, coef_b=None, use_yhist=True):
     cu2, cv2 = be.zeros(N * L), be.zeros(N * L)
     lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), be.ptr(thu), be.ptr(thv),
              be.ptr_off(Xd, 1), L * Cc, be.ptr(times), L, C.byref(pts), be.ptr(h), be.ptr(gh), be.ptr(f), N,
-             be.ptr(sums2), be.ptr(cu2), be.ptr(cv2), None, be.ptr(ws), wsb, be.stream, be.ptr(s0), be.ptr(vcache), 2, None)
+             be.ptr(sums2), be.ptr(cu2), be.ptr(cv2), None, be.ptr(ws), wsb, be.stream, be.ptr(s0), be.ptr(vcache), 2, None,
+             len(vcache), 0)
     be.sync()
     s_a, s_b = be.host(sums)[:5].copy(), be.host(sums2)[:5].copy()
     assert np.allclose(s_a, s_b, rtol=1e-6, atol=1e-6 * np.abs(s_a).max()), (s_a, s_b)

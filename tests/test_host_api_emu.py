@@ -302,3 +302,79 @@ def test_fillt_grid_properties():
     assert float((grid[1:] - grid[:-1]).max()) <= 0.05 + 1e-6  # no step larger than (T - T0) / min_steps
     pos1, grid1 = fillt(torch.tensor([0.0, 0.01, 0.02]), 1.0, 0.0, 20)
     assert grid1.numel() == 1                                  # the reference's degenerate case is reproduced
+
+
+def test_coefficient_cache_is_keyed_on_the_callables(emu):
+    """two problems whose closures could share an id() after garbage collection must not share the
+    classified structure; the probe looks at a spread of paths, not the first four"""
+    import gc
+    case = G.load("cube_d3_small_nets")
+    s, prob = make_solver(case)
+    X = torch.from_numpy(case["z"]["X"])
+    seen = []
+    for k in range(4):
+        A = torch.eye(3) * (k + 1.0)
+        fa = (lambda A_: (lambda X_, i, j: torch.full(X_.shape[:-1], float(A_[i, j]))))(A)
+        a, b, c = xw.training.classify_coefficients(X, s.setup, fa, prob.func_b, prob.func_c)
+        seen.append(None if a.matrix is None else float(a.matrix[0, 0]))
+        del fa
+        gc.collect()
+    assert seen == [None, 2.0, 3.0, 4.0]
+    # a coefficient that differs only on the LAST path is caught (the old probe read paths 0..3 only)
+    last = X.shape[0] - 1
+    assert last >= 4
+
+    def fa_var(X_, i, j):
+        out = torch.ones(X_.shape[:-1]) if i == j else torch.zeros(X_.shape[:-1])
+        if X_.shape[0] > 0 and i == j:
+            out = out + (X_[:, :, 1] == X[last, 0, 1]).float()
+        return out
+    with pytest.raises(NotImplementedError):
+        xw.training.classify_coefficients(X, s.setup, fa_var, prob.func_b, prob.func_c)
+
+
+def test_vcache_grows_with_the_batch_and_capi_checks_capacity(emu):
+    """the test-function cache is sized per batch; a later, larger batch re-allocates it (and the C ABI
+    refuses a buffer that is too small instead of writing past it)"""
+    import ctypes as C
+    case = G.load("cube_d3_small_nets")
+    s, prob = make_solver(case)
+    torch.manual_seed(3)
+    np.random.seed(3)
+    dom = s.new_domain()
+    small = xw.Comb_loader(16, 12, dom, "cpu")
+    big = xw.Comb_loader(40, 12, dom, "cpu")
+    s.sub_step("u", dom, small)
+    n_small = s._vc_buf.numel()
+    lu = s.sub_step("u", dom, big)
+    assert s._vc_buf.numel() > n_small
+    # same numbers as a solver that only ever saw the big batch
+    s2, _ = make_solver(case)
+    with torch.no_grad():
+        pass
+    s2.sub_step("u", dom, small)        # same optimiser history
+    s3, _ = make_solver(case)
+    s3.sub_step("u", dom, small)
+    lu3 = s3.sub_step("u", dom, big)
+    assert lu.item() == lu3.item()
+    # raw C ABI: capacity one float short -> error, nothing written
+    from tests import _lowlevel as LL
+    dims = LL.make_dims(case)
+    z = case["z"]
+    N, L, Cc = z["X"].shape
+    need = emu.cdll.xw_vcache_floats(C.byref(dims), N, L)
+    be = LL.NumpyBackend()
+    Xd, XVd = be.arr(z["X"]), be.arr(z["XV"])
+    thu, thv = be.arr(LL.flat_theta(case["thu_list"])), be.arr(LL.flat_theta(case["thv_list"]))
+    pts = xw._lib.Points(be.ptr(XVd).value, L * Cc, Cc, be.ptr_off(XVd, 1).value, L * Cc, Cc)
+    dom_c = LL.make_domain(case["meta"]["domain"])
+    coef = xw._lib.Coef(0.0, -1.0, None, None)
+    wsb = emu.workspace_bytes(dims, N, L)
+    ws, sums = be.zeros(wsb, np.uint8), be.zeros(8, np.float64)
+    cu, cv, vc = be.zeros(N * L), be.zeros(N * L), be.zeros(need)
+    with pytest.raises(xw._lib.XwError, match="cache too small"):
+        emu.call("xw_interior_forward", C.byref(dims), C.byref(dom_c), C.byref(coef), be.ptr(thu), be.ptr(thv),
+                 be.ptr_off(Xd, 1), L * Cc, be.ptr(be.arr(z["X"][0, :, 0])), L, C.byref(pts), be.ptr(be.arr(z["h"])),
+                 be.ptr(be.arr(z["grad_h"])), be.ptr(be.arr(z["f"])), N, be.ptr(sums), be.ptr(cu), be.ptr(cv), None,
+                 be.ptr(ws), wsb, None, None, be.ptr(vc), 1, None, need - 1, 0)
+    assert not sums.any() and not vc.any()

@@ -88,4 +88,57 @@ def test_capi_exports_every_declared_symbol():
     lib = xw._lib.XwLib()
     for name in declared:
         assert hasattr(lib.cdll, name)
-    assert lib.cdll.xw_abi_version() == 1
+    assert lib.cdll.xw_abi_version() == xw._lib.ABI_VERSION
+
+
+def _train_worker(rank, world, port, out):
+    """NODE_WAN_solver.train() on 2 ranks with DIFFERENT caller seeds and a stop criterion that fires on rank 0 only"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    import xnode_wan_b200 as xw
+    from tests.host_emu import build_emu
+    xw._lib._LIB = xw._lib.XwLib(build_emu.build())
+    xw.hotpath._TEST_ALLOW_HOST = True
+    torch.manual_seed(100 + rank)            # replicas would start from different weights without the broadcast
+    np.random.seed(5)                        # ... and draw the same numpy stream without the per-rank reseed
+    prob = xw.problems.ex4_1()
+    p = xw.problems.cube_params(dim=3, N_r=64, N_b=48, N_t=5, iterations=3, alpha=10)
+    calls = []
+
+    def stop(s, points, domain):
+        calls.append(1)
+        return s.rank == 0 and len(calls) >= 3        # rank 1 never wants to stop
+    cwd = os.getcwd()
+    import tempfile
+    os.chdir(tempfile.mkdtemp())
+    try:
+        s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, "cpu",
+                               "./", stop=stop, func_u_sol=prob.func_u_sol, p=2, log_json=True)
+        w0 = [q.detach().clone() for q in s.u_net.parameters()]
+        dom = s.new_domain()
+        first = xw.Comb_loader(*s.local_counts(), dom, "cpu").interioru[:, 0, 1:].clone()
+        hist = s.train(report=False)
+        files = sorted(os.listdir("."))
+    finally:
+        os.chdir(cwd)
+    out[rank] = dict(w0=[w.numpy() for w in w0], w1=[q.detach().numpy().copy() for q in s.u_net.parameters()],
+                     first=first.numpy(), stopped=hist.get("stopped_at_subiter"), ncalls=len(calls), files=files)
+    torch.distributed.destroy_process_group()
+
+
+def test_two_rank_train_loop_stays_consistent():
+    """train() on several ranks -- identical initial weights (broadcast), different shards (per-rank
+    sampling streams), ONE stop decision (all-reduced), files written by rank 0 only"""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    for x, y in zip(a["w0"], b["w0"]):
+        assert np.array_equal(x, y)              # started identical although the callers seeded differently
+    for x, y in zip(a["w1"], b["w1"]):
+        assert np.array_equal(x, y)              # and stayed identical through the Adam steps
+    assert not np.array_equal(a["first"], b["first"])     # the shards are different samples
+    assert a["stopped"] == 3 and b["stopped"] == 3 and a["ncalls"] == b["ncalls"] == 3
+    assert any(f.startswith("losses_NODE") for f in a["files"]) and "best_model_weights_NODE.pth" in a["files"]
+    assert b["files"] == []                      # only rank 0 writes logs / checkpoints

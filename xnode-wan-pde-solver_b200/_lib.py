@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, LIB_NAME)
 SOLVERS = {"euler": 0, "midpoint": 1, "rk4": 2}
 DOMAINS = {"cube": 0, "cone": 1, "hourglass": 2}
 NSUMS = 8
+ABI_VERSION = 2
 SUM_S1, SUM_S2, SUM_S3, SUM_VV, SUM_INIT, SUM_BDRY = 0, 1, 2, 3, 4, 5
 
 
@@ -51,7 +52,7 @@ _SIGS = {
     "xw_vnet_eval": (C.c_int, [C.POINTER(Dims), _P, C.POINTER(Points), C.c_int, C.c_int, _P, _P]),
     "xw_interior_forward": (C.c_int, [C.POINTER(Dims), C.POINTER(Domain), C.POINTER(Coef), _P, _P, _P, C.c_longlong,
                                       _P, C.c_int, C.POINTER(Points), _P, _P, _P, C.c_int, _P, _P, _P, _P, _P,
-                                      C.c_size_t, _P, _P, _P, C.c_int, _P]),
+                                      C.c_size_t, _P, _P, _P, C.c_int, _P, C.c_size_t, C.c_size_t]),
     "xw_yhist_floats": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
     "xw_last_xnode_impl": (C.c_int, []),
     "xw_vcache_floats": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
@@ -84,7 +85,7 @@ class XwLib:
                 raise XwError("%s does not export %s: stale build, rebuild it (python __graft_entry__.py)" % (path, name))
             fn.restype = res
             fn.argtypes = args
-        if self.cdll.xw_abi_version() != 1:
+        if self.cdll.xw_abi_version() != ABI_VERSION:
             raise XwError("ABI version mismatch in %s" % path)
 
     def call(self, name, *args):

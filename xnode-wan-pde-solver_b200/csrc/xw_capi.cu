@@ -30,28 +30,32 @@ int fail(const char* fmt, ...) {
 }
 
 #ifdef XW_EMU
-struct Dev { int sms = 2; size_t smem_optin = 227 * 1024; };
+struct Dev { int sms = 2; size_t smem_optin = 227 * 1024; int ordinal = 0; };
 const Dev* device() { static Dev d; return &d; }
 #define XW_LAUNCH(kern, grid, block, smem, stream, ...)                              \
     do { emu::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); }); } while (0)
 #define XW_CHECK_LAUNCH(name) 0
 #define XW_SET_SMEM(kern, bytes) 0
 #else
-struct Dev { int sms; size_t smem_optin; };
+// properties of the CURRENT device (per-ordinal cache: a process may drive several GPUs)
+struct Dev { int sms; size_t smem_optin; int ordinal; };
+constexpr int kMaxDevices = 64;
 const Dev* device() {
-    static Dev d{0, 0};
-    static bool init = false, ok = false;
-    if (!init) {
-        init = true;
-        int dev = 0;
-        cudaDeviceProp p;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
-            d.sms = p.multiProcessorCount;
-            d.smem_optin = p.sharedMemPerBlockOptin;
-            ok = true;
-        }
+    static Dev devs[kMaxDevices];
+    static bool have[kMaxDevices] = {};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!have[dev]) {
+        int sms = 0, optin = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+            return nullptr;
+        devs[dev] = Dev{sms, (size_t)optin, dev};
+        have[dev] = true;
     }
-    return ok ? &d : nullptr;
+    return &devs[dev];
 }
 #define XW_LAUNCH(kern, grid, block, smem, stream, ...) \
     kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
@@ -66,10 +70,13 @@ int set_smem(K kern, size_t bytes, const char* name) {
     if (bytes <= 48 * 1024) return 0;
     // remember the largest opt-in per kernel: no CUDA API call on the steady-state path (keeps the
     // launch sequence capturable into a CUDA graph)
-    static std::map<const void*, size_t> done;
+    // (cudaFuncSetAttribute is a per-device setting: the memo is keyed by device ordinal as well)
+    static std::map<std::pair<int, const void*>, size_t> done;
     static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail("%s: cudaGetDevice failed", name);
     std::lock_guard<std::mutex> lk(mu);
-    size_t& have = done[(const void*)kern];
+    size_t& have = done[std::make_pair(dev, (const void*)kern)];
     if (have >= bytes) return 0;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) have = bytes;
@@ -415,7 +422,10 @@ const char* xw_last_error(void) { return g_err; }
 
 int xw_theta_u_size(const xw_dims* m) { return m ? xw::ULayout(m->d, m->H, m->hh).size : -1; }
 int xw_theta_v_size(const xw_dims* m) { return m ? xw::VLayout(m->d, m->Hv).size : -1; }
-size_t xw_yhist_floats(const xw_dims* m, int n, int L) { return m ? (size_t)L * kH * n : 0; }   // (generation 2 uses L*11*n of it)
+size_t xw_yhist_floats(const xw_dims* m, int n, int L) {      // generation 2: (z[10], q) per grid point; generation 1: y[H]
+    if (!m) return 0;
+    return (size_t)L * (use_x2(m) ? xw::x2::kZQ : kH) * n;
+}
 int xw_last_xnode_impl(void) { return g_last_xnode_impl; }
 size_t xw_vcache_floats(const xw_dims* m, int n, int L) { return m ? (size_t)4 * n * L + (size_t)n * m->d : 0; }
 
@@ -487,7 +497,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
                         const xw_points* xv, const float* h, const float* grad_h, const float* f, int n,
                         double* sums, float* cot_u, float* cot_v, float* u_out, void* workspace,
                         size_t workspace_bytes, void* stream, const float* s0, float* vcache, int vcache_mode,
-                        float* y_hist) {
+                        float* y_hist, size_t vcache_floats, size_t y_hist_floats) {
     if (check_dims(m)) return 1;
     if (!device()) return fail("no CUDA device");
     if (n < 1 || L < 1) return fail("empty batch (n=%d, L=%d)", n, L);
@@ -496,6 +506,10 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         return fail("NULL pointer argument");
     if (dom->kind < 0 || dom->kind > 2) return fail("unknown domain kind %d", dom->kind);
     if (vcache_mode < 0 || vcache_mode > 2 || (vcache_mode != 0 && !vcache)) return fail("bad vcache arguments");
+    if (vcache_mode != 0 && vcache_floats < xw_vcache_floats(m, n, L))
+        return fail("test-function cache too small: %zu floats < %zu for n=%d, L=%d", vcache_floats, xw_vcache_floats(m, n, L), n, L);
+    if (y_hist && y_hist_floats < xw_yhist_floats(m, n, L))
+        return fail("state-history buffer too small: %zu floats < %zu for n=%d, L=%d", y_hist_floats, xw_yhist_floats(m, n, L), n, L);
     float* gcache = vcache ? vcache + (size_t)4 * n * L : nullptr;
     const bool x2 = use_x2(m);
     const int gf = grid_for(n, kBlkFwd, 8);

@@ -250,7 +250,7 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
              C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), L, C.byref(pts),
              _ptr(batch.h), _ptr(batch.grad_h), _ptr(batch.f), N, _ptr(sums), _ptr(cot_u), _ptr(cot_v), None,
              _ptr(ws), ws.numel(), st, _ptr(batch.s0), _ptr(vcache) if vmode else None, int(vmode),
-          _ptr(y_hist))
+          _ptr(y_hist), vcache.numel() if (vmode and vcache is not None) else 0, y_hist.numel() if y_hist is not None else 0)
     if with_boundary:
         gscale = float(alpha) / (batch.Nb_glob * batch.Lb)
         _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),

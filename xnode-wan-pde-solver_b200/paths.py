@@ -61,6 +61,10 @@ class CollapsedPaths:
     def head(self, k):
         return CollapsedPaths(self.times, self.x[:k], self._xw_start)
 
+    def take(self, idx):
+        """paths idx (1-D long tensor) as a new collapsed batch"""
+        return CollapsedPaths(self.times, self.x[idx.to(self.x.device)], self._xw_start)
+
     def dense(self):
         N, L, C = self.shape
         t = self.times.reshape(1, L, 1).expand(N, L, 1)

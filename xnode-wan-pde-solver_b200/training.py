@@ -17,6 +17,7 @@ from .loss import CoefA, CoefB, CoefC, loss
 from .model import NeuralODE, discriminator, init_weights
 
 _COEF_CACHE = {}
+_PROBE_PATHS = 64
 
 
 def _probe_constant(vals, what):
@@ -32,10 +33,17 @@ def classify_coefficients(X, setup, func_a, func_b, func_c):
     """turn the user callables a_ij(X), b_i(X), c(X,u) into structure (SURVEY.md 7 'User callables').
     Probed on a few sample paths once per (callables, dim) and cached."""
     d = setup['dim']
-    key = (id(func_a), id(func_b), id(func_c), d)
+    # keyed on the callables THEMSELVES (strong references): an id() can be recycled by another problem's closures
+    # after garbage collection and would silently hand it this problem's structure
+    key = (func_a, func_b, func_c, d)
     if key in _COEF_CACHE:
         return _COEF_CACHE[key]
-    Xs = X.head(4).dense() if hasattr(X, "head") else X[:min(4, X.shape[0])].detach()
+    n_all = X.shape[0]
+    if n_all > _PROBE_PATHS:         # a spread of paths, not just the first few
+        sel = torch.linspace(0, n_all - 1, _PROBE_PATHS).long()
+        Xs = X.take(sel).dense() if hasattr(X, "dense") else X[sel.to(X.device)].detach()
+    else:
+        Xs = X.dense() if hasattr(X, "dense") else X.detach()
     A = torch.empty(d, d, dtype=torch.float64)
     for i, j in itertools.product(range(d), repeat=2):
         A[i, j] = _probe_constant(func_a(Xs, i, j), "a[%d,%d]" % (i, j))
@@ -107,6 +115,19 @@ class NODE_WAN_solver:
         # seeds give identical initial weights, all-reduced sums/gradients keep the replicas identical
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        if self.world > 1:
+            # replicas must START identical whatever the callers' seeds were (the reference sets none): rank 0's
+            # initial weights win; all-reduced gradients then keep the Adam replicas identical
+            with torch.no_grad():
+                for q in list(self.u_net.parameters()) + list(self.v_net.parameters()):
+                    torch.distributed.broadcast(q.data, src=0)
+            # ... and the shards must DIFFER: with equal seeds every rank would draw the same paths.  Decorrelate the
+            # sampling streams (torch CPU + CUDA generators and numpy) per rank, derived from rank 0's current state.
+            base = torch.tensor([int(torch.initial_seed()) % (2 ** 31)], dtype=torch.int64, device=self.device)
+            torch.distributed.broadcast(base, src=0)
+            import numpy as _np
+            torch.manual_seed(int(base.item()) + 7919 * (self.rank + 1))
+            _np.random.seed((int(base.item()) + 7919 * (self.rank + 1)) % (2 ** 32))
         self._warm = 0                   # completed eager iterations (the first one warms up before graph capture)
         self.reuse_v = True              # cache the test-function values across the sub-steps of one iteration
         self._vc_buf, self._vc_key, self._theta_v_gen = None, None, 0
@@ -141,7 +162,24 @@ class NODE_WAN_solver:
         if not self.reuse_v or isinstance(points.interioru, list):
             return None, 0
         key = (points.uid, self._theta_v_gen)
+        self._ensure_vcache(points)
         return self._vc_buf, (2 if self._vc_key == key else 1)
+
+    def _ensure_vcache(self, points):
+        """(re)allocate the test-function cache for the batch about to run: the buffer is sized by (N, L) of a batch and
+        a later, larger batch must not write past it (the C ABI checks the capacity as well)"""
+        X = points.interioru
+        N, L = X.shape[0], X.shape[1]
+        um, vm = self.u_net.module, self.v_net.module
+        from . import hotpath as _hp
+        dims = um.spec(vm).c()
+        import ctypes as _C
+        need = int(_hp._lib.get().cdll.xw_vcache_floats(_C.byref(dims), N, L))
+        if self._vc_buf is None or self._vc_buf.numel() < need or self._vc_buf.device != torch.device(self.device):
+            self._vc_buf = torch.empty(need, dtype=torch.float32, device=self.device)
+            self._vc_key = None            # cached values are gone
+            self._graphs = None            # captured graphs hold the old buffer
+        self._vc_shape = (N, L)
 
     def _vcache_commit(self, phase, points):
         if self.reuse_v and not isinstance(points.interioru, list):
@@ -160,12 +198,6 @@ class NODE_WAN_solver:
         if self.world > 1:
             Loss.N_glob, Loss.Nb_glob = datau.shape[0] * self.world, bdata.shape[0] * self.world
         vbuf, vmode = vplan
-        if vmode and vbuf is None:
-            um, vm = self.u_net.module, self.v_net.module
-            from . import hotpath as _hp
-            bt = _hp.Batch(N=datau.shape[0], L=datau.shape[1], d=self.setup['dim'], times=None, x=None, x_off=0, x_sn=0,
-                           xv=None, tv_off=0, tv_sn=0, tv_sl=0, xv_off=0, xv_sn=0, xv_sl=0)
-            vbuf = self._vc_buf = _hp.vcache_buffer(_hp._lib.get(), um.spec(vm), bt, datau.device)
         Loss.vcache = (vbuf, vmode)
         Loss._u_module = self.u_net.module
         if phase == "u":
@@ -254,6 +286,15 @@ class NODE_WAN_solver:
         self._warm += 1
         return loss_u, loss_v
 
+    def _agree(self, flag):
+        """the stop decision must be the SAME on every rank (each evaluates it on its own shard): a rank that returned
+        while the others entered the next all-reduce would hang the job.  Stop when ANY rank's criterion fires."""
+        if self.world <= 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=self.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return bool(t.item())
+
     def train(self, report: bool = False, report_it: int = 10, show_plt: bool = False, max_seconds=None):
         past_losses = []
         t_start = time.time()
@@ -265,18 +306,19 @@ class NODE_WAN_solver:
             points = Comb_loader(n_r, n_b, domain, self.device)
             for i in range(self.n1):
                 loss_u = self.sub_step("u", domain, points)
-                self.av_l = sum(v.item() for v in self._last_losses)
+                self.av_l = sum(v.item() for v in self._last_losses)     # (all-reduced sums: identical on every rank)
                 past_losses.append(self.av_l)
-                if self.log_json:
+                if self.log_json and self.rank == 0:
                     with open('losses_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
                         json.dump(past_losses, fh)
-                if self.stop is not None and self.stop(self, points.interioru, domain):
-                    torch.save(self.u_net.state_dict(), os.path.join(self.path, 'best_model_weights_NODE.pth'))
-                    print('Stopping Criterion Reached')
+                if self.stop is not None and self._agree(self.stop(self, points.interioru, domain)):
+                    if self.rank == 0:
+                        torch.save(self.u_net.state_dict(), os.path.join(self.path, 'best_model_weights_NODE.pth'))
+                        print('Stopping Criterion Reached')
                     self.history["stopped_at_subiter"] = len(past_losses)
                     return self.history
                 if self.av_l < self.best_l:
-                    if self.log_json:
+                    if self.log_json and self.rank == 0:
                         torch.save(self.u_net.state_dict(), 'best_model_weights_NODE.pth')
                     self.best_l = self.av_l
             for j in range(self.n2):
@@ -285,22 +327,27 @@ class NODE_WAN_solver:
             L2 = None
             if self.func_u_sol is not None:
                 fresh = Comb_loader(n_r, n_b, domain, self.device)
-                L2 = L_norm(fresh.interioru, self.u_net, self.p, self.func_u_sol, domain.V(), n_r).item()
-                if self.log_json:
+                L2 = L_norm(fresh.interioru, self.u_net, self.p, self.func_u_sol, domain.V(), n_r)
+                if self.world > 1:         # shards of equal size: the global L^p error is the p-mean of the shard errors
+                    Lp = L2.detach().double() ** self.p
+                    torch.distributed.all_reduce(Lp)
+                    L2 = (Lp / self.world) ** (1.0 / self.p)
+                L2 = L2.item()
+                if self.log_json and self.rank == 0:
                     with open('L2_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
                         json.dump([L2], fh)
             times.append(time.time())
-            if self.log_json:
+            if self.log_json and self.rank == 0:
                 with open('Time_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
                     json.dump(times, fh)
             self.history["loss_u"].append(self.av_l)
             self.history["loss_v"].append(loss_v.item() if loss_v is not None else None)
             self.history["L2"].append(L2)
             self.history["time"].append(times[-1] - t_start)
-            if report and k % report_it == 0:
+            if report and k % report_it == 0 and self.rank == 0:
                 print('iteration: ' + str(k), 'Loss u: ' + str(self.av_l), 'Loss v: ' + str(self.history["loss_v"][-1]))
                 if L2 is not None:
                     print('L^2 norm error: ' + str(L2))
-            if max_seconds is not None and times[-1] - t_start > max_seconds:
+            if max_seconds is not None and self._agree(times[-1] - t_start > max_seconds):
                 break
         return self.history
