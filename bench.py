@@ -8,9 +8,14 @@ one (path, time-index) sample; a u-step covers (N_r + N_b) * N_t of them, a v-st
 
   python bench.py --gpus N --steps K --warmup W             # this framework (sm_100a kernels)
   python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
+  python bench.py --config xl ...                            # BASELINE configs[4]: d=100, 2^22 paths
 
 Workload (BASELINE.json configs[3]): cube PDE (Ex4_1), d=20, N_t=20, N_r = N_b = 2^20 paths PER
-RANK (weak scaling), alpha=1e8, shipped network sizes, synthetic seeded samples, xavier weights.
+RANK (weak scaling, `value`), alpha=1e8, shipped network sizes, synthetic seeded samples, xavier
+weights.  In the same run the STRONG split of configs[3] is timed too (2^20 paths in total, 2^20/N per
+rank, `strong`), at N=1 the shipped config is trained to the reference's stop criterion on several seeds
+(`time_to_target`), and at N>1 the sharded loss/gradients are checked against the unsharded ones on
+rank 0 (`shard_check`).
 """
 import argparse
 import json
@@ -26,6 +31,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 L_T = 20
+CONFIGS = {"m": dict(dim=20, log2n=20), "xl": dict(dim=100, log2n=22)}
 
 
 def alg_flops(d, H=20, hh=10, nu=8, Hv=50, nv=9, L=L_T):
@@ -33,10 +39,15 @@ def alg_flops(d, H=20, hh=10, nu=8, Hv=50, nv=9, L=L_T):
     F = (H + d + 1) * hh + (nu - 1) * hh * hh + hh * H
     U = 2 * (L - 1) / L * F + H + (H + 2 * H * H) / L
     Vm = (d + 1) * Hv + nv * Hv * Hv + Hv
+    # what the generation-2 XNODE kernels actually execute per field evaluation (reduced state z = Wy y):
+    Fr = (nu - 1) * hh * hh + hh * hh + hh          # shared layers + M tau + v.tau
+    Ur = 2 * (L - 1) / L * Fr
     return {"u_interior": 2 * (4 * U + 2 * Vm), "u_boundary": 2 * 3 * U, "v_interior": 2 * (2 * U + 4 * Vm),
-            "U": U, "Vm": Vm,
+            "U": U, "Vm": Vm, "U_reduced_hw": Ur,
             # per C-ABI call (what one launch group computes), per point of its own batch
-            "xw_interior_forward": 2 * (2 * U + 2 * Vm), "xw_boundary_u": 2 * 3 * U,
+            "xw_interior_forward": 2 * (2 * U + 2 * Vm),          # XNODE forward + du sweep, v net value + tangent
+            "xw_interior_forward:cached_v": 2 * (2 * U),          # test-function values come from the cache
+            "xw_boundary_u": 2 * 3 * U,
             "xw_interior_backward_u": 2 * 2 * U, "xw_interior_backward_v": 2 * 2 * Vm}
 
 
@@ -125,22 +136,133 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "path-points/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "path-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference CPU path = oracle/torch_port.py (the reference itself cannot travel to the GPU box; "
-                    "the port is pinned to it by golden vectors); the reference cannot run the full 2^20-path "
-                    "config (dense a[d,d,N,L] = 33.5 GB), so a bounded sample is timed and quoted per path-point"}
+                    "the port is pinned to it by golden vectors); the reference cannot run the full 2^%d-path "
+                    "config (dense a[d,d,N,L]), so a bounded sample is timed and quoted per path-point" % args.log2n}
     print(json.dumps(line), flush=True)
 
 
 def config_of(args):
     return {"workload": "cube PDE Ex4_1 d=%d, N_r=N_b=2^%d paths per rank, N_t=%d, alpha=1e8, H=20 hh=10 nu=8 Hv=50 nv=9, "
                         "midpoint; step = 2 u-steps + 1 v-step on one sample" % (args.dim, args.log2n, L_T),
-            "dim": args.dim, "N_r_per_rank": 1 << args.log2n, "N_b_per_rank": 1 << args.log2n, "N_t": L_T,
-            "layout": "collapsed (times[L] + x[N,d]); kernels also take the reference [N,L,C] layout",
+            "name": args.config, "dim": args.dim, "N_r_per_rank": 1 << args.log2n, "N_b_per_rank": 1 << args.log2n, "N_t": L_T,
+            "layout": "collapsed (times[L] + x[N,d]); kernels also take the reference [N,L,C] layout (e2e_nlc)",
             "l2": "inputs_exceed_L2 (3 x %.0f MB of coordinates + 2 x %.0f MB of per-point seeds per step vs 126 MB L2)"
                   % ((1 << args.log2n) * args.dim * 4 / 1e6, (1 << args.log2n) * L_T * 4 / 1e6),
-            "arithmetic": "fp32 results: XNODE kernels FP32 FFMA (+ mma.sync 3xTF32 for the weight-gradient outer products); "
+            "arithmetic": "fp32 results: XNODE kernels FP32 FFMA2 (reduced state z = Wy y, shared layer in registers); "
                           "test-function net on tcgen05 kind::tf32 with 3xTF32 error compensation (1e-6 vs fp64; "
                           "XW_VNET_IMPL=tile selects the pure-FP32 kernels)",
             "parallelism": "dp%d (paths sharded, 2 small all-reduces per sub-step)" % args.gpus}
+
+
+XNODE_NAMES = {1: ("k_xnode_fwd", "k_xnode_bwd"), 2: ("k_xnode2_fwd", "k_xnode2_bwd (+ k_xnode2_lift, k_xnode2_finish)")}
+VNET_FWD = {1: "k_vnet_points", 2: "k_vnet_tile_fwd", 3: "k_vnet_tc_fwd (+ k_vnet_tc_row0)"}
+VNET_BWD = {1: "k_vnet_bwd", 2: "k_vnet_tile_bwd", 3: "k_vnet_tc_bwd3"}
+
+
+def make_solver(xw, d, n_glob, dev, **kw):
+    prob = xw.problems.ex4_1()
+    params = xw.problems.cube_params(dim=d, N_r=n_glob, N_b=n_glob, N_t=L_T, shape_param=[-1.0, 1.0])
+    torch.manual_seed(0)
+    return xw.NODE_WAN_solver(params, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g,
+                              dev, "./", func_u_sol=prob.func_u_sol, p=2, log_json=False, **kw), prob
+
+
+def time_to_target(xw, dev, seeds, max_outer=600):
+    """shipped config (configs/cube_pde.yaml + Ex4_1: d=5, N_r=N_b=4000, n1=2, n2=1) trained through the public API
+    until the reference's own stop criterion fires (rel-L2 < 0.01 on the training sample,
+    /root/reference/configs/Ex4_1_funcs.py:36-37, evaluated after every u sub-iteration as src/training.py:142)"""
+    import numpy as np
+    out = {"config": "cube_pde.yaml + Ex4_1, d=5, N_r=N_b=4000, N_t=20, n1=2, n2=1; CPU sampling with the reference's RNG stream; "
+                     "CUDA-graph replay of the sub-steps", "criterion": "rel-L2 < 0.01 (reference stop())",
+           "seeds": [], "sub_iters": [], "seconds": [], "final_rel_l2": [], "ms_per_sub_iter": []}
+    for seed in seeds:
+        prob = xw.problems.ex4_1()
+        params = xw.problems.cube_params(dim=5, iterations=max_outer)
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        trace = []
+        solver = xw.NODE_WAN_solver(params, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g,
+                                    dev, "./", func_u_sol=prob.func_u_sol, p=2, log_json=False, use_cuda_graph=True)
+
+        def stop(s, points, domain):
+            r = xw.rel_err(points, s.u_net, s.func_u_sol, s.p, domain.V(), s.params['N_r']).item()
+            trace.append(r)
+            return r < 0.01
+        solver.stop = stop
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):       # train() prints 'Stopping Criterion Reached' as the reference does
+            hist = solver.train(report=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["seeds"].append(seed)
+        out["sub_iters"].append(hist.get("stopped_at_subiter"))
+        out["seconds"].append(round(dt, 3))
+        out["final_rel_l2"].append(trace[-1] if trace else None)
+        out["ms_per_sub_iter"].append(round(1e3 * dt / max(1, len(trace)), 3))
+    ref = []
+    try:      # the UNMODIFIED reference on the same seeds (CPU, build container; oracle/ref_time_to_target.py)
+        ref = json.load(open(os.path.join(ROOT, "profiles", "r02_ref_time_to_target.json")))["runs"]
+    except Exception:
+        pass
+    out["reference_cpu"] = {"source": "profiles/r02_ref_time_to_target.json (unmodified reference, CPU fp64, build container)",
+                            "seeds": [r["seed"] for r in ref], "sub_iters": [r["sub_iters"] if r["stopped"] else None for r in ref],
+                            "final_rel_l2": [r["final_rel_l2"] for r in ref], "seconds": [r["wall_s"] for r in ref]}
+    return out
+
+
+def shard_check(xw, dev, world, rank, d, log2n=14):
+    """sharded == unsharded on the real path: every rank evaluates loss_u / loss_v and their gradients on its shard of
+    one sample (all-reduced sums and gradients); rank 0 then evaluates the gathered sample alone."""
+    import numpy as np
+    n_loc = 1 << log2n
+    solver, _ = make_solver(xw, d, n_loc * world, dev)
+    torch.manual_seed(777 + rank)
+    dom = solver.new_domain(sample_device=dev, collapsed=True)
+    pts = xw.Comb_loader(n_loc, n_loc, dom, dev)
+    g0 = torch.distributed.new_group(ranks=[0])      # a one-rank group: rank 0's unsharded evaluation reduces over itself only
+
+    def evaluate(s, points, domain, group=None):
+        res = {}
+        for phase in ("u", "v"):
+            s.optimizer_u.zero_grad(set_to_none=True)
+            s.optimizer_v.zero_grad(set_to_none=True)
+            X, XV, BX = points[0]
+            pv, pu = s.v_net(XV), s.u_net(X)
+            h, f, g, a, b, c = xw.func_eval(X, BX, s.setup, pu, s.func_a, s.func_b, s.func_c, s.func_h, s.func_f, s.func_g)
+            Lo = xw.loss(s.config["alpha"], a, b, c, h, f, g, s.setup, domain, dev)
+            if s.world > 1:
+                Lo.N_glob, Lo.Nb_glob = X.shape[0] * s.world, BX.shape[0] * s.world
+            if group is not None:
+                Lo.group = group
+            val = Lo.u(pu, pv, s.u_net, X, XV, BX) if phase == "u" else Lo.v(pu, pv, X, XV)
+            val.backward()
+            net = s.u_net if phase == "u" else s.v_net
+            res[phase] = (val.detach().clone(), torch.cat([q.grad.reshape(-1) for q in net.parameters()]).clone())
+        return res
+    sharded = evaluate(solver, pts, dom)
+    # gather the shards on every rank (rank 0 uses them)
+    parts = []
+    for t in (pts.interioru.x, pts.interiorv.x, pts.boundary.x):
+        buf = [torch.empty_like(t) for _ in range(world)]
+        torch.distributed.all_gather(buf, t.contiguous())
+        parts.append(torch.cat(buf, 0))
+    out = None
+    if rank == 0:
+        solver.world = 1                    # evaluate the gathered sample alone: no all-reduce, local == global counts
+        full = xw.Comb_loader.from_tensors(*[xw.CollapsedPaths(dom.times.to(dev), p) for p in parts], dev)
+        single = evaluate(solver, full, dom, g0)
+        solver.world = world
+        out = {"paths_per_rank": n_loc, "dim": d}
+        for phase in ("u", "v"):
+            lv, gv = sharded[phase]
+            ls, gs = single[phase]
+            out["loss_%s_rel" % phase] = abs(lv.item() - ls.item()) / max(abs(ls.item()), 1e-300)
+            out["grad_%s_rel_l2" % phase] = (torch.linalg.norm(gv - gs) / torch.linalg.norm(gs)).item()
+        out["ok"] = bool(out["loss_u_rel"] < 1e-6 and out["loss_v_rel"] < 1e-6 and out["grad_u_rel_l2"] < 1e-4 and out["grad_v_rel_l2"] < 1e-4)
+    torch.distributed.barrier()
+    return out
 
 
 def run_ours(args):
@@ -156,20 +278,7 @@ def run_ours(args):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     lib = xw._lib.get()
-    n_loc = 1 << args.log2n
     d = args.dim
-    prob = xw.problems.ex4_1()
-    params = xw.problems.cube_params(dim=d, N_r=n_loc * world, N_b=n_loc * world, N_t=L_T, shape_param=[-1.0, 1.0])
-    torch.manual_seed(0)
-    solver = xw.NODE_WAN_solver(params, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g,
-                                dev, "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
-    torch.manual_seed(1000 + rank)
-    domain = solver.new_domain(sample_device=dev, collapsed=True)
-    points = xw.Comb_loader(n_loc, n_loc, domain, dev)
-    points[0]
-    # pinned host copy of the same sample for the end-to-end arm
-    host = [t.to("cpu").pin_memory() for t in (points.interioru, points.interiorv, points.boundary)]
-    pp_step = (2 * (n_loc + n_loc) + n_loc) * L_T * world
 
     def barrier():
         if world > 1:
@@ -188,6 +297,21 @@ def run_ours(args):
         if world > 1:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return ms.item() / steps
+
+    def workload(n_loc):
+        solver, _ = make_solver(xw, d, n_loc * world, dev)
+        torch.manual_seed(1000 + rank)
+        domain = solver.new_domain(sample_device=dev, collapsed=True)
+        points = xw.Comb_loader(n_loc, n_loc, domain, dev)
+        points[0]
+        return solver, domain, points
+
+    # ------------------------------------------------------------------ weak workload (the headline `value`)
+    n_loc = 1 << args.log2n
+    solver, domain, points = workload(n_loc)
+    # pinned host copy of the same sample for the end-to-end arm
+    host = [t.to("cpu").pin_memory() for t in (points.interioru, points.interiorv, points.boundary)]
+    pp_step = (2 * (n_loc + n_loc) + n_loc) * L_T * world
 
     def step_resident():
         solver.train_iteration(domain, points)
@@ -222,9 +346,11 @@ def run_ours(args):
     hp.CALLS.clear()
     hp.LAUNCHES[0] = 0
     ms = timed(step_resident, args.steps)
-    prof, calls = hp.PROFILE, dict(hp.CALLS)
+    prof = hp.PROFILE
     hp.PROFILE = None
     clk = clocks.stop() if rank == 0 else None
+    xnode_impl = lib.cdll.xw_last_xnode_impl()
+    vimpl = lib.cdll.xw_last_vnet_impl()
     # per-entry-point device time (CUDA events on the launching stream, inside the timed region)
     per_call = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in prof.items()}
     per_step = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in prof.items()}
@@ -235,6 +361,47 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     h2d = sum(t.nbytes() for t in host)
     d2h = 16
+    del host
+
+    # e2e through the reference's own [N, L, C] layout (time in channel 0, x repeated along L): 3 x N*L*C*4 bytes per step
+    e2e_nlc = None
+    nlc_bytes = 3 * n_loc * L_T * (d + 1) * 4
+    if nlc_bytes <= args.nlc_max_gb * 1e9:
+        host_nlc = [t.dense().to("cpu").pin_memory() for t in (points.interioru, points.interiorv, points.boundary)]
+
+        def step_nlc():
+            pts = xw.Comb_loader.from_tensors(host_nlc[0], host_nlc[1], host_nlc[2], dev)
+            lu, lv = solver.train_iteration(domain, pts)
+            last["lu_nlc"] = lu.item() + 0 * lv.item()
+        step_nlc()
+        ms_nlc = timed(step_nlc, max(1, args.steps // 2))
+        e2e_nlc = {"value": pp_step / (ms_nlc * 1e-3), "unit": "path-points/s", "ms_per_step": ms_nlc,
+                   "h2d_bytes_per_step": sum(t.nbytes for t in host_nlc), "d2h_bytes_per_step": 16, "loss_u": last.get("lu_nlc"),
+                   "layout": "reference [N,L,C] fp32 from pinned host memory (what /root/reference/src/dataset.py:321 moves)"}
+        del host_nlc
+    del solver, points
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ strong split of the same config (2^log2n paths in total)
+    strong = None
+    if world > 1 and (n_loc % world) == 0:
+        n_s = n_loc // world
+        solver_s, domain_s, points_s = workload(n_s)
+
+        def step_strong():
+            solver_s.train_iteration(domain_s, points_s)
+        for _ in range(args.warmup):
+            step_strong()
+        ms_s = timed(step_strong, args.steps)
+        strong = {"paths_total": n_loc, "paths_per_rank": n_s, "ms_per_step": ms_s, "value": (2 * (n_loc + n_loc) + n_loc) * L_T / (ms_s * 1e-3),
+                  "unit": "path-points/s", "note": "BASELINE configs[3] as written: N_r = N_b = 2^%d paths in total, sharded over %d ranks" % (args.log2n, world)}
+        del solver_s, points_s
+        torch.cuda.empty_cache()
+    elif world == 1:
+        strong = {"paths_total": n_loc, "paths_per_rank": n_loc, "ms_per_step": ms, "value": pp_step / (ms * 1e-3), "unit": "path-points/s",
+                  "note": "N=1: identical to the weak line"}
+
+    check = shard_check(xw, dev, world, rank, d) if world > 1 else None
 
     if rank != 0:
         if world > 1:
@@ -249,8 +416,8 @@ def run_ours(args):
         pass
     ncalls = {k: len(v) / args.steps for k, v in prof.items()}
     tj = {}
-    try:       # DRAM bytes per point of each kernel from the committed `ncu --set full` captures
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    try:       # DRAM bytes per point of each kernel from the committed `ncu --set full` captures (NOT measured in this run)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
         pass
     nv_, kin = 9, (d + 2 + 7) // 8 * 8
@@ -262,11 +429,14 @@ def run_ours(args):
     tc_bwd_exec = (3 * (kin // 8 + 7 * nv_) * mma_flops(56) + 3 * 7 * nv_ * mma_flops(56) + 3 * 16 * nv_ * mma_flops(56) +
                    3 * 16 * mma_flops(kin)) / 128.0
     tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+    xf, xb = XNODE_NAMES.get(xnode_impl, ("xnode_fwd?", "xnode_bwd?"))
+    vf, vb = VNET_FWD.get(vimpl & 15, "vnet_fwd?"), VNET_BWD.get((vimpl >> 4) & 15, "vnet_bwd?")
     groups = {
-        # kernel -> (C-ABI entries it serves, bound)
-        "k_xnode_bwd": (["xw_boundary_u", "xw_interior_backward_u"], "fp32_fma"),
-        "k_vnet_tc_bwd3": (["xw_interior_backward_v"], "tensor"),
-        "interior_forward (k_xnode_fwd + k_vnet_tc_fwd | k_weak_combine + k_vnet_points<row0>)": (["xw_interior_forward"], "mixed"),
+        # kernel (named after what actually launched: xw_last_xnode_impl / xw_last_vnet_impl) -> (C-ABI entries, bound)
+        xb: (["xw_boundary_u", "xw_interior_backward_u"], "fp32_fma"),
+        vb: (["xw_interior_backward_v"], "tensor" if (vimpl >> 4) & 15 == 3 else "fp32_fma"),
+        "%s + k_weak_combine (interior forward, test-function values cached)" % xf: (["xw_interior_forward:cached_v"], "fp32_fma"),
+        "%s + %s (interior forward, test-function net evaluated)" % (xf, vf): (["xw_interior_forward"], "mixed"),
     }
     kern = {}
     for name, (entries, bound) in groups.items():
@@ -275,42 +445,55 @@ def run_ours(args):
             continue
         alg = sum(fl_[e] * pts_call * ncalls.get(e, 0) for e in entries)
         launches_k = sum(ncalls.get(e, 0) for e in entries)
-        r = {"bound": bound, "ms_per_step": t_ms, "launches_per_step": launches_k,
+        r = {"bound": bound, "ms_per_step": t_ms, "calls_per_step": launches_k, "entries": entries,
              "algorithmic_tflops": alg / (t_ms * 1e-3) / 1e12}
         if bound == "fp32_fma":
             r.update(achieved=r["algorithmic_tflops"], peak=fma_peak, unit="TFLOP/s", frac=r["algorithmic_tflops"] / fma_peak,
-                     peak_source="xw_fma_probe (FFMA chains) measured in this run; nominal 74.4")
+                     peak_source="xw_fma_probe (FFMA chains) measured in this run; nominal 74.4",
+                     note="achieved = ALGORITHMIC FLOPs (SURVEY 8d un-hoisted dense counts) / time; the generation-2 XNODE kernels "
+                          "execute fewer (reduced state: %.0f instead of %.0f MAC per point and pass)" % (fl_["U_reduced_hw"], fl_["U"]))
         elif bound == "tensor":
             ex = tc_bwd_exec * pts_call * launches_k / (t_ms * 1e-3) / 1e12
-            r.update(achieved=ex, peak=tf32_peak, unit="TFLOP/s", frac=ex / tf32_peak,
+            r.update(achieved=r["algorithmic_tflops"], peak=tf32_peak, unit="TFLOP/s", frac=r["algorithmic_tflops"] / tf32_peak,
+                     executed_tflops=ex, frac_executed=ex / tf32_peak,
+                     useful_3x_tflops=3 * r["algorithmic_tflops"], frac_useful_3x=3 * r["algorithmic_tflops"] / tf32_peak,
+                     frac_of_fp32_fma_peak=r["algorithmic_tflops"] / fma_peak,
                      executed_flops_per_point=tc_bwd_exec,
-                     peak_source="MEASURED_PEAKS.json bf16_tflops (burst) / 2: kind::tf32 runs at half the bf16 rate; "
-                                 "achieved counts EXECUTED tensor FLOPs (3 MMAs per product, 128 x 56 x 56 padded tiles)")
+                     peak_source="MEASURED_PEAKS.json bf16_tflops (burst) / 2: kind::tf32 runs at half the bf16 rate",
+                     note="achieved / frac = ALGORITHMIC FLOPs (4 Vm per point); fp32-accurate results need 3 TF32 MMAs per product "
+                          "(frac_useful_3x) and the tiles are padded 50->56 with a forward recompute (frac_executed); "
+                          "frac_of_fp32_fma_peak = the same algorithmic rate against the FP32 pipe it replaces")
         kern[name] = r
     dom_name = max((k for k in kern if kern[k]["bound"] != "mixed"), key=lambda k: kern[k]["ms_per_step"])
     domr = dict(kern[dom_name])
     dom_entries = groups[dom_name][0]
     traffic = None
     try:
-        per_pt = [tj["dram_bytes_per_point"][tj["entry_to_kernel"][e]] * ncalls.get(e, 0) for e in dom_entries]
+        per_pt = [tj["dram_bytes_per_point"][e] * ncalls.get(e, 0) for e in dom_entries]
         traffic = sum(per_pt) / max(1e-9, sum(ncalls.get(e, 0) for e in dom_entries)) * pts_call
     except Exception:
         pass
     bytes_call = {"xw_interior_forward": n_loc * (2 * d * 4 + 2 * L_T * 4 + (d + 1) * 4) + 2 * pts_call * 4,
+                  "xw_interior_forward:cached_v": n_loc * (d * 4 + (d + 1) * 4) + 2 * pts_call * 4 + 4 * pts_call * 4,
                   "xw_interior_backward_v": n_loc * d * 4 + pts_call * 4,
                   "xw_interior_backward_u": n_loc * d * 4 + pts_call * 4 + n_loc * 4,
                   "xw_boundary_u": n_loc * d * 4 + pts_call * 4 + n_loc * 4}
     alg_bytes = sum(bytes_call[e] * ncalls.get(e, 0) for e in dom_entries) / max(1e-9, sum(ncalls.get(e, 0) for e in dom_entries))
     step_flops = (2 * (fl_["u_interior"] + fl_["u_boundary"]) + fl_["v_interior"]) * n_loc * L_T
-    roofline = {"bound": domr["bound"], "kernel": dom_name, "achieved": domr["achieved"], "peak": domr["peak"],
-                "unit": "TFLOP/s", "frac": domr["frac"], "traffic": traffic, "traffic_source": tj.get("source"),
-                "algorithmic_bytes": alg_bytes, "peak_source": domr["peak_source"],
-                "points_per_launch": pts_call, "share_of_step": domr["ms_per_step"] / ms,
+    # FLOPs of the work that actually ran (the test-function net is evaluated once per step, not three times)
+    step_flops_run = sum(fl_[e] * pts_call * ncalls.get(e, 0) for e in per_step if e in fl_)
+    roofline = {"bound": "tensor" if domr["bound"] == "tensor" else "fp32_fma", "kernel": dom_name, "achieved": domr["achieved"], "peak": domr["peak"],
+                "unit": "TFLOP/s", "frac": domr["frac"], "traffic": traffic,
+                "traffic_source": (tj.get("source", "") + " (static: from a committed ncu capture, not this run)") if traffic is not None else None,
+                "algorithmic_bytes": alg_bytes, "peak_source": domr["peak_source"], "note": domr.get("note"),
+                "points_per_call": pts_call, "share_of_step": domr["ms_per_step"] / ms,
                 "kernels": kern,
-                "step_algorithmic_tflops": step_flops / (ms * 1e-3) / 1e12,
-                "step_note": "whole-step algorithmic FLOP/s; the test-function net runs on the tensor cores (3xTF32), so this "
-                             "is context, not a fraction of one pipe's peak (FP32 FFMA peak measured here: %.1f TFLOP/s)" % fma_peak,
-                "hbm_context": {"algorithmic_GBs": alg_bytes / (domr["ms_per_step"] / max(1e-9, domr["launches_per_step"]) * 1e-3) / 1e9,
+                "step_algorithmic_tflops_run": step_flops_run / (ms * 1e-3) / 1e12,
+                "step_algorithmic_tflops_uncached": step_flops / (ms * 1e-3) / 1e12,
+                "step_note": "whole-step algorithmic FLOP/s over two different pipes (context only): `_run` charges the test-function "
+                             "forward once per step (it IS evaluated once: the 2nd u-step and the v-step read the cache), `_uncached` "
+                             "charges it in all three sub-steps as the reference does; FP32 FFMA peak measured here: %.1f TFLOP/s" % fma_peak,
+                "hbm_context": {"algorithmic_GBs": alg_bytes / (domr["ms_per_step"] / max(1e-9, domr["calls_per_step"]) * 1e-3) / 1e9,
                                 "peak_GBs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json"}}
     line = {"metric": "weak-loss+grad path-points/sec", "value": pp_step / (ms * 1e-3), "unit": "path-points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -318,11 +501,17 @@ def run_ours(args):
             "config": config_of(args),
             "e2e": {"value": pp_step / (ms_e2e * 1e-3), "unit": "path-points/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "loss_u": last.get("lu"), "loss_v": last.get("lv")},
+            "e2e_nlc": e2e_nlc,
+            "strong": strong,
+            "shard_check": check,
             "gpu_launches": launches,
             "roofline": roofline,
+            "kernels_launched": {"xnode_generation": xnode_impl, "vnet_forward": vf, "vnet_backward": vb},
             "kernels_ms_per_step": per_step, "kernels_ms_per_call": per_call,
-            "kernels_alg_tflops": {k: fl_[k] * pts_call / (per_call[k] * 1e-3) / 1e12 for k in per_call},
+            "kernels_alg_tflops": {k: fl_[k] * pts_call / (per_call[k] * 1e-3) / 1e12 for k in per_call if k in fl_},
             "clocks": clk}
+    if world == 1 and not args.no_ttt:
+        line["time_to_target"] = time_to_target(xw, dev, list(range(args.ttt_seeds)))
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         n = args.cpu_paths
@@ -341,11 +530,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log2n", type=int, default=20, help="log2 of interior (= boundary) paths per rank")
-    ap.add_argument("--dim", type=int, default=20)
-    ap.add_argument("--cpu-paths", type=int, default=4096, help="paths of the bounded CPU sample")
+    ap.add_argument("--config", default="m", choices=sorted(CONFIGS), help="m: BASELINE configs[3] (d=20, 2^20 paths); xl: configs[4] (d=100, 2^22)")
+    ap.add_argument("--log2n", type=int, default=None, help="log2 of interior (= boundary) paths per rank (overrides --config)")
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--cpu-paths", type=int, default=None, help="paths of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ttt", action="store_true", help="skip the time-to-target runs (N=1 only)")
+    ap.add_argument("--ttt-seeds", type=int, default=5)
+    ap.add_argument("--nlc-max-gb", type=float, default=8.0, help="skip the [N,L,C]-layout e2e arm above this many GB of pinned host memory")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.dim = args.dim if args.dim is not None else cfg["dim"]
+    args.log2n = args.log2n if args.log2n is not None else cfg["log2n"]
+    if args.cpu_paths is None:
+        args.cpu_paths = 4096 if args.dim <= 20 else 1024      # dense a[d,d,N,L] of the reference: 0.8 GB at d=100, N=1024
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -170,3 +170,51 @@ def test_evaluation_from_inside_the_domain_on_gpu(name):
     with torch.no_grad():
         u = s.u_net(torch.from_numpy(z["X"]).to(DEV))
     assert np.abs(u.cpu().numpy()[..., 0] - z["u"]).max() < 2e-5
+
+
+def test_cuda_graph_replay_matches_eager():
+    """NODE_WAN_solver(use_cuda_graph=True): the captured sub-steps (coefficient evaluation + fused loss + backward +
+    Adam) replayed on fresh samples must follow the eager path: 20 outer iterations (60 sub-steps) at the shipped
+    config, same seeds -> losses within 1e-6 relative and parameters within 1e-6 (reference loop src/training.py:119-162).
+    Both runs use the same optimiser arithmetic (Adam with capturable=True, as the graph path needs: its bias
+    corrections are fp32 device tensors; torch's default Adam computes them in Python doubles, which alone moves
+    loss_u by 5e-6 after one step at alpha = 1e8)."""
+    def run(graph):
+        torch.manual_seed(11)
+        np.random.seed(11)
+        p = xw.problems.cube_params(dim=5, N_r=4000, N_b=4000)
+        prob = xw.problems.ex4_1()
+        s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, DEV, "./",
+                               func_u_sol=prob.func_u_sol, p=2, log_json=False, use_cuda_graph=True)
+        s.use_cuda_graph = graph                 # False: eager launches with the same (capturable) Adam
+        losses = []
+        for it in range(20):
+            dom = s.new_domain()
+            pts = xw.Comb_loader(4000, 4000, dom, DEV)
+            lu, lv = s.train_iteration(dom, pts)
+            losses.append((lu.item(), lv.item()))
+        torch.cuda.synchronize()
+        used = s._graphs is not None and len(s._graphs["graphs"]) > 0
+        return losses, [q.detach().clone() for q in list(s.u_net.parameters()) + list(s.v_net.parameters())], used
+    le, pe, ue = run(False)
+    lg, pg, ug = run(True)
+    assert ug and not ue                     # the graph path really replayed graphs
+    for (a0, b0), (a1, b1) in zip(le, lg):
+        # loss_v = -(log I^2 - log S) is O(1) and crosses zero: 1e-6 absolute there, 1e-6 relative on loss_u
+        assert abs(a0 - a1) <= 1e-6 * abs(a0) + 1e-9 and abs(b0 - b1) <= 1e-6 * max(abs(b0), 1.0), (le, lg)
+    for a, b in zip(pe, pg):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+
+
+def test_larger_later_batch_reallocates_the_test_function_cache():
+    """sub_step accepts any `points`; a bigger batch after a small one must not overrun the cache"""
+    torch.manual_seed(5)
+    np.random.seed(5)
+    s, _ = _rand_case(5, 512, 256, 5)
+    dom = s.new_domain()
+    small = xw.Comb_loader(512, 256, dom, DEV)
+    big = xw.Comb_loader(4096, 256, dom, DEV)
+    s.train_iteration(dom, small)
+    n0 = s._vc_buf.numel()
+    lu, lv = s.train_iteration(dom, big)
+    assert s._vc_buf.numel() > n0 and np.isfinite(lu.item()) and np.isfinite(lv.item())

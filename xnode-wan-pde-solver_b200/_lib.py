@@ -55,6 +55,7 @@ _SIGS = {
                                       C.c_size_t, _P, _P, _P, C.c_int, _P, C.c_size_t, C.c_size_t]),
     "xw_yhist_floats": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
     "xw_last_xnode_impl": (C.c_int, []),
+    "xw_last_vnet_impl": (C.c_int, []),
     "xw_vcache_floats": (C.c_size_t, [C.POINTER(Dims), C.c_int, C.c_int]),
     "xw_boundary_u": (C.c_int, [C.POINTER(Dims), _P, _P, C.c_longlong, _P, C.c_int, _P, _P, C.c_int, C.c_double, _P,
                                 _P, C.c_int, _P, C.c_size_t, _P]),

@@ -329,7 +329,8 @@ bool use_x2(const xw_dims* m) {
     const char* e = getenv("XW_XNODE_IMPL");
     return !(e && strcmp(e, "v1") == 0);
 }
-int g_last_xnode_impl = 0;       // 1 / 2: which generation the last XNODE launch used (xw_last_kernel_info)
+int g_last_xnode_impl = 0;       // 1 / 2: which generation the last XNODE launch used
+int g_last_vnet_fwd = 0, g_last_vnet_bwd = 0;   // 1 points, 2 FP32 tile engine, 3 tcgen05 (last v-net forward / backward launch)
 
 size_t x2_smem_fwd(int d, int L) {
     using S = xw::USmem<kH, kHH>;
@@ -427,6 +428,7 @@ size_t xw_yhist_floats(const xw_dims* m, int n, int L) {      // generation 2: (
     return (size_t)L * (use_x2(m) ? xw::x2::kZQ : kH) * n;
 }
 int xw_last_xnode_impl(void) { return g_last_xnode_impl; }
+int xw_last_vnet_impl(void) { return g_last_vnet_fwd | (g_last_vnet_bwd << 4); }
 size_t xw_vcache_floats(const xw_dims* m, int n, int L) { return m ? (size_t)4 * n * L + (size_t)n * m->d : 0; }
 
 size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
@@ -555,6 +557,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         if (vcache_mode != 0) return fail("XW_VNET_IMPL=points (generation-1 kernels) has no test-function cache: call with vcache_mode 0");
         if (XW_SET_SMEM((xw::k_vnet_points<kHV, 1>), smem)) return 1;
         XW_LAUNCH((xw::k_vnet_points<kHV, 1>), grid_for((long long)n * L, 128, 8), 128, smem, stream, b);
+        g_last_vnet_fwd = 1;
         return XW_CHECK_LAUNCH("k_vnet_points<interior>");
     }
     // generation 2: time-row-0 gradient term (one thread per path) + CTA-tiled pass over all points
@@ -598,6 +601,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         const long long nt = ((long long)n * L + 63) / 64;
         const int g3 = (int)std::max<long long>(1, std::min<long long>((nt + ng - 1) / ng, (long long)device()->sms));
         xw::tc::k_vnet_tc_fwd<<<g3, 128 * ng, sm, (cudaStream_t)stream>>>(t, ng);
+        g_last_vnet_fwd = 3;
         return XW_CHECK_LAUNCH("k_vnet_tc_fwd");
     }
 #endif
@@ -608,6 +612,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     const long long ntiles = ((long long)n * L + VT::ROWS - 1) / VT::ROWS;
     const int tgrid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms * ctas_per_sm_for(tsmem, 6)));
     XW_LAUNCH((xw::k_vnet_tile_fwd<kHV, kQR, kNH>), tgrid, VT::THREADS, tsmem, stream, t);
+    g_last_vnet_fwd = 2;
     return XW_CHECK_LAUNCH("k_vnet_tile_fwd");
 }
 
@@ -697,6 +702,7 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
             xw::tc::k_vnet_tc_bwd3<<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
             if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
         }
+        g_last_vnet_bwd = 3;
         return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
     }
 #endif
@@ -712,6 +718,7 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         if (XW_SET_SMEM((xw::k_vnet_tile_bwd<kHV, kQRB>), pl.smem)) return 1;
         XW_LAUNCH((xw::k_vnet_tile_bwd<kHV, kQRB>), pl.grid, VT::THREADS, pl.smem, stream, t);
         if (XW_CHECK_LAUNCH("k_vnet_tile_bwd")) return 1;
+        g_last_vnet_bwd = 2;
         return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
     }
     const int block = 128;
@@ -727,6 +734,7 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
     if (XW_SET_SMEM((xw::k_vnet_bwd<kHV>), smem)) return 1;
     XW_LAUNCH((xw::k_vnet_bwd<kHV>), grid, block, smem, stream, a);
     if (XW_CHECK_LAUNCH("k_vnet_bwd")) return 1;
+    g_last_vnet_bwd = 1;
     return reduce_partials(a.gpart, grid, P, grad_v, accumulate, stream);
 }
 
