@@ -18,7 +18,6 @@ from tests.host_emu import build_emu
 def emu(monkeypatch):
     lib = xw._lib.XwLib(build_emu.build())
     monkeypatch.setattr(xw._lib, "_LIB", lib)
-    monkeypatch.setattr(xw.hotpath, "_TEST_ALLOW_HOST", True)
     return lib
 
 

@@ -28,7 +28,6 @@ def _worker(rank, world, port, name, out):
     from tests.host_emu import build_emu
     from tests.test_host_api_emu import make_solver
     xw._lib._LIB = xw._lib.XwLib(build_emu.build())
-    xw.hotpath._TEST_ALLOW_HOST = True
     case = G.load(name)
     s, _ = make_solver(case)
     assert s.world == world and s.rank == rank
@@ -99,7 +98,6 @@ def _train_worker(rank, world, port, out):
     import xnode_wan_b200 as xw
     from tests.host_emu import build_emu
     xw._lib._LIB = xw._lib.XwLib(build_emu.build())
-    xw.hotpath._TEST_ALLOW_HOST = True
     torch.manual_seed(100 + rank)            # replicas would start from different weights without the broadcast
     np.random.seed(5)                        # ... and draw the same numpy stream without the per-rank reseed
     prob = xw.problems.ex4_1()

@@ -86,6 +86,9 @@ class XwLib:
                 raise XwError("%s does not export %s: stale build, rebuild it (python __graft_entry__.py)" % (path, name))
             fn.restype = res
             fn.argtypes = args
+        # host pointers are only meaningful to the CPU emulation build of the same ABI (tests/host_emu), which
+        # identifies itself with an extra symbol; the product library (nvcc, sm_100a) never has it
+        self.host_memory = hasattr(self.cdll, "xw_emu_marker")
         if self.cdll.xw_abi_version() != ABI_VERSION:
             raise XwError("ABI version mismatch in %s" % path)
 

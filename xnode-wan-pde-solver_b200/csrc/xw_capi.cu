@@ -419,6 +419,11 @@ int x2_run_bwd(const xw_dims* m, xw::x2::BwdArgs a, const X2BwdPlan& p, void* wo
 extern "C" {
 
 int xw_abi_version(void) { return XW_ABI_VERSION; }
+#ifdef XW_EMU
+// only the CPU emulation build (tests/host_emu) has this symbol: it tells the Python layer that THIS library takes host
+// pointers.  The product library does not export it, so the product path keeps refusing CPU tensors.
+int xw_emu_marker(void) { return 1; }
+#endif
 const char* xw_last_error(void) { return g_err; }
 
 int xw_theta_u_size(const xw_dims* m) { return m ? xw::ULayout(m->d, m->H, m->hh).size : -1; }

@@ -18,8 +18,6 @@ import torch
 
 from . import _lib
 
-_TEST_ALLOW_HOST = False      # set ONLY by tests that inject the CPU emulation build
-
 # optional per-call CUDA-event timing (bench.py's roofline): PROFILE = {} to switch on;
 # maps C-ABI entry name -> list of (start_event, end_event) recorded on the launching stream
 PROFILE = None
@@ -61,8 +59,8 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _check_dev(t, what):
-    if not t.is_cuda and not _TEST_ALLOW_HOST:
+def _check_dev(t, what, lib):
+    if not t.is_cuda and not lib.host_memory:
         raise RuntimeError("%s must be a CUDA tensor: the XNODE-WAN hot path has no CPU fallback" % what)
 
 
@@ -283,7 +281,7 @@ class WeakLoss(torch.autograd.Function):
     def forward(ctx, phase, lib, spec, dom, coef, alpha, batch, group, side_effect, vcache, vmode, nu_params, *params):
         pu, pv = params[:nu_params], params[nu_params:]
         theta_u, theta_v = flatten_params(pu), flatten_params(pv)
-        _check_dev(theta_u, "parameters")
+        _check_dev(theta_u, "parameters", lib)
         dev = theta_u.device
         gb = torch.zeros(theta_u.numel(), dtype=torch.float32, device=dev) if phase == "u" else None
         yh = None
@@ -362,7 +360,7 @@ def xnode_eval(spec, u_params, x_base, x_off, x_sn, times, s0, n, lib=None):
     """u[n, L] forward only (fp32)"""
     lib = lib or _lib.get()
     theta_u = flatten_params(u_params)
-    _check_dev(theta_u, "parameters")
+    _check_dev(theta_u, "parameters", lib)
     dims = spec.c()
     L = times.numel()
     out = torch.empty(n, L, dtype=torch.float32, device=theta_u.device)
@@ -375,7 +373,7 @@ def vnet_eval(spec, v_params, XV, lib=None):
     """v[N, L] forward only (fp32) for XV [N, L, C]"""
     lib = lib or _lib.get()
     theta_v = flatten_params(v_params)
-    _check_dev(theta_v, "parameters")
+    _check_dev(theta_v, "parameters", lib)
     XVf = as_f32(XV)
     N, L, Cc = XVf.shape
     dims = spec.c()
