@@ -56,7 +56,7 @@ def test_umma_probe_rejects_bad_shapes(lib):
         lib.call("xw_umma_probe", z.data_ptr(), z.data_ptr(), z.data_ptr(), 8, 16, 2, err.data_ptr(), None)
 
 
-VARIANTS = [("tc", None), ("tc", "serial"), ("tile", None)]
+VARIANTS = [("tc", None), ("tile", None)]
 
 
 @pytest.mark.parametrize("name", ["cube_d20_ex41", "cube_d3_rk4", "cone_d5_g2", "hourglass_d5_g4_reentry"])
@@ -84,15 +84,6 @@ def test_kernel_variants_agree_and_match_golden(lib, name):
             assert abs(r[k] - float(z[k])) <= 1e-4 * abs(float(z[k])) + 1e-9, (key, k)
         for i, (a, b) in enumerate(zip(r["grads_v"], c["gv"])):
             assert G.rel(a, b) < 1e-3, (key, "grad_v", i, G.rel(a, b))
-    # generation 1 (one thread per point) has no test-function cache: asking for it fails loudly
-    os.environ["XW_VNET_IMPL"] = "points"
-    try:
-        with pytest.raises(xw._lib.XwError):
-            LL.run_case(lib, LL.TorchBackend(), c)
-    finally:
-        os.environ.pop("XW_VNET_IMPL", None)
-        if old["XW_VNET_IMPL"] is not None:
-            os.environ["XW_VNET_IMPL"] = old["XW_VNET_IMPL"]
     base = out[("tile", None)]
     for key, r in out.items():
         # (I is a difference of Monte-Carlo sums: on the small sphere groups it cancels to ~1e-2 of its terms)

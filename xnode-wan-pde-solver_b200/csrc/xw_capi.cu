@@ -167,10 +167,6 @@ int plan_vtile_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
     p->part_bytes = align_up((size_t)p->grid * xw::VLayout(m->d, m->Hv).size * 4, 256);
     return 0;
 }
-bool use_point_kernels() {
-    const char* e = getenv("XW_VNET_IMPL");
-    return e && strcmp(e, "points") == 0;
-}
 #ifndef XW_EMU
 // tensor-core backward: one 128-point tile per CTA iteration, one CTA per SM (tensor memory: 512 columns)
 bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
@@ -185,8 +181,7 @@ int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
     return 0;
 }
 #endif
-// XW_VNET_IMPL: "tc" (default on the device build: tcgen05 3xTF32 kernels), "tile" (FP32 FFMA2 tile engine),
-// "points" (generation 1, one thread per point)
+// XW_VNET_IMPL: "tc" (default on the device build: tcgen05 3xTF32 kernels), "tile" (FP32 FFMA2 tile engine)
 bool use_tc_kernels() {
 #ifdef XW_EMU
     return false;
@@ -194,15 +189,6 @@ bool use_tc_kernels() {
     const char* e = getenv("XW_VNET_IMPL");
     return !e || strcmp(e, "tc") == 0;
 #endif
-}
-size_t smem_vnet_bwd(const xw_dims* m, int block) {
-    using S = xw::VSmem<kHV>;
-    const int nw = block / 32;
-    const xw::VLayout g(m->d, m->Hv);
-    size_t f = (size_t)xw::pad4(S::size(m->d + 1));
-    f += (size_t)nw * 128 * xw::kStgLd;
-    f += (size_t)nw * xw::pad4(g.size);
-    return f * 4;
 }
 
 int grid_for(long long items, int block, int ctas_per_sm) {
@@ -217,61 +203,13 @@ int ctas_per_sm_for(size_t smem, int cap) {
     return std::max(1, std::min(k, cap));
 }
 
-// Experiment kept behind a macro: XNODE weights in the constant bank instead of shared memory
-// (to take the warp-uniform weight reads off the LSU pipe).  Measured on B200 (r01): no gain --
-// ptxas turns the constant reads into LDC + register operands and hoists them (255 registers,
-// spills): xnode_eval 0.381 ms vs 0.390 ms, interior forward 7.46 ms vs 6.78 ms at 2^17 paths.
-bool use_const_weights() {
-#ifdef XW_ENABLE_CONST_W
-    const char* e = getenv("XW_XNODE_W");
-    return e && strcmp(e, "const") == 0;
-#else
-    return false;
-#endif
-}
-
-// stage theta_u into the constant bank (c_theta_u) in the USmem image layout
-int upload_u_image(const xw_dims* m, const float* theta_u, void* stream) {
-    using S = xw::USmem<kH, kHH>;
-    const size_t n = (size_t)S::size(m->d);
-    if (n > (size_t)xw::kConstUFloats) return fail("dim %d too large for the constant-bank weight image", m->d);
-#ifdef XW_EMU
-    static float img[xw::kConstUFloats];
-    XW_LAUNCH((xw::k_build_u_image<kH, kHH>), 1, 256, 0, stream, theta_u, m->d, m->H, m->hh, img);
-    memcpy(xw::c_theta_u, img, n * 4);
-    return 0;
-#else
-    static float* img = nullptr;
-    if (!img && cudaMalloc(&img, xw::kConstUFloats * 4) != cudaSuccess) return fail("cudaMalloc failed");
-    XW_LAUNCH((xw::k_build_u_image<kH, kHH>), 1, 256, 0, stream, theta_u, m->d, m->H, m->hh, img);
-    if (check_launch("k_build_u_image")) return 1;
-    cudaError_t e = cudaMemcpyToSymbolAsync(xw::c_theta_u, img, n * 4, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail("cudaMemcpyToSymbolAsync: %s", cudaGetErrorString(e));
-    return 0;
-#endif
-}
-
-#ifdef XW_ENABLE_CONST_W
-#define XW_CONST_LAUNCH(SOLV)                                                               \
-    if (XW_SET_SMEM((k_xnode_fwd<kH, kHH, SOLV, MODE, WConst>), smem)) return 1;            \
-    XW_LAUNCH((k_xnode_fwd<kH, kHH, SOLV, MODE, WConst>), grid, kBlkFwd, smem, stream, a);
-#else
-#define XW_CONST_LAUNCH(SOLV)
-#endif
-
 template <int MODE>
 int launch_xnode_fwd(const xw_dims* m, const xw::XnodeFwdArgs& a, int grid, size_t smem, void* stream) {
     using namespace xw;
-    const bool cw = use_const_weights();
-    if (cw && upload_u_image(m, a.theta, stream)) return 1;
 #define XW_CASE(SOLV)                                                                       \
     case SOLV: {                                                                            \
-        if (cw) {                                                                           \
-            XW_CONST_LAUNCH(SOLV)                                                           \
-        } else {                                                                            \
-            if (XW_SET_SMEM((k_xnode_fwd<kH, kHH, SOLV, MODE, WSmem>), smem)) return 1;     \
-            XW_LAUNCH((k_xnode_fwd<kH, kHH, SOLV, MODE, WSmem>), grid, kBlkFwd, smem, stream, a); \
-        }                                                                                   \
+        if (XW_SET_SMEM((k_xnode_fwd<kH, kHH, SOLV, MODE, WSmem>), smem)) return 1;         \
+        XW_LAUNCH((k_xnode_fwd<kH, kHH, SOLV, MODE, WSmem>), grid, kBlkFwd, smem, stream, a); \
         break;                                                                              \
     }
     switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
@@ -451,9 +389,7 @@ size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
         if (x2_plan_bwd(m, n, L, &p2)) return 0;
         bwd_u = std::max(bwd_u, x2_bwd_bytes(p2));
     }
-    const int vb = 128;
-    int gv = grid_for((long long)n * L, vb, ctas_per_sm_for(smem_vnet_bwd(m, vb), 8));
-    size_t bwd_v = align_up((size_t)gv * xw::VLayout(m->d, m->Hv).size * 4, 256);
+    size_t bwd_v = 0;
     VtileBwdPlan pv;
     if (plan_vtile_bwd(m, n, L, &pv)) return 0;
     bwd_v = std::max(bwd_v, pv.scratch_bytes + pv.part_bytes);
@@ -558,13 +494,6 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         return XW_CHECK_LAUNCH("k_weak_combine");
     }
     const size_t smem = smem_vnet_fwd(m->d);
-    if (use_point_kernels()) {
-        if (vcache_mode != 0) return fail("XW_VNET_IMPL=points (generation-1 kernels) has no test-function cache: call with vcache_mode 0");
-        if (XW_SET_SMEM((xw::k_vnet_points<kHV, 1>), smem)) return 1;
-        XW_LAUNCH((xw::k_vnet_points<kHV, 1>), grid_for((long long)n * L, 128, 8), 128, smem, stream, b);
-        g_last_vnet_fwd = 1;
-        return XW_CHECK_LAUNCH("k_vnet_points<interior>");
-    }
     // generation 2: time-row-0 gradient term (one thread per path) + CTA-tiled pass over all points
     bool row0_done = false;
 #ifndef XW_EMU
@@ -697,21 +626,14 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
         t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
         t.cot = cot_v; t.coefs = coefs_dev; t.scratch = (float*)workspace; t.gpart = (float*)((char*)workspace + pl.scratch_bytes);
-        const char* ev = getenv("XW_VNET_BWD");
-        if (ev && strcmp(ev, "serial") == 0) {           // single warpgroup, everything in sequence (kept for A/B runs)
-            if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd, pl.smem)) return 1;
-            xw::tc::k_vnet_tc_bwd<<<pl.grid, 128, pl.smem, (cudaStream_t)stream>>>(t);
-            if (XW_CHECK_LAUNCH("k_vnet_tc_bwd")) return 1;
-        } else {
-            if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, pl.smem)) return 1;
-            xw::tc::k_vnet_tc_bwd3<<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
-            if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
-        }
+        if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, pl.smem)) return 1;
+        xw::tc::k_vnet_tc_bwd3<<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
+        if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
         g_last_vnet_bwd = 3;
         return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
     }
 #endif
-    if (!use_point_kernels()) {
+    {
         VtileBwdPlan pl;
         if (plan_vtile_bwd(m, n, L, &pl)) return 1;
         if (workspace_bytes < pl.scratch_bytes + pl.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, pl.scratch_bytes + pl.part_bytes);
@@ -726,21 +648,6 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         g_last_vnet_bwd = 2;
         return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
     }
-    const int block = 128;
-    const size_t smem = smem_vnet_bwd(m, block);
-    if (smem > device()->smem_optin) return fail("v backward needs %zu B shared memory per CTA (> %zu)", smem, device()->smem_optin);
-    const int grid = grid_for((long long)n * L, block, ctas_per_sm_for(smem, 8));
-    const int P = xw_theta_v_size(m);
-    if (workspace_bytes < (size_t)grid * P * 4) return fail("workspace too small: %zu < %zu", workspace_bytes, (size_t)grid * P * 4);
-    xw::VnetBwdArgs a{};
-    a.d = m->d; a.Hvr = m->Hv; a.nv = m->nv; a.n = n; a.L = L; a.theta = theta_v; a.p = view_of(xv);
-    a.dom_kind = dom->kind; a.dp0 = dom->p0; a.dp1 = dom->p1; a.dp2 = dom->p2;
-    a.cot = cot_v; a.coefs = coefs_dev; a.gpart = (float*)workspace;
-    if (XW_SET_SMEM((xw::k_vnet_bwd<kHV>), smem)) return 1;
-    XW_LAUNCH((xw::k_vnet_bwd<kHV>), grid, block, smem, stream, a);
-    if (XW_CHECK_LAUNCH("k_vnet_bwd")) return 1;
-    g_last_vnet_bwd = 1;
-    return reduce_partials(a.gpart, grid, P, grad_v, accumulate, stream);
 }
 
 }  // extern "C"

@@ -118,7 +118,7 @@ XW_DEV void rk_step(const W& sw, const float (&ax)[HH], float t0, float dt, int 
 // words kept per field evaluation for the reverse "ones" sweep: 128 mask bits + HH tanh outputs
 template <int HH> constexpr int kRecWords = 4 + HH;
 
-template <int H, int HH, int SOLVER, int MODE, class WS>
+template <int H, int HH, int SOLVER, int MODE, class WS = WSmem>
 XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
     using S = USmem<H, HH>;
     using T = Tableau<SOLVER>;
@@ -261,15 +261,9 @@ XW_GLOBAL void k_xnode_fwd(XnodeFwdArgs a) {
     }
 }
 
-// builds the USmem weight image in GLOBAL memory (one CTA); the host then copies it into the constant bank
-template <int H, int HH>
-XW_GLOBAL void k_build_u_image(const float* theta, int d, int Hr, int HHr, float* img) {
-    stage_theta_u<H, HH>(img, theta, d, Hr, HHr);
-}
-
 // =============================================================================================
-// v net over all points.  MODE 0: v only.  MODE 1: interior forward sums + cotangent seeds
-// (reference src/loss.py:46-76; time derivative of phi and, on time-row 0, grad_x phi)
+// v net, one thread per point.  MODE 0: v only (forward evaluation).  MODE 2: time-row 0 of every path: the
+// a grad(phi).du + b.du phi term of src/loss.py:66-69 (used when the tensor-core row-0 kernel does not cover d)
 // =============================================================================================
 struct VnetFwdArgs {
     int d, Hvr, nv, n, L;
@@ -306,7 +300,6 @@ XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
         if (MODE == 0) { a.v_out[p] = v; continue; }
         float dl[HV];
         vnet_rev_bits<HV>(sv, a.nv, masks, tau, 1.f, dl);
-        const float dv_t = vnet_input_grad<HV>(sv, 0, dl);
         const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, t, xp, d);
         const float phi = v * W.w;
         if (MODE == 2) {
@@ -332,44 +325,7 @@ XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
             acc[2] += (double)s31;
             continue;
         }
-        const float dphi0 = fmaf(W.w, dv_t, v * W.dw_t);
-        const float u = a.u[p], fv = a.f[p];
-        const float cu_ = fmaf(a.c1, u, a.c0);
-        const float A = cu_ * u, Ap = fmaf(a.c1, u, cu_);
-        float s1 = 0.f, s3 = (A + fv) * phi;
-        float cu = Ap * phi, cv = W.w * (A + fv);
-        if (l == L - 1) { s1 = fmaf(u, v, s1); cu = fmaf((float)L, v, cu); cv = fmaf((float)L, u, cv); }
-        if (l == 0) {
-            const float hn = a.h[n];
-            s1 = fmaf(-hn, v, s1);
-            cv = fmaf(-(float)L, hn, cv);
-            const float* dun = a.du + n * d;
-            float s31 = 0.f;
-            for (int i = 0; i < d; ++i) {
-                const float dphi_i = fmaf(W.w, vnet_input_grad<HV>(sv, 1 + i, dl), v * domain_dw_x(W, i, xp));
-                float q;
-                if (a.ca) {
-                    q = 0.f;
-                    for (int j = 0; j < d; ++j) q = fmaf(a.ca[i * d + j], dun[j], q);
-                } else {
-                    q = dun[i];
-                }
-                s31 = fmaf(dphi_i, q, s31);
-            }
-            if (a.cb) {
-                float bq = 0.f;
-                for (int j = 0; j < d; ++j) bq = fmaf(a.cb[j], dun[j], bq);
-                s31 = fmaf(phi, bq, s31);
-            }
-            s3 += s31;
-        }
-        a.cot_u[p] = cu;
-        a.cot_v[p] = cv;
-        if (a.v_out) a.v_out[p] = v;
-        acc[0] += (double)s1;
-        acc[1] += (double)(u * dphi0);
-        acc[2] += (double)s3;
-        acc[3] += (double)(v * v);
+        static_assert(MODE == 0 || MODE == 2, "generation-1 interior pass (MODE 1) was removed");
     }
     if (MODE != 0) {
         const int idx[4] = {0, 1, 2, 3};
@@ -701,119 +657,6 @@ XW_GLOBAL void k_xnode_bwd(XnodeBwdArgs a) {
         double v[1] = {bd_acc};
         const int idx[1] = {5};
         block_sum_to_global<1>(v, red, a.sums, idx);
-    }
-}
-
-// =============================================================================================
-// v net backward: parameter gradients of sum_p G[p] v[p],  G = k0*cot_v + k1*v + k2*w
-// =============================================================================================
-struct VnetBwdArgs {
-    int d, Hvr, nv, n, L;
-    const float* theta; PointsView p;
-    int dom_kind; float dp0, dp1, dp2;
-    const float* cot; const double* coefs;
-    float* gpart;
-};
-
-template <int HV>
-struct StoreLocal {
-    float* acts;   // [nv][HV] per thread (local memory)
-    XW_DEV void operator()(int k, const float (&r)[HV]) const {
-#pragma unroll
-        for (int i = 0; i < HV; ++i) acts[k * HV + i] = r[i];
-    }
-};
-
-template <int HV>
-XW_GLOBAL void k_vnet_bwd(VnetBwdArgs a) {
-    using S = VSmem<HV>;
-    XW_DYN_SMEM(smem_raw);
-    const int nwarps = XW_BDIM >> 5, warp = XW_TID >> 5;
-    const VLayout g(a.d, a.Hvr);
-    const int Pp = pad4(g.size);
-    float* sv = reinterpret_cast<float*>(smem_raw);
-    float* sstg = sv + pad4(S::size(a.d + 1));                       // [nwarps][128][kStgLd]
-    float* sgrad = sstg + (size_t)nwarps * 128 * kStgLd;             // [nwarps][Pp]
-    stage_theta_v<HV>(sv, a.theta, a.d, a.Hvr);
-    for (int i = XW_TID; i < nwarps * Pp; i += XW_BDIM) sgrad[i] = 0.f;
-    XW_SYNCTHREADS();
-    float* stg = sstg + (size_t)warp * 128 * kStgLd;
-    float* gw = sgrad + (size_t)warp * Pp;
-    const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
-
-    const long long nthr = (long long)XW_GDIM * XW_BDIM;
-    const long long gtid = (long long)XW_BID * XW_BDIM + XW_TID;
-    const long long npts = (long long)a.n * a.L;
-    const long long iters = (npts + nthr - 1) / nthr;
-    const int L = a.L, d = a.d, C = a.d + 1, Hvr = a.Hvr;
-    float acts[kMaxNv * HV];
-    for (long long it = 0; it < iters; ++it) {
-        const long long praw = it * nthr + gtid;
-        const bool active = praw < npts;
-        const long long p = active ? praw : npts - 1;
-        const long long n = p / L;
-        const int l = (int)(p - n * L);
-        const float t = a.p.t[n * a.p.t_sn + l * a.p.t_sl];
-        const float* xp = a.p.x + n * a.p.x_sn + l * a.p.x_sl;
-        float tau1[HV + 1];
-        float v;
-        {
-            float tau[HV];
-            v = vnet_fwd<HV>(sv, t, xp, d, a.nv, nullptr, tau, StoreLocal<HV>{acts});
-#pragma unroll
-            for (int i = 0; i < HV; ++i) tau1[i] = tau[i];
-            tau1[HV] = 1.f;
-        }
-        float G = 0.f;
-        if (active) {
-            const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, t, xp, d);
-            G = fmaf(k0, a.cot[p], fmaf(k1, v, k2 * W.w));
-        }
-        {
-            float g1[1] = {G};
-            outer_auto<1, HV + 1, 64>(g1, tau1, stg, [&](int o, int i) -> float* {
-                if (i == HV) return gw + g.bz;
-                return i < Hvr ? gw + g.Wz + i : nullptr;
-            });
-        }
-        float dl[HV];
-        {
-            float wz[HV];
-            load_row<HV>(sv + S::WZ, wz);
-#pragma unroll
-            for (int i = 0; i < HV; ++i) dl[i] = G * wz[i] * (1.f - tau1[i] * tau1[i]);
-        }
-        for (int k = a.nv; k > 0; --k) {
-            float r1[HV + 1];
-#pragma unroll
-            for (int i = 0; i < HV; ++i) r1[i] = acts[(k - 1) * HV + i];
-            r1[HV] = 1.f;
-            outer_auto<HV, HV + 1, 64>(dl, r1, stg, [&](int o, int i) -> float* {
-                if (o >= Hvr) return nullptr;
-                if (i == HV) return gw + g.bh + o;
-                return i < Hvr ? gw + g.Wh + o * Hvr + i : nullptr;
-            });
-            float dn[HV];
-#pragma unroll
-            for (int i = 0; i < HV; ++i) dn[i] = 0.f;
-            matvec_acc<HV, HV, S::HVP>(sv + S::WH, dl, dn);
-#pragma unroll
-            for (int i = 0; i < HV; ++i) dl[i] = r1[i] > 0.f ? dn[i] : 0.f;
-        }
-        // input layer: columns (t, x_0..x_{d-1}, 1)
-        warp_outer_dyn<HV, 7, 4>(dl, C + 1,
-                              [&](int c) -> float { return c == 0 ? t : (c <= d ? xp[c - 1] : 1.f); },
-                              stg, stg + 64 * kStgLd,
-                              [&](int o, int c) -> float* {
-                                  if (o >= Hvr) return nullptr;
-                                  return c < C ? gw + g.Wi + o * C + c : gw + g.bi + o;
-                              });
-    }
-    XW_SYNCTHREADS();
-    for (int e = XW_TID; e < g.size; e += XW_BDIM) {
-        float sgr = 0.f;
-        for (int w = 0; w < nwarps; ++w) sgr += sgrad[(size_t)w * Pp + e];
-        a.gpart[(size_t)XW_BID * g.size + e] = sgr;
     }
 }
 

@@ -160,26 +160,13 @@ XW_DEV void stage_theta_v(float* s, const float* XW_RESTRICT th, int d, int Hvr)
     XW_SYNCTHREADS();
 }
 
-// ---------------------------------------------------------------------------------------------
-// where the XNODE weight image lives: shared memory (LDS: the one LSU pipe per SM) or the constant
-// bank (FFMA takes c[bank][imm] operands directly: no LSU traffic for the warp-uniform weights)
-// ---------------------------------------------------------------------------------------------
-constexpr int kConstUFloats = 8192;
-#ifdef XW_EMU
-inline float c_theta_u[kConstUFloats];
-#else
-__constant__ float c_theta_u[kConstUFloats];
-#endif
+// where the XNODE weight image lives (shared memory).  (A constant-bank variant was measured in round 1 and dropped:
+// ptxas turns the constant reads into LDC + register operands and hoists them -- 255 registers, spills, no gain.)
 struct WSmem {
     static constexpr bool kStage = true;
     const float* p;
     XW_DEV static WSmem make(const float* smem) { return WSmem{smem}; }
     XW_DEV const float* at(int off) const { return p + off; }
-};
-struct WConst {
-    static constexpr bool kStage = false;
-    XW_DEV static WConst make(const float*) { return WConst{}; }
-    XW_DEV const float* at(int off) const { return c_theta_u + off; }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -315,258 +315,6 @@ __device__ __forceinline__ void issue_pop(uint32_t tD, const float* a_hi, const 
     }
 }
 
-__global__ void __launch_bounds__(128) k_vnet_tc_bwd(VtileBwdArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int C = a.d + 1, kin = kin_of(a.d), KA = KP, GS = KP + kin;
-    const VLayout g(a.d, a.Hvr);
-    WImages w;
-    w.wh_hi = reinterpret_cast<float*>(smem_raw);
-    w.wh_lo = w.wh_hi + KP * NP;
-    w.wht_hi = w.wh_lo + KP * NP;
-    w.wht_lo = w.wht_hi + KP * NP;
-    w.wi_hi = w.wht_lo + KP * NP;
-    w.wi_lo = w.wi_hi + kin * NP;
-    w.wz = w.wi_lo + kin * NP;
-    float* dT_hi = w.wz + 64;
-    float* dT_lo = dT_hi + TIMG;
-    float* rT_hi = dT_lo + TIMG;
-    float* rT_lo = rT_hi + TIMG;
-    float* gimg = rT_lo + TIMG;                                  // [56][GS], also the overrun pad of the M = 128 reads
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(gimg + KP * GS + 512);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < 4 * TIMG + KP * GS + 512; i += blockDim.x) dT_hi[i] = 0.f;
-    stage_images(w, a.theta, a.d, a.Hvr, kin);
-    if (tid == 0) { umma::mbar_init(mbar, 1); umma::mbar_init(mbar + 1, 1); }
-    if (warp == 0) umma::tmem_alloc(slot, 512);
-    umma::fence_before();
-    __syncthreads();
-    umma::fence_after();
-    const uint32_t tbase = *slot;
-    const uint32_t lane_addr = tbase + ((uint32_t)(32 * warp) << 16);
-    const uint32_t idesc = umma::idesc_tf32(128, NP), idesc_in = umma::idesc_tf32(128, kin);
-    uint32_t parA = 0, parB = 0;
-    const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
-    const long long npts = (long long)a.n * a.L;
-    const long long ntiles = (npts + 127) / 128;
-    const int L = a.L, nv = a.nv;
-    f4* scr = reinterpret_cast<f4*>(a.scratch) + (size_t)blockIdx.x * (nv > 0 ? nv : 1) * 13 * 128 + tid;
-    float gwz[HV];
-#pragma unroll
-    for (int o = 0; o < HV; ++o) gwz[o] = 0.f;
-    float gbz = 0.f;
-
-    for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
-        const long long p = tix * 128 + tid;
-        const bool valid = p < npts;
-        const long long n = valid ? p / L : 0;
-        const int l = (int)(p - n * L);
-        const float* xr = a.p.x + n * a.p.x_sn + (long long)l * a.p.x_sl;
-        const float tval = valid ? a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl] : 0.f;
-        // ---------------------------------------------------------------- forward (recompute)
-#pragma unroll 1
-        for (int c8 = 0; c8 < kin; c8 += 8) {
-            float hi[8], lo[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int idx = c8 + e;
-                float v = 0.f;
-                if (valid) v = idx == 0 ? tval : (idx <= a.d ? xr[idx - 1] : (idx == C ? 1.f : 0.f));
-                hi[e] = umma::tf32_hi(v);
-                lo[e] = v - hi[e];
-            }
-            umma::tmem_st8(lane_addr + A_COL + c8, hi);
-            umma::tmem_st8(lane_addr + A_COL + KA + c8, lo);
-        }
-        umma::tmem_wait_st();
-        umma::fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after();
-            issue_3xtf32<0>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
-            umma::commit(mbar);
-        }
-        float h[KP];
-        mbar_wait_or_trap(mbar, parA);
-        umma::fence_after();
-        umma::tmem_ld56(lane_addr + D_COL, h);
-#pragma unroll 1
-        for (int layer = 0; layer < nv; ++layer) {
-#pragma unroll
-            for (int o = 0; o < HV; ++o) h[o] = fmaxf(h[o], 0.f);
-            h[BIASC] = 0.f; h[BIASC + 1] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 13; ++c) {
-                f4 v; v.x = h[4 * c]; v.y = h[4 * c + 1]; v.z = h[4 * c + 2]; v.w = h[4 * c + 3];
-                scr[(size_t)(layer * 13 + c) * 128] = v;
-            }
-            h[BIASC] = 1.f;
-#pragma unroll
-            for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
-            store_a_row(lane_addr, KA, h);
-            umma::tmem_wait_st();
-            umma::fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                umma::fence_after();
-                issue_3xtf32<KP / 8>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wh_hi, w.wh_lo, 0, idesc);
-                umma::commit(mbar);
-            }
-            mbar_wait_or_trap(mbar, parA);
-            umma::fence_after();
-            umma::tmem_ld56(lane_addr + D_COL, h);
-        }
-        // ---------------------------------------------------------------- output layer, cotangent G
-        {
-            float v = w.wz[KP];
-#pragma unroll
-            for (int o = 0; o < HV; ++o) {
-                h[o] = tanh_fast(h[o]);
-                v = fmaf(w.wz[o], h[o], v);
-            }
-            float G = 0.f;
-            if (valid) {
-                const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
-                G = fmaf(k0, a.cot[p], fmaf(k1, v, k2 * W.w));
-            }
-            gbz += G;
-#pragma unroll
-            for (int o = 0; o < HV; ++o) {
-                const float t = h[o];
-                gwz[o] = fmaf(G, t, gwz[o]);
-                h[o] = G * w.wz[o] * (1.f - t * t);              // delta_nv
-            }
-#pragma unroll
-            for (int o = HV; o < KP; ++o) h[o] = 0.f;
-        }
-        // ---------------------------------------------------------------- reverse sweep
-        uint32_t pacc = 0;                                        // the first P-op of a tile overwrites the accumulator
-#pragma unroll 1
-        for (int k = nv; k >= 0; --k) {
-            // delta_k: transposed image (A of the P-op) and, for k > 0, tensor-memory row (A of the R-op)
-#pragma unroll
-            for (int o = 0; o < HV; ++o) {
-                const float hi = umma::tf32_hi(h[o]);
-                dT_hi[t_off(o, tid)] = hi;
-                dT_lo[t_off(o, tid)] = h[o] - hi;
-            }
-            if (k == 0) break;
-            store_a_row(lane_addr, KA, h);
-            // r_{k-1}: back from the scratch -> relu mask + transposed image with the ones column
-            uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll
-            for (int c = 0; c < 13; ++c) {
-                const f4 v = scr[(size_t)((k - 1) * 13 + c) * 128];
-                const float rv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int o = 4 * c + e;
-                    if (o < HV) {
-                        if (o < 32) m0 |= (rv[e] > 0.f ? 1u : 0u) << o; else m1 |= (rv[e] > 0.f ? 1u : 0u) << (o - 32);
-                        const float hi = umma::tf32_hi(rv[e]);
-                        rT_hi[t_off(o, tid)] = hi;
-                        rT_lo[t_off(o, tid)] = rv[e] - hi;
-                    }
-                }
-            }
-            rT_hi[t_off(BIASC, tid)] = 1.f; rT_lo[t_off(BIASC, tid)] = 0.f;
-#pragma unroll
-            for (int o = BIASC + 1; o < KP; ++o) { rT_hi[t_off(o, tid)] = 0.f; rT_lo[t_off(o, tid)] = 0.f; }
-            umma::fence_smem_to_async();
-            umma::tmem_wait_st();
-            umma::fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                umma::fence_after();
-                issue_3xtf32<KP / 8>(tbase + D_COL, tbase + A_COL, tbase + A_COL + KA, w.wht_hi, w.wht_lo, 0, idesc);
-                umma::commit(mbar);
-                issue_pop(tbase + WH_COL, dT_hi, dT_lo, rT_hi, rT_lo, idesc, pacc);
-                umma::commit(mbar + 1);
-            }
-            pacc = 1;
-            mbar_wait_or_trap(mbar, parA);
-            umma::fence_after();
-            umma::tmem_ld56(lane_addr + D_COL, h);
-#pragma unroll
-            for (int o = 0; o < 32; ++o) h[o] = ((m0 >> o) & 1u) ? h[o] : 0.f;
-#pragma unroll
-            for (int o = 32; o < HV; ++o) h[o] = ((m1 >> (o - 32)) & 1u) ? h[o] : 0.f;
-#pragma unroll
-            for (int o = HV; o < KP; ++o) h[o] = 0.f;
-            mbar_wait_or_trap(mbar + 1, parB);                    // the images and the A rows are free again
-        }
-        // ---------------------------------------------------------------- input layer: dWi | dbi
-#pragma unroll 1
-        for (int c = 0; c < kin; ++c) {
-            float v = 0.f;
-            if (valid) v = c == 0 ? tval : (c <= a.d ? xr[c - 1] : (c == C ? 1.f : 0.f));
-            const float hi = umma::tf32_hi(v);
-            rT_hi[t_off(c, tid)] = hi;
-            rT_lo[t_off(c, tid)] = v - hi;
-        }
-        umma::fence_smem_to_async();
-        umma::fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after();
-            issue_pop(tbase + WI_COL, dT_hi, dT_lo, rT_hi, rT_lo, idesc_in, 0u);
-            umma::commit(mbar + 1);
-        }
-        mbar_wait_or_trap(mbar + 1, parB);
-        umma::fence_after();
-        // ---------------------------------------------------------------- flush the tile's accumulators
-        if (warp < 2) {                                           // rows o = tid < 56 carry data; warps stay converged for tcgen05.ld
-            float* grow = gimg + (tid < KP ? tid : 0) * GS;
-            if (nv > 0) {
-                float acc[KP];
-                umma::tmem_ld56(lane_addr + WH_COL, acc);
-                if (tid < KP) {
-#pragma unroll
-                    for (int i = 0; i < KP; ++i) grow[i] += acc[i];
-                }
-            }
-#pragma unroll 1
-            for (int c8 = 0; c8 < kin; c8 += 8) {
-                float acc[8];
-                umma::tmem_ld8(lane_addr + WI_COL + c8, acc);
-                if (tid < KP) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) grow[KP + c8 + e] += acc[e];
-                }
-            }
-        }
-        umma::fence_before();
-    }
-    __syncthreads();
-    // ------------------------------------------------------------------------ write the CTA's partial
-    float* zimg = dT_hi;                                           // [64]: dWz | dbz
-    if (tid < 64) zimg[tid] = 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int o = 0; o < HV; ++o) {
-        const float sred = warp_sum(gwz[o]);
-        if (lane == 0) atomicAdd(zimg + o, sred);
-    }
-    {
-        const float sb = warp_sum(gbz);
-        if (lane == 0) atomicAdd(zimg + KP, sb);
-    }
-    __syncthreads();
-    float* out = a.gpart + (size_t)blockIdx.x * g.size;
-    const int Hvr = a.Hvr;
-    for (int e = tid; e < Hvr * C; e += blockDim.x) { const int o = e / C, c = e - o * C; out[g.Wi + e] = gimg[o * GS + KP + c]; }
-    for (int e = tid; e < Hvr * Hvr; e += blockDim.x) { const int o = e / Hvr, i = e - o * Hvr; out[g.Wh + e] = gimg[o * GS + i]; }
-    for (int o = tid; o < Hvr; o += blockDim.x) {
-        out[g.bi + o] = gimg[o * GS + KP + C];
-        out[g.bh + o] = gimg[o * GS + BIASC];
-        out[g.Wz + o] = zimg[o];
-    }
-    if (tid == 0) out[g.bz] = zimg[KP];
-    umma::fence_before();
-    __syncthreads();
-    if (warp == 0) umma::tmem_free(tbase, 512);
-}
-
 // =============================================================================================
 // The same backward as a three-stage warp-specialised pipeline (384 threads, one CTA per SM):
 //   F (warps 0-3)  : forward recompute of tile t+1, output layer, cotangent G, dWz, delta_nv -> mailbox (D_f)
@@ -635,6 +383,30 @@ __device__ __forceinline__ void store_a_row_chunked(uint32_t addr_hi, uint32_t a
     }
 }
 
+
+// L2 residency hints for the activation scratch of k_vnet_tc_bwd3: the scratch (2 x nv x 28 KB per CTA, ~76 MB per launch)
+// is written by the F role and read back by the R / P roles one or two tiles later, then overwritten in place -- it never
+// needs to reach HBM.  With default policies the streaming inputs evicted it (28.6 GB of DRAM write-back per launch in
+// the r01h capture); scratch accesses carry an evict_last policy and the once-read inputs are loaded evict_first.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_scratch(f4* ptr, const f4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st_scratch1(float* ptr, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ f4 ld_scratch(const f4* ptr, uint64_t pol) {
+    f4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol)
+                 : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = a.d + 1, kin = kin_of(a.d), GS = KP + kin;
@@ -682,6 +454,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     const long long ntiles = (npts + 127) / 128;
     const int L = a.L, nv = a.nv, nvs = nv > 0 ? nv : 1;
     f4* scr = reinterpret_cast<f4*>(a.scratch) + (size_t)blockIdx.x * 2 * nvs * 14 * 128 + j;
+    const uint64_t pol = l2_evict_last_policy();
 
     if (wg == 0) {
         // ======================================================================== F: forward of every tile
@@ -708,7 +481,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 for (int e = 0; e < 8; ++e) {
                     const int idx = c8 + e;
                     float v = 0.f;
-                    if (valid) v = idx == 0 ? tval : (idx <= a.d ? xr[idx - 1] : (idx == C ? 1.f : 0.f));
+                    if (valid) v = idx == 0 ? tval : (idx <= a.d ? __ldcs(xr + idx - 1) : (idx == C ? 1.f : 0.f));
                     hi[e] = umma::tf32_hi(v);
                     lo[e] = v - hi[e];
                 }
@@ -740,16 +513,16 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
 #pragma unroll
                     for (int c = 0; c < 7; ++c) {
                         f4 v; v.x = h[4 * c]; v.y = h[4 * c + 1]; v.z = h[4 * c + 2]; v.w = h[4 * c + 3];
-                        sb[(size_t)(layer * 14 + c) * 128] = v;
+                        st_scratch(sb + (size_t)(layer * 14 + c) * 128, v, pol);
                     }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 6; ++c) {                         // units 28..51
                         f4 v; v.x = h[4 * c]; v.y = h[4 * c + 1]; v.z = h[4 * c + 2]; v.w = h[4 * c + 3];
-                        sb[(size_t)(layer * 14 + 7 + c) * 128] = v;
+                        st_scratch(sb + (size_t)(layer * 14 + 7 + c) * 128, v, pol);
                     }
                 }
-                reinterpret_cast<float*>(sb + (size_t)(layer * 14 + 13) * 128)[ch] = __uint_as_float(m);
+                st_scratch1(reinterpret_cast<float*>(sb + (size_t)(layer * 14 + 13) * 128) + ch, __uint_as_float(m), pol);
                 uint32_t rh[28], rl[28];
 #pragma unroll
                 for (int i = 0; i < 28; ++i) {
@@ -789,7 +562,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 float G = 0.f;
                 if (valid) {
                     const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
-                    G = fmaf(k0, a.cot[p], fmaf(k1, v, k2 * W.w));
+                    G = fmaf(k0, __ldcs(a.cot + p), fmaf(k1, v, k2 * W.w));
                 }
                 gbz += G;
                 uint32_t r[28];
@@ -859,7 +632,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 umma::mbar_arrive(mDPh + hh_);
                 published = true;
                 if (k == 0) break;
-                const f4 mv = sb[(size_t)((k - 1) * 14 + 13) * 128];
+                const f4 mv = ld_scratch(sb + (size_t)((k - 1) * 14 + 13) * 128, pol);
                 const uint32_t m0 = __float_as_uint(mv.x), m1 = __float_as_uint(mv.y);
                 mbar_wait_or_trap(mR, pR);
                 umma::fence_after();
@@ -895,7 +668,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 f4 rv4[13];
                 if (k > 0) {
 #pragma unroll
-                    for (int c = 0; c < 13; ++c) rv4[c] = sb[(size_t)((k - 1) * 14 + c) * 128];
+                    for (int c = 0; c < 13; ++c) rv4[c] = ld_scratch(sb + (size_t)((k - 1) * 14 + c) * 128, pol);
                 }
                 if (pending) { mbar_wait_or_trap(mPh + hh_, pP); pending = false; }     // this half's images are free again
                 if (k > 0) {
@@ -919,7 +692,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
 #pragma unroll 1
                     for (int c = 0; c < kin; ++c) {
                         float v = 0.f;
-                        if (valid) v = c == 0 ? tval : (c <= a.d ? xr[c - 1] : (c == C ? 1.f : 0.f));
+                        if (valid) v = c == 0 ? tval : (c <= a.d ? __ldcs(xr + c - 1) : (c == C ? 1.f : 0.f));
                         const float hi = umma::tf32_hi(v);
                         rT_hi[th_off(c, j)] = hi;
                         rT_lo[th_off(c, j)] = v - hi;
