@@ -154,7 +154,8 @@ def config_of(args):
             "parallelism": "dp%d (paths sharded, 2 small all-reduces per sub-step)" % args.gpus}
 
 
-XNODE_NAMES = {1: ("k_xnode_fwd", "k_xnode_bwd"), 2: ("k_xnode2_fwd", "k_xnode2_bwd (+ k_xnode2_lift, k_xnode2_finish)")}
+XNODE_NAMES = {1: ("k_xnode_fwd", "k_xnode_bwd"), 2: ("k_xnode2_fwd", "k_xnode2_bwd (+ k_xnode2_lift, k_xnode2_finish)"),
+               3: ("k_xnode2_fwd", "k_xnode3_bwd (+ k_xnode2_fwd<history> in front of the boundary pass, k_xnode2_lift, k_xnode2_finish)")}
 VNET_FWD = {1: "k_vnet_points", 2: "k_vnet_tile_fwd", 3: "k_vnet_tc_fwd (+ k_vnet_tc_row0)"}
 VNET_BWD = {1: "k_vnet_bwd", 2: "k_vnet_tile_bwd", 3: "k_vnet_tc_bwd3"}
 

@@ -9,6 +9,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -24,9 +25,18 @@ struct NamedBar {
     unsigned gen = 0;
 };
 
+// mbarrier (PTX mbarrier.init / arrive / try_wait.parity) keyed by the address of its 8-byte slot in shared memory
+struct MBar {
+    int count = 0, pending = 0;
+    unsigned phase = 0;
+};
+
 struct Block {
     int bdim = 0;
     NamedBar nbar[16];
+    std::mutex mb_mu;
+    std::condition_variable mb_cv;
+    std::map<const void*, MBar> mbars;
     std::unique_ptr<std::barrier<>> bar;
     std::vector<std::unique_ptr<std::barrier<>>> wbar;
     std::vector<uint64_t> xchg;           // [nwarps][32]
@@ -78,6 +88,28 @@ inline T atomic_add(T* p, T v) {
     return old;
 }
 
+inline void mbar_init(const void* p, int count) {
+    std::lock_guard<std::mutex> lk(blk->mb_mu);
+    MBar& m = blk->mbars[p];
+    m.count = m.pending = count;
+    m.phase = 0;
+}
+inline void mbar_arrive(const void* p) {
+    std::lock_guard<std::mutex> lk(blk->mb_mu);
+    MBar& m = blk->mbars[p];
+    if (--m.pending == 0) {
+        m.pending = m.count;
+        m.phase ^= 1u;
+        blk->mb_cv.notify_all();
+    }
+}
+// waits for the completion of the phase with parity `parity` (the barrier starts in phase 0)
+inline void mbar_wait(const void* p, unsigned parity) {
+    std::unique_lock<std::mutex> lk(blk->mb_mu);
+    MBar& m = blk->mbars[p];
+    blk->mb_cv.wait(lk, [&] { return (m.phase & 1u) != (parity & 1u); });
+}
+
 // run `f()` as a kernel body over grid x block threads with `smem_bytes` of dynamic shared memory
 template <typename F>
 inline void launch(int grid, int block, size_t smem_bytes, F f) {
@@ -116,6 +148,11 @@ inline unsigned char* dyn_smem() {
 #define XW_SYNCWARP() emu::warp_sync()
 #define XW_BAR_SYNC(id, n) emu::named_bar((id), (n), true)
 #define XW_BAR_ARRIVE(id, n) emu::named_bar((id), (n), false)
+#define XW_MBAR_INIT(p, n) emu::mbar_init((p), (n))
+#define XW_MBAR_ARRIVE(p) emu::mbar_arrive((p))
+#define XW_MBAR_WAIT(p, parity) emu::mbar_wait((p), (parity))
+#define XW_SETMAXNREG_INC(n) ((void)0)
+#define XW_SETMAXNREG_DEC(n) ((void)0)
 #define XW_SHFL_XOR(v, m) emu::shfl_xor((v), (m))
 #define XW_SHFL_IDX(v, l) emu::shfl_idx((v), (l))
 #define XW_TID (emu::tid)

@@ -6,6 +6,7 @@
 #include "../../include/xnode_wan_b200.h"
 #include "xw_kernels.cuh"
 #include "xw_xnode2.cuh"
+#include "xw_xnode3.cuh"
 #include "xw_umma.cuh"
 #include "xw_vnet_tc.cuh"
 
@@ -278,11 +279,20 @@ int x2_grid_fwd(int n) { return grid_for(n, xw::x2::kFwdThreads, 1); }
 size_t x2_rec_bytes(const xw_dims* m, int n, int L) {
     return align_up((size_t)std::max(L, 1) * stages_of(m->solver) * xw::x2::kRecWords2 * x2_grid_fwd(n) * xw::x2::kFwdThreads * 4, 256);
 }
-struct X2BwdPlan { int grid, lgrid, lblock; size_t smem, lsmem, hist_b, pp_b, pa_b, pb_b; };
+struct X2BwdPlan { int grid, lgrid, lblock; size_t smem, lsmem, hist_b, pp_b, pa_b, pb_b; bool three; };
+// XW_XNODE_BWD=v2 forces the 2-role backward kernel (k_xnode2_bwd) instead of the 3-role one (k_xnode3_bwd): A/B runs
+bool use_three_roles() {
+    const char* e = getenv("XW_XNODE_BWD");
+    return !(e && strcmp(e, "v2") == 0);
+}
 int x2_plan_bwd(const xw_dims* m, int n, int L, X2BwdPlan* p) {
     using S = xw::USmem<kH, kHH>;
     const Dev* dv = device();
     p->smem = (size_t)(xw::pad4(S::size(m->d)) + xw::x2::R::size + xw::pad4(L) + 4 + xw::x2::kCW * 3 * xw::x2::kTile + xw::x2::kPartA) * 4 + 32 * 8;
+    const size_t smem3 = (size_t)(xw::pad4(xw::x3::Sm::fixed + m->d * xw::x2::HHP) + xw::pad4(L) + 4 + xw::x3::kTriples * 4 * xw::x2::kTile) * 4 +
+                         xw::x3::kTriples * 8 * 8 + 32 * 8;
+    p->three = use_three_roles() && smem3 <= dv->smem_optin;
+    if (p->three) p->smem = smem3;
     if (p->smem > dv->smem_optin)
         return fail("xnode backward needs %zu B shared memory per CTA (> %zu): N_t/dim too large", p->smem, dv->smem_optin);
     const int cpaths = 32 * xw::x2::kCW;
@@ -294,7 +304,7 @@ int x2_plan_bwd(const xw_dims* m, int n, int L, X2BwdPlan* p) {
     if (p->lsmem > dv->smem_optin)
         return fail("xnode lift backward needs %zu B shared memory per CTA (> %zu): dim too large", p->lsmem, dv->smem_optin);
     p->lgrid = grid_for(n, p->lblock, ctas_per_sm_for(p->lsmem, 4));
-    p->hist_b = align_up((size_t)L * xw::x2::kZQ * p->grid * cpaths * 4, 256);
+    p->hist_b = align_up((size_t)L * xw::x2::kZQ * (p->three ? (size_t)n : (size_t)p->grid * cpaths) * 4, 256);
     p->pp_b = align_up((size_t)xw::x2::kPerPath * n * 4, 256);
     p->pa_b = align_up((size_t)p->grid * xw::x2::kPartA * 4, 256);
     p->pb_b = align_up((size_t)p->lgrid * P * 4, 256);
@@ -329,16 +339,42 @@ int x2_run_bwd(const xw_dims* m, xw::x2::BwdArgs a, const X2BwdPlan& p, void* wo
     a.perpath = (float*)(ws + p.hist_b);
     a.partA = (float*)(ws + p.hist_b + p.pp_b);
     float* partB = (float*)(ws + p.hist_b + p.pp_b + p.pa_b);
+    if (p.three) {
+        // 3-role kernel: the reduced state history is an input; without one (boundary batch, or an interior call that was
+        // not handed the forward kernel's history) a forward-only launch writes it into the workspace first
+        if (!a.zq) {
+            FwdArgs f{};
+            f.d = a.d; f.Hr = a.Hr; f.HHr = a.HHr; f.nsh = a.nsh; f.L = a.L; f.n = a.n;
+            f.theta = a.theta; f.x = a.x; f.x_sn = a.x_sn; f.times = a.times; f.s0 = a.s0; f.zq = a.hist;
+            if (x2_launch_fwd<0>(m, f, stream)) return 1;
+            a.zq = a.hist;
+        }
+        xw::x3::Args q{};
+        q.d = a.d; q.Hr = a.Hr; q.HHr = a.HHr; q.nsh = a.nsh; q.L = a.L; q.n = a.n;
+        q.theta = a.theta; q.x = a.x; q.x_sn = a.x_sn; q.times = a.times; q.cot = a.cot; q.coefs = a.coefs; q.hloss = a.hloss;
+        q.zq = a.zq; q.gscale = a.gscale; q.perpath = a.perpath; q.partA = a.partA; q.sums = a.sums;
+#define XW_CASE(SOLV)                                                                                   \
+    case SOLV: {                                                                                        \
+        if (XW_SET_SMEM((xw::x3::k_xnode3_bwd<SOLV, MODE>), p.smem)) return 1;                          \
+        XW_LAUNCH((xw::x3::k_xnode3_bwd<SOLV, MODE>), p.grid, xw::x3::kThreads, p.smem, stream, q);    \
+        break;                                                                                          \
+    }
+        switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
+#undef XW_CASE
+        g_last_xnode_impl = 3;
+        if (XW_CHECK_LAUNCH("k_xnode3_bwd")) return 1;
+    } else {
 #define XW_CASE(SOLV)                                                                       \
     case SOLV: {                                                                            \
         if (XW_SET_SMEM((k_xnode2_bwd<SOLV, MODE>), p.smem)) return 1;                      \
         XW_LAUNCH((k_xnode2_bwd<SOLV, MODE>), p.grid, kBwdThreads, p.smem, stream, a);      \
         break;                                                                              \
     }
-    switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
+        switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
 #undef XW_CASE
-    g_last_xnode_impl = 2;
-    if (XW_CHECK_LAUNCH("k_xnode2_bwd")) return 1;
+        g_last_xnode_impl = 2;
+        if (XW_CHECK_LAUNCH("k_xnode2_bwd")) return 1;
+    }
     if (!grad_u) return 0;
     LiftArgs l{};
     l.d = a.d; l.Hr = a.Hr; l.HHr = a.HHr; l.n = a.n; l.theta = a.theta; l.x = a.x; l.x_sn = a.x_sn; l.s0 = a.s0;

@@ -27,12 +27,34 @@
 #define XW_BAR_ARRIVE(id, n) asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory")
 #define XW_SHFL_XOR(v, m) __shfl_xor_sync(0xffffffffu, (v), (m))
 #define XW_SHFL_IDX(v, l) __shfl_sync(0xffffffffu, (v), (l))
+// shared-memory mbarriers (phase-parity producer / consumer hand-offs; any number of them, unlike the 16 named barriers).
+// arrive = release.cta, wait = acquire.cta: data written before the arrive is visible after the matching wait.
+#define XW_MBAR_INIT(p, n)                                                                                             \
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"((int)(n)) : "memory")
+#define XW_MBAR_ARRIVE(p) \
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(p)) : "memory")
+#define XW_MBAR_WAIT(p, parity) xw_mbar_wait((p), (parity))
+// per-warpgroup register re-allocation (warp-specialised kernels)
+#define XW_SETMAXNREG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(n))
+#define XW_SETMAXNREG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(n))
 #define XW_TID ((int)threadIdx.x)
 #define XW_BID ((int)blockIdx.x)
 #define XW_BDIM ((int)blockDim.x)
 #define XW_GDIM ((int)gridDim.x)
 #define XW_ATOMIC_ADD_F(p, v) atomicAdd((p), (v))
 #define XW_ATOMIC_ADD_D(p, v) atomicAdd((p), (v))
+#endif
+
+#ifndef XW_EMU
+// spin on mbarrier.try_wait.parity (the instruction itself suspends the thread for a bounded time per probe)
+__device__ __forceinline__ void xw_mbar_wait(const void* p, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
 #endif
 
 // 16-byte asynchronous global->shared copy (LDGSTS) and its completion wait

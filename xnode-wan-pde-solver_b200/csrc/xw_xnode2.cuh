@@ -84,20 +84,22 @@ struct CoreRegs {
     fpair w[HH][HH / 2];
     fpair b[HH / 2];
 };
-XW_DEV void load_core(const float* su, CoreRegs& cr) {
+// wst: [HH][HHP] in-major image of Ws (wst[i][o] = Ws[o][i]); bs: [HHP]
+XW_DEV void load_core_from(const float* wst, const float* bs, CoreRegs& cr) {
 #pragma unroll
     for (int i = 0; i < HH; ++i)
 #pragma unroll
         for (int jp = 0; jp < HH / 2; ++jp) {
-            const f2 v = ld2(su + S::WST + i * S::HHP + 2 * jp);
+            const f2 v = ld2(wst + i * HHP + 2 * jp);
             cr.w[i][jp] = pack2(v.x, v.y);
         }
 #pragma unroll
     for (int jp = 0; jp < HH / 2; ++jp) {
-        const f2 v = ld2(su + S::BS + 2 * jp);
+        const f2 v = ld2(bs + 2 * jp);
         cr.b[jp] = pack2(v.x, v.y);
     }
 }
+XW_DEV void load_core(const float* su, CoreRegs& cr) { load_core_from(su + S::WST, su + S::BS, cr); }
 
 XW_DEV void st_vec10(float* p, const float (&v)[HH], float v10) {
     st4(p, f4{v[0], v[1], v[2], v[3]});
@@ -226,11 +228,14 @@ XW_DEV float p_of(const float* sr, const float (&tau)[HH]) {
     return p0 + p1;
 }
 // first pre-activation of a stage: a = ax + wt t + zin
-XW_DEV void stage_input(const float* su, const float (&ax)[HH], float t, const float (&zin)[HH], float (&a)[HH]) {
+XW_DEV void stage_input_from(const float* wtp, const float (&ax)[HH], float t, const float (&zin)[HH], float (&a)[HH]) {
     float wt[HH];
-    load_row<HH>(su + S::WT, wt);
+    load_row<HH>(wtp, wt);
 #pragma unroll
     for (int i = 0; i < HH; ++i) a[i] = fmaf(wt[i], t, ax[i]) + zin[i];
+}
+XW_DEV void stage_input(const float* su, const float (&ax)[HH], float t, const float (&zin)[HH], float (&a)[HH]) {
+    stage_input_from(su + S::WT, ax, t, zin, a);
 }
 
 // one explicit RK step of the reduced state (z, q), recording stage internals in rec[s]
@@ -311,7 +316,7 @@ struct FwdArgs {
     const float* theta; const float* x; long long x_sn; const float* times; const float* s0;
     float* u_out;
     const float* grad_h; float* du_out; float* rec; double* sums; const float* hloss;
-    float* zq;                   // MODE 1, optional: [L][kZQ][n] reduced state history kept for the interior backward
+    float* zq;                   // optional: [L][kZQ][n] reduced state history kept for the backward kernels
 };
 constexpr int kFwdThreads = 256;
 constexpr int kRecWords2 = 4 + HH;
@@ -345,13 +350,11 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kFwdThreads, 1) k_xnode2_fwd(FwdArgs a) {
         float z[HH], q;
         lift_reduced(su, s0, z, q);
         if (a.u_out) a.u_out[n * L] = q + bo;
-        if (MODE == 1) {
-            { const float hd = (q + bo) - a.hloss[n]; init_acc += (double)(hd * hd); }
-            if (a.zq) {
+        if (MODE == 1) { const float hd = (q + bo) - a.hloss[n]; init_acc += (double)(hd * hd); }
+        if (a.zq) {
 #pragma unroll
-                for (int i = 0; i < HH; ++i) a.zq[(long long)i * a.n + n] = z[i];
-                a.zq[(long long)HH * a.n + n] = q;
-            }
+            for (int i = 0; i < HH; ++i) a.zq[(long long)i * a.n + n] = z[i];
+            a.zq[(long long)HH * a.n + n] = q;
         }
         for (int l = 0; l + 1 < L; ++l) {
             const float t0 = st[l], dt = st[l + 1] - st[l];
@@ -370,14 +373,14 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kFwdThreads, 1) k_xnode2_fwd(FwdArgs a) {
 #pragma unroll
                     for (int i = 0; i < HH; ++i) hp[(4 + i) * nthr] = rec[s].tau[i];
                 }
-                if (a.zq) {
-#pragma unroll
-                    for (int i = 0; i < HH; ++i) a.zq[((long long)(l + 1) * kZQ + i) * a.n + n] = z[i];
-                    a.zq[((long long)(l + 1) * kZQ + HH) * a.n + n] = q;
-                }
             } else {
                 NoRec rec[T::S];
                 rk_step_red<SOLVER>(cr, su, sr, ax, t0, dt, nsh, z, q, rec);
+            }
+            if (a.zq) {
+#pragma unroll
+                for (int i = 0; i < HH; ++i) a.zq[((long long)(l + 1) * kZQ + i) * a.n + n] = z[i];
+                a.zq[((long long)(l + 1) * kZQ + HH) * a.n + n] = q;
             }
             if (a.u_out) a.u_out[n * L + l + 1] = q + bo;
         }
