@@ -377,3 +377,38 @@ def test_vcache_grows_with_the_batch_and_capi_checks_capacity(emu):
                  be.ptr(be.arr(z["grad_h"])), be.ptr(be.arr(z["f"])), N, be.ptr(sums), be.ptr(cu), be.ptr(cv), None,
                  be.ptr(ws), wsb, None, None, be.ptr(vc), 1, None, need - 1, 0)
     assert not sums.any() and not vc.any()
+
+
+def test_coefficient_values_are_evaluated_once_per_sample(emu):
+    """the sub-steps of one outer iteration run on one sample: h, f, g, grad h are evaluated by the first one only, and
+    the numbers are the same as re-evaluating them every time"""
+    case = G.load("cube_d3_small_nets")
+    calls = {"h": 0, "f": 0}
+
+    def run(cache):
+        torch.manual_seed(4)
+        np.random.seed(4)
+        s, prob = make_solver(case)
+        fh, ff = s.func_h, s.func_f
+        s.func_h = lambda X0: (calls.__setitem__("h", calls["h"] + 1), fh(X0))[1]
+        s.func_f = lambda X: (calls.__setitem__("f", calls["f"] + 1), ff(X))[1]
+        s.u_net.module.h = s.func_h
+        dom = s.new_domain()
+        pts = xw.Comb_loader(32, 24, dom, "cpu")
+        out = []
+        if not cache:
+            orig = s._step
+            s._step = lambda ph, d_, b_, vp=(None, 0), token=None: orig(ph, d_, b_, vp, token=None)
+        for _ in range(2):
+            lu, lv = s.train_iteration(dom, pts)
+            out.append((lu.item(), lv.item()))
+        return out
+    calls.update(h=0, f=0)
+    a = run(True)
+    n_cached = dict(calls)
+    calls.update(h=0, f=0)
+    b = run(False)
+    for (x0, y0), (x1, y1) in zip(a, b):       # (the kernels' shared-memory atomics make runs agree to ~1e-8, not bit for bit)
+        assert abs(x0 - x1) <= 1e-6 * abs(x0) and abs(y0 - y1) <= 1e-6 * abs(y0)
+    assert n_cached["f"] == 1 and calls["f"] == 6          # 2 iterations x 3 sub-steps on ONE sample
+    assert n_cached["h"] < calls["h"]

@@ -47,13 +47,22 @@
 
 #ifndef XW_EMU
 // spin on mbarrier.try_wait.parity (the instruction itself suspends the thread for a bounded time per probe)
+// The wait is bounded in TIME (about 10 s of SM clock), not in probes: a protocol bug must surface as a CUDA error, never
+// as a hung GPU, and a slow phase (contention, a debugger, throttled clocks) must not be mistaken for one.
 __device__ __forceinline__ void xw_mbar_wait(const void* p, unsigned parity) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(p);
     unsigned ok;
-    do {
+    long long t0 = 0;
+    for (unsigned it = 0;; ++it) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    } while (!ok);
+        if (ok) return;
+        if ((it & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000LL) __trap();
+        }
+    }
 }
 #endif
 

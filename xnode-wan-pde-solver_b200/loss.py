@@ -62,6 +62,8 @@ class loss:
         self.Nb_glob = None
         self.side_effect = True      # reproduce the reference's helper-backward side effects
         self.vcache = None           # (buffer or None, mode): test-function cache, managed by NODE_WAN_solver
+        self.batch_cache = None      # a hotpath.Batch built for this very sample by an earlier sub-step (NODE_WAN_solver)
+        self.last_batch = None       # the Batch the last .u / .v call ran on
         for nm, obj, cls in (("a", a, CoefA), ("b", b, CoefB), ("c", c, CoefC)):
             if not isinstance(obj, cls):
                 raise TypeError("coefficient %s must be a %s produced by func_eval (dense tensors of the reference "
@@ -172,7 +174,11 @@ class loss:
             u_mod = getattr(y_output_u, "_xw_net", None) or self._u_module
             return self._single_time_group(phase, u_mod, v_mod, X, XV, border)
         u_mod, v_mod = self._nets(y_output_u, y_output_v)
-        batch = self._batch(u_mod, X, XV, border)
+        # the Batch holds only sample-dependent values (fp32 views, h, grad_h, f, g, initial scalars): the sub-steps of one
+        # outer iteration run on ONE sample (src/training.py:125-162), so the solver may hand back the one built earlier;
+        # a v-phase call (no boundary) can use a Batch that also carries the boundary part
+        batch = self.batch_cache if self.batch_cache is not None else self._batch(u_mod, X, XV, border)
+        self.last_batch = batch
         spec = u_mod.spec(v_mod)
         dom = domain_spec(self.domain)
         vbuf, vmode = self.vcache if self.vcache is not None else (None, 0)

@@ -131,6 +131,8 @@ class NODE_WAN_solver:
         self._warm = 0                   # completed eager iterations (the first one warms up before graph capture)
         self.reuse_v = True              # cache the test-function values across the sub-steps of one iteration
         self._vc_buf, self._vc_key, self._theta_v_gen = None, None, 0
+        self._coef = None                # (sample token, (h, f, g, a, b, c), hotpath.Batch) of the sample in flight
+        self._load_gen = 0               # bumped whenever new data lands in the graphs' static buffers
         self.best_l = float('inf')
         self.av_l = 0
         self.history = {"loss_u": [], "loss_v": [], "L2": [], "time": []}
@@ -188,13 +190,22 @@ class NODE_WAN_solver:
             else:
                 self._vc_key = (points.uid, self._theta_v_gen)
 
-    def _step(self, phase, domain, batch, vplan=(None, 0)):
+    def _step(self, phase, domain, batch, vplan=(None, 0), token=None):
+        """one sub-step on one batch.  `token` identifies the SAMPLE: the coefficient values on it (h, f, g, grad h, the
+        boundary's initial scalars -- about 60 small torch launches through the user callables) do not depend on the
+        parameters, so the first sub-step on a sample evaluates them and the following ones (same token) reuse them."""
         datau, datav, bdata = batch
         prediction_v = self.v_net(datav)
         prediction_u = self.u_net(datau)
-        h, f, g, a, b, c = func_eval(datau.detach(), bdata.detach(), self.setup, prediction_u, self.func_a,
-                                     self.func_b, self.func_c, self.func_h, self.func_f, self.func_g)
+        cached = self._coef if (token is not None and self._coef is not None and self._coef[0] == token) else None
+        if cached is not None:
+            h, f, g, a, b, c = cached[1]
+        else:
+            h, f, g, a, b, c = func_eval(datau.detach(), bdata.detach(), self.setup, prediction_u, self.func_a,
+                                         self.func_b, self.func_c, self.func_h, self.func_f, self.func_g)
         Loss = loss(self.config['alpha'], a, b, c, h, f, g, self.setup, domain, self.device)
+        if cached is not None and (phase == "v" or cached[2].Nb > 0):
+            Loss.batch_cache = cached[2]
         if self.world > 1:
             Loss.N_glob, Loss.Nb_glob = datau.shape[0] * self.world, bdata.shape[0] * self.world
         vbuf, vmode = vplan
@@ -208,6 +219,8 @@ class NODE_WAN_solver:
             val = Loss.v(prediction_u, prediction_v, datau, datav)
             val.backward()
             self.optimizer_v.step()
+        if token is not None and Loss.last_batch is not None and (cached is None or Loss.last_batch.Nb > cached[2].Nb):
+            self._coef = (token, (h, f, g, a, b, c), Loss.last_batch)
         # hand back a detached scalar: keeping the autograd graph alive would pin the parameters'
         # AccumulateGrad nodes to the stream of this call (and break later CUDA-graph capture)
         out = val.detach()
@@ -225,22 +238,27 @@ class NODE_WAN_solver:
             t._xw_start = getattr(src, "_xw_start", None)
         self._graphs = dict(static=static, graphs={}, outs={}, domain=domain)
 
-    def _graph_for(self, phase, vmode):
-        key = (phase, vmode)
+    def _graph_for(self, phase, vmode, fresh):
+        # `fresh`: first sub-step after new data was copied into the static buffers -> this graph contains the
+        # coefficient evaluation; the graphs of the following sub-steps read its results
+        key = (phase, vmode, fresh)
         if key not in self._graphs["graphs"]:
             g = torch.cuda.CUDAGraph()
             opt = self.optimizer_u if phase == "u" else self.optimizer_v
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
                 opt.zero_grad(set_to_none=True)
+                if fresh:
+                    self._coef = None
                 self._graphs["outs"][key] = self._step(phase, self._graphs["domain"], self._graphs["static"],
-                                                       (self._vc_buf, vmode))
+                                                       (self._vc_buf, vmode), token=("graph", id(self._graphs)))
             self._graphs["graphs"][key] = g
         return key
 
     def _graph_step(self, phase, batch, vmode):
         st = self._graphs["static"]
-        if batch is not self._graphs.get("loaded"):
+        fresh = batch is not self._graphs.get("loaded")
+        if fresh:
             for dst, src in zip(st, batch):
                 if hasattr(dst, "times"):
                     dst.times.copy_(src.times, non_blocking=True)
@@ -248,7 +266,7 @@ class NODE_WAN_solver:
                 else:
                     dst.copy_(src, non_blocking=True)
             self._graphs["loaded"] = batch
-        key = self._graph_for(phase, vmode)
+        key = self._graph_for(phase, vmode, fresh)
         self._graphs["graphs"][key].replay()
         self._last_losses = [self._graphs["outs"][key]]
         return self._graphs["outs"][key]
@@ -265,8 +283,8 @@ class NODE_WAN_solver:
         (self.optimizer_u if phase == "u" else self.optimizer_v).zero_grad()
         val = None
         self._last_losses = []
-        for batch in points:
-            val = self._step(phase, domain, batch, vplan)
+        for k, batch in enumerate(points):
+            val = self._step(phase, domain, batch, vplan, token=(points.uid, k))
             self._last_losses.append(val)
         self._vcache_commit(phase, points)
         if self.use_cuda_graph and single and self._graphs is None and self._warm >= 1:
