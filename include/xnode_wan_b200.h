@@ -148,6 +148,13 @@ int xw_interior_backward_v(const xw_dims* dims, const xw_domain* dom, const floa
                            const double* coefs_dev, float* grad_v, int accumulate,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Adam step of one net on its flat parameter vector (reference: torch.optim.Adam(net.parameters(), lr) with default
+ * betas / eps, /root/reference/src/training.py:103-104, stepped at :138 / :162).  params / exp_avg / exp_avg_sq: fp64 [n];
+ * grad: the flat fp32 gradient the backward entries produce; step: device counter (incremented by the call); params_f32
+ * (optional): receives the updated parameters in fp32 = the theta_u / theta_v argument of the next forward call. */
+int xw_adam_step(double* params, const float* grad, double* exp_avg, double* exp_avg_sq, long long* step,
+                 float* params_f32, int n, double lr, double beta1, double beta2, double eps, void* stream);
+
 /* FP32-FMA micro-benchmark used as the roofline denominator: runs `iters`
  * dependent-chain FFMA blocks on every SM and returns the FLOP count in *flops_host. */
 int xw_fma_probe(int variant, int iters, double* flops_host, void* stream);

@@ -412,3 +412,61 @@ def test_coefficient_values_are_evaluated_once_per_sample(emu):
         assert abs(x0 - x1) <= 1e-6 * abs(x0) and abs(y0 - y1) <= 1e-6 * abs(y0)
     assert n_cached["f"] == 1 and calls["f"] == 6          # 2 iterations x 3 sub-steps on ONE sample
     assert n_cached["h"] < calls["h"]
+
+
+def test_adam_step_kernel_matches_torch_adam(emu):
+    """xw_adam_step on a flat fp64 vector == torch.optim.Adam (defaults) on the same numbers, step after step"""
+    import ctypes as C
+    torch.manual_seed(0)
+    n = 1651
+    p0 = torch.randn(n, dtype=torch.float64)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=0.015)
+    p, m, v = p0.clone(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    step = torch.zeros(1, dtype=torch.int64)
+    p32 = torch.zeros(n, dtype=torch.float32)
+    ptr = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+    for it in range(6):
+        g = (torch.randn(n) * (10.0 ** (it - 3))).float()
+        ref.grad = g.double()
+        opt.step()
+        emu.call("xw_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(step), ptr(p32), n, 0.015, 0.9, 0.999, 1e-8, None)
+        assert int(step) == it + 1
+        assert torch.allclose(p, ref.detach(), rtol=1e-13, atol=1e-15)
+        assert torch.equal(p32, p.float())
+
+
+def test_fused_optimizer_follows_torch_adam(emu):
+    """NODE_WAN_solver(fused_optimizer=True): flat parameter buffers + single-launch Adam; same trajectory as the two
+    torch.optim.Adam of the reference, and state_dict / named_parameters keep the reference's names and shapes"""
+    case = G.load("cube_d3_small_nets")
+
+    def run(fused):
+        torch.manual_seed(9)
+        np.random.seed(9)
+        p = dict(case["params"])
+        p["domain"] = "Hypercube"
+        prob = xw.problems.ex4_1()
+        s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, "cpu", "./",
+                               func_u_sol=prob.func_u_sol, p=2, log_json=False, fused_optimizer=fused)
+        names = [(k, tuple(v.shape)) for k, v in s.u_net.state_dict().items()]
+        dom = s.new_domain()
+        out = []
+        for _ in range(3):
+            pts = xw.Comb_loader(p["N_r"], p["N_b"], dom, "cpu")
+            lu, lv = s.train_iteration(dom, pts)
+            out.append((lu.item(), lv.item()))
+        return out, names, [q.detach().clone() for q in list(s.u_net.parameters()) + list(s.v_net.parameters())], s
+    a, na, pa, sa = run(False)
+    b, nb, pb, sb = run(True)
+    assert sb.fused_optimizer and not sa.fused_optimizer and na == nb
+    for (x0, y0), (x1, y1) in zip(a, b):
+        assert abs(x0 - x1) <= 1e-6 * abs(x0) and abs(y0 - y1) <= 1e-6 * max(abs(y0), 1.0)
+    for x, y in zip(pa, pb):
+        assert torch.allclose(x, y, rtol=1e-6, atol=1e-8)
+    # parameters modified in place behind the optimiser's back are picked up (version counters)
+    with torch.no_grad():
+        for q in sb.u_net.parameters():
+            q.mul_(0.5)
+    th = xw.hotpath.flatten_params(sb.u_net.module.kernel_parameters())
+    assert torch.equal(th, torch.cat([q.detach().reshape(-1) for q in sb.u_net.module.kernel_parameters()]).float())

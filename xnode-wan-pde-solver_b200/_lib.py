@@ -63,6 +63,7 @@ _SIGS = {
                                          C.c_int, _P, C.c_size_t, _P, _P, _P]),
     "xw_interior_backward_v": (C.c_int, [C.POINTER(Dims), C.POINTER(Domain), _P, C.POINTER(Points), _P, C.c_int,
                                          C.c_int, _P, _P, C.c_int, _P, C.c_size_t, _P]),
+    "xw_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     "xw_fma_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), _P]),
     "xw_umma_probe": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
 }

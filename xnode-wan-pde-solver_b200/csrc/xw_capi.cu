@@ -438,6 +438,15 @@ size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
     return std::max(fwd, std::max(bwd_u, bwd_v)) + 1024;
 }
 
+int xw_adam_step(double* params, const float* grad, double* exp_avg, double* exp_avg_sq, long long* step, float* params_f32,
+                 int n, double lr, double beta1, double beta2, double eps, void* stream) {
+    if (!params || !grad || !exp_avg || !exp_avg_sq || !step) return fail("NULL pointer argument");
+    if (n < 1) return fail("empty parameter vector");
+    if (!device()) return fail("no CUDA device");
+    XW_LAUNCH(xw::k_adam_step, 1, 1024, 0, stream, params, grad, exp_avg, exp_avg_sq, step, params_f32, n, lr, beta1, beta2, eps);
+    return XW_CHECK_LAUNCH("k_adam_step");
+}
+
 int xw_xnode_eval(const xw_dims* m, const float* theta_u, const float* x, long long x_sn, const float* times,
                   int L, const float* s0, int n, float* u_out, void* stream) {
     if (check_dims(m)) return 1;

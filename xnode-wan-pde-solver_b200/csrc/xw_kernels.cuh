@@ -676,6 +676,29 @@ XW_GLOBAL void k_reduce_partials(const float* gpart, int nblocks, int P, float* 
 namespace xw {
 
 // =============================================================================================
+// Adam step on one flat parameter vector (reference: torch.optim.Adam with default betas / eps, no weight decay, no
+// amsgrad, src/training.py:103-104,138,162).  ONE CTA (the nets have 1.5-7.7 k parameters): reads the step counter,
+// updates fp64 parameters and moments from the kernels' flat fp32 gradient, refreshes the fp32 copy the kernels read,
+// then bumps the counter -- one launch instead of torch's ~15 foreach launches + 14 gradient casts + the re-packing.
+// =============================================================================================
+XW_GLOBAL void k_adam_step(double* p, const float* g, double* m, double* v, long long* step, float* p32, int n, double lr,
+                           double b1, double b2, double eps) {
+    const long long t = step[0] + 1;
+    const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+    const double step_size = lr / bc1, bc2s = sqrt(bc2);
+    for (int i = XW_TID; i < n; i += XW_BDIM) {
+        const double gi = (double)g[i];
+        const double mi = m[i] + (gi - m[i]) * (1.0 - b1);          // exp_avg.lerp_(grad, 1 - beta1)
+        const double vi = v[i] * b2 + (1.0 - b2) * gi * gi;
+        const double pi = p[i] - step_size * (mi / (sqrt(vi) / bc2s + eps));
+        m[i] = mi; v[i] = vi; p[i] = pi;
+        if (p32) p32[i] = (float)pi;
+    }
+    XW_SYNCTHREADS();
+    if (XW_TID == 0) step[0] = t;
+}
+
+// =============================================================================================
 // weak-form sums from the CACHED test-function values: when the sample and theta_v are unchanged
 // (2nd u-step and the v-step of one outer iteration, src/training.py:125-162) only u, du change, so
 // the v net need not be evaluated again.  One thread per point; time-row-0 threads add the

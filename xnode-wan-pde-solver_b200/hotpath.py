@@ -206,6 +206,12 @@ _WS = _Workspace()
 
 
 def flatten_params(params):
+    """flat fp32 parameter vector in named_parameters() order.  Parameters that live in one flat buffer
+    (optim.FlatParameters) come back without re-packing."""
+    from .optim import flat_of
+    fp = flat_of(list(params))
+    if fp is not None:
+        return fp.theta32()
     return torch.cat([p.detach().reshape(-1) for p in params]).float()
 
 
@@ -278,7 +284,7 @@ class WeakLoss(torch.autograd.Function):
     side effects of the two helper backward calls at src/loss.py:55,60 (`side_effect=True`)."""
 
     @staticmethod
-    def forward(ctx, phase, lib, spec, dom, coef, alpha, batch, group, side_effect, vcache, vmode, nu_params, *params):
+    def forward(ctx, phase, lib, spec, dom, coef, alpha, batch, group, side_effect, vcache, vmode, sink, nu_params, *params):
         pu, pv = params[:nu_params], params[nu_params:]
         theta_u, theta_v = flatten_params(pu), flatten_params(pv)
         _check_dev(theta_u, "parameters", lib)
@@ -293,7 +299,7 @@ class WeakLoss(torch.autograd.Function):
         _allreduce(sums, group)
         I, S, init, bdry, integ = loss_from_sums(sums, batch, dom.V, alpha)
         ctx.phase, ctx.lib, ctx.spec, ctx.dom, ctx.batch, ctx.group = phase, lib, spec, dom, batch, group
-        ctx.nu_params, ctx.side = nu_params, 1.0 if side_effect else 0.0
+        ctx.nu_params, ctx.side, ctx.sink = nu_params, 1.0 if side_effect else 0.0, sink
         ctx.meta = [(tuple(p.shape), p.dtype) for p in params]
         N, L = batch.N_glob, batch.L
         if phase == "u":
@@ -312,7 +318,8 @@ class WeakLoss(torch.autograd.Function):
         lib, spec, batch = ctx.lib, ctx.spec, ctx.batch
         dims = spec.c()
         nup = ctx.nu_params
-        none = (None,) * 12
+        none = (None,) * 13
+        sink = ctx.sink          # flat fp32 gradient buffer of a FusedAdam: the gradient goes there, not into p.grad
         if ctx.phase == "u":
             theta_u, cot_u, k, gb, yh = ctx.saved_tensors
             dev = theta_u.device
@@ -320,12 +327,14 @@ class WeakLoss(torch.autograd.Function):
             ws = _WS.get(dev, lib.workspace_bytes(dims, batch.N, batch.L))
             ks = k.clone()
             ks[0:2] *= go.to(ks.dtype)
-            grad = (gb * go.to(gb.dtype)).contiguous()
+            grad = torch.mul(gb, go.to(gb.dtype), out=sink) if sink is not None else (gb * go.to(gb.dtype)).contiguous()
             _call(lib, "xw_interior_backward_u", dev, C.byref(dims), _ptr(theta_u),
                      C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), batch.L,
                      _ptr(batch.h), _ptr(cot_u), batch.N, _ptr(ks), _ptr(grad), 1, _ptr(ws), ws.numel(), st,
                      _ptr(batch.s0), _ptr(yh))
             _allreduce(grad, ctx.group)
+            if sink is not None:
+                return none + (None,) * len(ctx.meta)
             gl = unflatten_like(grad, ctx.meta[:nup])
             return none + tuple(gl) + (None,) * (len(ctx.meta) - nup)
         theta_v, cot_v, k = ctx.saved_tensors
@@ -334,23 +343,25 @@ class WeakLoss(torch.autograd.Function):
         ws = _WS.get(dev, lib.workspace_bytes(dims, batch.N, batch.L))
         ks = k.clone()
         ks[0:2] *= go.to(ks.dtype)
-        grad = torch.empty(theta_v.numel(), dtype=torch.float32, device=dev)
+        grad = sink if sink is not None else torch.empty(theta_v.numel(), dtype=torch.float32, device=dev)
         cdom, pts = ctx.dom.c(), batch.points()
         _call(lib, "xw_interior_backward_v", dev, C.byref(dims), C.byref(cdom), _ptr(theta_v), C.byref(pts), _ptr(cot_v),
                  batch.N, batch.L, _ptr(ks), _ptr(grad), 0, _ptr(ws), ws.numel(), st)
         _allreduce(grad, ctx.group)
+        if sink is not None:
+            return none + (None,) * len(ctx.meta)
         gl = unflatten_like(grad, ctx.meta[nup:])
         return none + (None,) * nup + tuple(gl)
 
 
 def weak_loss(phase, spec, dom, coef, alpha, batch, u_params, v_params, group=None, side_effect=True, lib=None,
-              vcache=None, vmode=0):
+              vcache=None, vmode=0, grad_sink=None):
     """public functional entry: returns the scalar loss tensor (fp64) with autograd wired to the
     phase's own parameters.  `loss.components` is attached for logging (I, S, init, bdry)."""
     assert phase in ("u", "v")
     lib = lib or _lib.get()
     u_params, v_params = list(u_params), list(v_params)
-    out = WeakLoss.apply(phase, lib, spec, dom, coef, alpha, batch, group, side_effect, vcache, vmode,
+    out = WeakLoss.apply(phase, lib, spec, dom, coef, alpha, batch, group, side_effect, vcache, vmode, grad_sink,
                          len(u_params), *(u_params + v_params))
     out.components = getattr(out.grad_fn, "components", None)
     return out

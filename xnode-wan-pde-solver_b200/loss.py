@@ -62,6 +62,7 @@ class loss:
         self.Nb_glob = None
         self.side_effect = True      # reproduce the reference's helper-backward side effects
         self.vcache = None           # (buffer or None, mode): test-function cache, managed by NODE_WAN_solver
+        self.grad_sink = None        # flat fp32 gradient buffer of an optim.FusedAdam (NODE_WAN_solver), else p.grad is filled
         self.batch_cache = None      # a hotpath.Batch built for this very sample by an earlier sub-step (NODE_WAN_solver)
         self.last_batch = None       # the Batch the last .u / .v call ran on
         for nm, obj, cls in (("a", a, CoefA), ("b", b, CoefB), ("c", c, CoefC)):
@@ -186,7 +187,7 @@ class loss:
             raise RuntimeError("vcache mode without a buffer")
         return hotpath.weak_loss(phase, spec, dom, self._coef(X.device), float(self.alpha), batch,
                                  u_mod.kernel_parameters(), v_mod.flat_parameters(), group=self.group,
-                                 side_effect=self.side_effect, vcache=vbuf, vmode=vmode)
+                                 side_effect=self.side_effect, vcache=vbuf, vmode=vmode, grad_sink=self.grad_sink)
 
     # ------------------------------------------------------------------------------ reference API
     _u_module = None

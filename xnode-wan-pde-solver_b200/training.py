@@ -79,7 +79,7 @@ class NODE_WAN_solver:
 
     def __init__(self, params: dict, func_a, func_b, func_c, func_h, func_f, func_g, device, path, stop=None,
                  func_u_sol=None, p: float = 1, log_json: bool = True, use_cuda_graph: bool = False,
-                 sample_on_device: bool = False, collapsed_layout: bool = False):
+                 sample_on_device: bool = False, collapsed_layout: bool = False, fused_optimizer=None):
         self.params = params
         self.func_a, self.func_b, self.func_c = func_a, func_b, func_c
         self.func_h, self.func_f, self.func_g = func_h, func_f, func_g
@@ -109,8 +109,19 @@ class NODE_WAN_solver:
         self.u_net.apply(init_weights)
         self.v_net.apply(init_weights)
         cap = self.use_cuda_graph        # step counters on the device so that Adam can live inside a CUDA graph
-        self.optimizer_u = torch.optim.Adam(self.u_net.parameters(), lr=self.config['u_rate'], capturable=cap)
-        self.optimizer_v = torch.optim.Adam(self.v_net.parameters(), lr=self.config['v_rate'], capturable=cap)
+        # fused_optimizer (default: on with CUDA-graph replay): one flat fp64 buffer per net + a single-launch Adam that
+        # consumes the kernels' flat fp32 gradient (optim.py); off = two torch.optim.Adam as the reference
+        self.fused_optimizer = bool(self.use_cuda_graph if fused_optimizer is None else fused_optimizer)
+        if self.fused_optimizer and self.config['u_layers'] > 1:
+            from . import hotpath as _hp
+            from .optim import FlatParameters, FusedAdam
+            lib = _hp._lib.get()
+            self.optimizer_u = FusedAdam(FlatParameters(self.u_net.module.kernel_parameters()), self.config['u_rate'], lib)
+            self.optimizer_v = FusedAdam(FlatParameters(self.v_net.module.flat_parameters()), self.config['v_rate'], lib)
+        else:
+            self.fused_optimizer = False
+            self.optimizer_u = torch.optim.Adam(self.u_net.parameters(), lr=self.config['u_rate'], capturable=cap)
+            self.optimizer_v = torch.optim.Adam(self.v_net.parameters(), lr=self.config['v_rate'], capturable=cap)
         # one process per GPU: N_r / N_b are GLOBAL counts, every rank samples its own shard; identical
         # seeds give identical initial weights, all-reduced sums/gradients keep the replicas identical
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
@@ -121,6 +132,9 @@ class NODE_WAN_solver:
             with torch.no_grad():
                 for q in list(self.u_net.parameters()) + list(self.v_net.parameters()):
                     torch.distributed.broadcast(q.data, src=0)
+                if self.fused_optimizer:         # (.data writes do not bump version counters: refresh the fp32 copies)
+                    for opt in (self.optimizer_u, self.optimizer_v):
+                        opt.flat.f32.copy_(opt.flat.flat)
             # ... and the shards must DIFFER: with equal seeds every rank would draw the same paths.  Decorrelate the
             # sampling streams (torch CPU + CUDA generators and numpy) per rank, derived from rank 0's current state.
             base = torch.tensor([int(torch.initial_seed()) % (2 ** 31)], dtype=torch.int64, device=self.device)
@@ -210,6 +224,8 @@ class NODE_WAN_solver:
             Loss.N_glob, Loss.Nb_glob = datau.shape[0] * self.world, bdata.shape[0] * self.world
         vbuf, vmode = vplan
         Loss.vcache = (vbuf, vmode)
+        if self.fused_optimizer:
+            Loss.grad_sink = (self.optimizer_u if phase == "u" else self.optimizer_v).grad32
         Loss._u_module = self.u_net.module
         if phase == "u":
             val = Loss.u(prediction_u, prediction_v, self.u_net, datau, datav, bdata)
