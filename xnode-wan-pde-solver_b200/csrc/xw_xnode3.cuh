@@ -11,7 +11,7 @@
 //                  delta-tile; carries the adjoint (zbar, qbar) from step to step;
 //   G (gradient) : lane = (path group, task slot); 55 FFMA2 per task into register-resident 10 x 11 accumulators.
 // Hand-offs are shared-memory mbarriers (two r-tiles and two delta-tiles per triple, phase parity per use).  Registers:
-// the CTA is compiled at 168 per thread (384 threads); R takes 200 and G gives back to 144 with setmaxnreg.
+// the CTA is launched at 168 per thread (384 threads); G gives back to 144 and R takes 192 with setmaxnreg (the sum must stay 3 x 168).
 // The forward sweep (state history) is NOT part of this kernel: the interior history comes from the interior forward
 // kernel, the boundary history from a k_xnode2_fwd<.,0> launch in front of it.
 #pragma once
@@ -192,7 +192,7 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kThreads, 1) k_xnode3_bwd(Args a) {
         }
     } else if (role == 1) {
         // ================================================================================== R: reverse sweep
-        XW_SETMAXNREG_INC(200);
+        XW_SETMAXNREG_INC(192);     // 168 (F) + 192 (R) + 144 (G) = 3 x 168: the pool is what the CTA was launched with
         x2::CoreRegs cr;
         x2::load_core_from(sm + Sm::WST, sm + Sm::BS, cr);
         const float bo = sm[Sm::BO];
