@@ -304,7 +304,7 @@ int x2_plan_bwd(const xw_dims* m, int n, int L, X2BwdPlan* p) {
     if (p->lsmem > dv->smem_optin)
         return fail("xnode lift backward needs %zu B shared memory per CTA (> %zu): dim too large", p->lsmem, dv->smem_optin);
     p->lgrid = grid_for(n, p->lblock, ctas_per_sm_for(p->lsmem, 4));
-    p->hist_b = align_up((size_t)L * xw::x2::kZQ * (p->three ? (size_t)n : (size_t)p->grid * cpaths) * 4, 256);
+    p->hist_b = align_up((size_t)L * (xw::x2::kZQ + xw::x2::HH * (stages_of(m->solver) - 1)) * (p->three ? (size_t)n : (size_t)p->grid * cpaths) * 4, 256);
     p->pp_b = align_up((size_t)xw::x2::kPerPath * n * 4, 256);
     p->pa_b = align_up((size_t)p->grid * xw::x2::kPartA * 4, 256);
     p->pb_b = align_up((size_t)p->lgrid * P * 4, 256);
@@ -404,7 +404,7 @@ int xw_theta_u_size(const xw_dims* m) { return m ? xw::ULayout(m->d, m->H, m->hh
 int xw_theta_v_size(const xw_dims* m) { return m ? xw::VLayout(m->d, m->Hv).size : -1; }
 size_t xw_yhist_floats(const xw_dims* m, int n, int L) {      // generation 2: (z[10], q) per grid point; generation 1: y[H]
     if (!m) return 0;
-    return (size_t)L * (use_x2(m) ? xw::x2::kZQ : kH) * n;
+    return (size_t)L * (use_x2(m) ? xw::x2::kZQ + xw::x2::HH * (stages_of(m->solver) - 1) : kH) * n;
 }
 int xw_last_xnode_impl(void) { return g_last_xnode_impl; }
 int xw_last_vnet_impl(void) { return g_last_vnet_fwd | (g_last_vnet_bwd << 4); }

@@ -50,7 +50,8 @@ constexpr int kCW = 4;                           // compute warps per CTA (= gra
 constexpr int kBwdThreads = 64 * kCW;
 constexpr int kPartA = 232;                      // [S: 10 x 11][M: 10 x 11][dv 10][de 1] (+1 pad)
 constexpr int kPerPath = 31;                     // a0[10], a0t[10], zbar0[10], qbar0
-constexpr int kZQ = 11;                          // history row: z[10], q
+constexpr int kZQ = 11;                          // history row: z[10], q, then the inputs z_in of stages 1..S-1 of the step
+template <int SOLVER> constexpr int zq_row() { return kZQ + HH * (Tableau<SOLVER>::S - 1); }   // floats per grid point
 
 XW_DEV void stage_reduced(float* sr, const float* su) {
     for (int i = XW_TID; i < R::size; i += XW_BDIM) sr[i] = 0.f;
@@ -241,7 +242,8 @@ XW_DEV void stage_input(const float* su, const float (&ax)[HH], float t, const f
 // one explicit RK step of the reduced state (z, q), recording stage internals in rec[s]
 template <int SOLVER, class Rec>
 XW_DEV void rk_step_red(const CoreRegs& cr, const float* su, const float* sr, const float (&ax)[HH], float t0, float dt,
-                        int nsh, float (&z)[HH], float& q, Rec (&rec)[Tableau<SOLVER>::S]) {
+                        int nsh, float (&z)[HH], float& q, Rec (&rec)[Tableau<SOLVER>::S], float* zin_out = nullptr,
+                        long long zin_stride = 0) {
     using T = Tableau<SOLVER>;
     float kap[T::S][HH];
     float pq = 0.f;
@@ -258,6 +260,10 @@ XW_DEV void rk_step_red(const CoreRegs& cr, const float* su, const float* sr, co
 #pragma unroll
                 for (int i = 0; i < HH; ++i) zin[i] = fmaf(cd, kap[r][i], zin[i]);
             }
+        }
+        if (s > 0 && zin_out) {                 // stage inputs kept for the backward (it then needs no unrecorded pass)
+#pragma unroll
+            for (int i = 0; i < HH; ++i) zin_out[(long long)((s - 1) * HH + i) * zin_stride] = zin[i];
         }
         float a[HH], tau[HH];
         stage_input(su, ax, fmaf(T::c(s), dt, t0), zin, a);
@@ -340,6 +346,7 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kFwdThreads, 1) k_xnode2_fwd(FwdArgs a) {
     const long long nthr = (long long)XW_GDIM * XW_BDIM;
     const long long gtid = (long long)XW_BID * XW_BDIM + XW_TID;
     const int L = a.L, nsh = a.nsh;
+    constexpr int ROW = zq_row<SOLVER>();
     const float bo = su[S::BO];
     double init_acc = 0.0;
     for (long long n = gtid; n < a.n; n += nthr) {
@@ -362,7 +369,8 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kFwdThreads, 1) k_xnode2_fwd(FwdArgs a) {
                 BitsRec rec[T::S];
 #pragma unroll
                 for (int s = 0; s < T::S; ++s) rec[s].m.clear();
-                rk_step_red<SOLVER>(cr, su, sr, ax, t0, dt, nsh, z, q, rec);
+                rk_step_red<SOLVER>(cr, su, sr, ax, t0, dt, nsh, z, q, rec,
+                                    a.zq ? a.zq + ((long long)l * ROW + kZQ) * a.n + n : nullptr, a.n);
 #pragma unroll
                 for (int s = 0; s < T::S; ++s) {
                     float* hp = a.rec + ((long long)(l * T::S + s) * kRecWords2) * nthr + gtid;
@@ -375,12 +383,13 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kFwdThreads, 1) k_xnode2_fwd(FwdArgs a) {
                 }
             } else {
                 NoRec rec[T::S];
-                rk_step_red<SOLVER>(cr, su, sr, ax, t0, dt, nsh, z, q, rec);
+                rk_step_red<SOLVER>(cr, su, sr, ax, t0, dt, nsh, z, q, rec,
+                                    a.zq ? a.zq + ((long long)l * ROW + kZQ) * a.n + n : nullptr, a.n);
             }
             if (a.zq) {
 #pragma unroll
-                for (int i = 0; i < HH; ++i) a.zq[((long long)(l + 1) * kZQ + i) * a.n + n] = z[i];
-                a.zq[((long long)(l + 1) * kZQ + HH) * a.n + n] = q;
+                for (int i = 0; i < HH; ++i) a.zq[((long long)(l + 1) * ROW + i) * a.n + n] = z[i];
+                a.zq[((long long)(l + 1) * ROW + HH) * a.n + n] = q;
             }
             if (a.u_out) a.u_out[n * L + l + 1] = q + bo;
         }
@@ -479,7 +488,7 @@ struct BwdArgs {
     const float* hloss;          // MODE 0: func_h values of loss.init
     const float* zq;             // optional: [L][kZQ][n] reduced state history written by the forward kernel
     double gscale;               // MODE 1
-    float* hist;                 // [L][kZQ][gridDim*32*kCW] scratch, used when zq == nullptr
+    float* hist;                 // [L][zq_row][gridDim*32*kCW] scratch, used when zq == nullptr
     float* perpath;              // [kPerPath][n]
     float* partA;                // [gridDim][kPartA]
     double* sums;
@@ -508,6 +517,7 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kBwdThreads, 1) k_xnode2_bwd(BwdArgs a) {
     float* dtile = rt0 + 2 * kTile;
     const int bar_full = 1 + 2 * pair, bar_empty = 2 + 2 * pair;
     const int L = a.L, nsh = a.nsh;
+    constexpr int ROW = zq_row<SOLVER>();
     const int cpaths = 32 * kCW;
     const int nchunks = (a.n + cpaths - 1) / cpaths;
     int my_chunks = 0;
@@ -549,8 +559,8 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kBwdThreads, 1) k_xnode2_bwd(BwdArgs a) {
                     NoRec rec[T::S];
                     rk_step_red<SOLVER>(cr, su, sr, ax, st[l], st[l + 1] - st[l], nsh, z, q, rec);
 #pragma unroll
-                    for (int i = 0; i < HH; ++i) hw[((long long)(l + 1) * kZQ + i) * hstr] = z[i];
-                    hw[((long long)(l + 1) * kZQ + HH) * hstr] = q;
+                    for (int i = 0; i < HH; ++i) hw[((long long)(l + 1) * ROW + i) * hstr] = z[i];
+                    hw[((long long)(l + 1) * ROW + HH) * hstr] = q;
                 }
             }
             // cotangent of u[n, l]
@@ -569,13 +579,13 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kBwdThreads, 1) k_xnode2_bwd(BwdArgs a) {
             float zb[HH], a0[HH], a0t[HH];
 #pragma unroll
             for (int i = 0; i < HH; ++i) { zb[i] = 0.f; a0[i] = 0.f; a0t[i] = 0.f; }
-            float qb = cot_at(L - 1, hbase[((long long)(L - 1) * kZQ + HH) * hstr] + bo);
+            float qb = cot_at(L - 1, hbase[((long long)(L - 1) * ROW + HH) * hstr] + bo);
             for (int l = L - 2; l >= 0; --l) {
                 const float t0 = st[l], dt = st[l + 1] - st[l];
                 float zl[HH];
 #pragma unroll
-                for (int i = 0; i < HH; ++i) zl[i] = hbase[((long long)l * kZQ + i) * hstr];
-                const float ql = hbase[((long long)l * kZQ + HH) * hstr];
+                for (int i = 0; i < HH; ++i) zl[i] = hbase[((long long)l * ROW + i) * hstr];
+                const float ql = hbase[((long long)l * ROW + HH) * hstr];
                 // stage inputs zin[s] (forward through the stages; only the LAST stage records its internals: earlier
                 // stages are re-evaluated right before their own reverse -> 2S-1 evaluations of the layer stack)
                 float zin[T::S][HH];

@@ -52,7 +52,7 @@ struct Args {
     const float* cot;            // MODE 0: cot_u[n*L]   MODE 1: g[n*L]
     const double* coefs;         // MODE 0: device k0,k1,k2
     const float* hloss;          // MODE 0: func_h values of loss.init
-    const float* zq;             // [L][kZQ][n] reduced state history (required)
+    const float* zq;             // [L][zq_row<SOLVER>][n] reduced state history incl. stage inputs (required)
     double gscale;               // MODE 1
     float* perpath;              // [x2::kPerPath][n]
     float* partA;                // [gridDim][kPartA]
@@ -120,6 +120,7 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kThreads, 1) k_xnode3_bwd(Args a) {
     unsigned long long* mb = mbar + tri * 8;
     unsigned long long *full_r = mb, *empty_r = mb + 2, *full_d = mb + 4, *empty_d = mb + 6;
     const int L = a.L, nsh = a.nsh;
+    constexpr int ROW = x2::zq_row<SOLVER>();
     const int cpaths = 32 * kTriples;
     const int nchunks = (a.n + cpaths - 1) / cpaths;
     double bd_acc = 0.0;
@@ -145,35 +146,15 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kThreads, 1) k_xnode3_bwd(Args a) {
             const float* hb = a.zq + n;
             for (int l = L - 2; l >= 0; --l) {
                 const float t0 = st[l], dt = st[l + 1] - st[l];
-                float zl[HH];
-#pragma unroll
-                for (int i = 0; i < HH; ++i) zl[i] = hb[((long long)l * kZQ + i) * a.n];
-                // stage inputs: stages before the last one are evaluated (unrecorded) for their kappa only
+                // stage inputs straight from the history the forward kernel kept (z_l and the z_in of stages 1..S-1):
+                // no unrecorded evaluation here
                 float zin[T::S][HH];
-                {
-                    float kap[T::S][HH];
 #pragma unroll
-                    for (int s = 0; s < T::S; ++s) {
+                for (int i = 0; i < HH; ++i) zin[0][i] = hb[((long long)l * ROW + i) * a.n];
 #pragma unroll
-                        for (int i = 0; i < HH; ++i) zin[s][i] = zl[i];
+                for (int s = 1; s < T::S; ++s)
 #pragma unroll
-                        for (int r = 0; r < s; ++r) {
-                            const float cc = T::a(s, r);
-                            if (cc != 0.f) {
-                                const float cd = cc * dt;
-#pragma unroll
-                                for (int i = 0; i < HH; ++i) zin[s][i] = fmaf(cd, kap[r][i], zin[s][i]);
-                            }
-                        }
-                        if (s + 1 < T::S) {
-                            float av[HH], tau[HH];
-                            x2::NoRec none;
-                            x2::stage_input_from(sm + Sm::WT, ax, fmaf(T::c(s), dt, t0), zin[s], av);
-                            x2::core_fwd(cr, av, nsh, tau, none);
-                            x2::kappa_of(sr, tau, kap[s]);
-                        }
-                    }
-                }
+                    for (int i = 0; i < HH; ++i) zin[s][i] = hb[((long long)l * ROW + kZQ + (s - 1) * HH + i) * a.n];
                 // recorded evaluations in the order the reverse sweep consumes them: last stage first
 #pragma unroll
                 for (int s = T::S - 1; s >= 0; --s) {
@@ -221,10 +202,10 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kThreads, 1) k_xnode3_bwd(Args a) {
             float zb[HH], a0[HH], a0t[HH];
 #pragma unroll
             for (int i = 0; i < HH; ++i) { zb[i] = 0.f; a0[i] = 0.f; a0t[i] = 0.f; }
-            float qb = cot_at(L - 1, hb[((long long)(L - 1) * kZQ + HH) * a.n] + bo);
+            float qb = cot_at(L - 1, hb[((long long)(L - 1) * ROW + HH) * a.n] + bo);
             for (int l = L - 2; l >= 0; --l) {
                 const float t0 = st[l], dt = st[l + 1] - st[l];
-                const float ql = hb[((long long)l * kZQ + HH) * a.n];
+                const float ql = hb[((long long)l * ROW + HH) * a.n];
                 float kbar[T::S][HH], zacc[HH];
 #pragma unroll
                 for (int s = 0; s < T::S; ++s)

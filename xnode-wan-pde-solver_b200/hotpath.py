@@ -157,6 +157,22 @@ class Batch:
                            self.xv.data_ptr() + 4 * self.xv_off, self.xv_sn, self.xv_sl)
 
 
+_BATCH_VALUE_FIELDS = ("times", "tv", "h", "s0", "grad_h", "f", "times_b", "sb", "g")
+
+
+def copy_batch_values_(dst, src):
+    """copy the sample-dependent VALUES of `src` into the tensors of `dst` (same shapes): used to keep one persistent
+    home for them across CUDA graphs (training.py); path tensors (x, xv, xb) are views of the caller's inputs"""
+    for name in _BATCH_VALUE_FIELDS:
+        a, b = getattr(dst, name), getattr(src, name)
+        if a is None or b is None:
+            if (a is None) != (b is None):
+                raise RuntimeError("batch structure changed (%s)" % name)
+            continue
+        if a.data_ptr() != b.data_ptr():
+            a.copy_(b)
+
+
 def batch_from_reference_layout(X, XV, BX=None):
     """X, XV [N,L,C], BX [Nb,Lb,C] (any float dtype) -> Batch (fp32 views, no repack when already fp32)"""
     Xf, XVf = as_f32(X), as_f32(XV)

@@ -212,11 +212,24 @@ class NODE_WAN_solver:
         prediction_v = self.v_net(datav)
         prediction_u = self.u_net(datau)
         cached = self._coef if (token is not None and self._coef is not None and self._coef[0] == token) else None
+        persist = self._graphs.get("persist") if (self._graphs is not None and token is not None and token[0] == "graph") else None
         if cached is not None:
             h, f, g, a, b, c = cached[1]
         else:
             h, f, g, a, b, c = func_eval(datau.detach(), bdata.detach(), self.setup, prediction_u, self.func_a,
                                          self.func_b, self.func_c, self.func_h, self.func_f, self.func_g)
+            if persist is not None:
+                # captured "fresh" graph: the sample-dependent values go to their PERSISTENT home (allocated eagerly in
+                # _capture), which every other captured graph reads -- whichever fresh graph ran last filled it
+                (ph, pf, pg, _, _, _), pb = persist
+                tmp = loss(self.config['alpha'], a, b, c, h, f, g, self.setup, domain, self.device)
+                nb = tmp._batch(self.u_net.module, datau, datav, bdata)
+                ph.copy_(h); pf.copy_(f); pg.copy_(g)
+                from . import hotpath as _hp
+                _hp.copy_batch_values_(pb, nb)
+                h, f, g = ph, pf, pg
+                cached = (token, (h, f, g, a, b, c), pb)
+                self._coef = cached
         Loss = loss(self.config['alpha'], a, b, c, h, f, g, self.setup, domain, self.device)
         if cached is not None and (phase == "v" or cached[2].Nb > 0):
             Loss.batch_cache = cached[2]
@@ -252,7 +265,15 @@ class NODE_WAN_solver:
         static = tuple(t.clone() for t in batch)
         for t, src in zip(static, batch):
             t._xw_start = getattr(src, "_xw_start", None)
-        self._graphs = dict(static=static, graphs={}, outs={}, domain=domain)
+        # persistent home of the sample-dependent values (coefficient values + packed batch) on the static copies,
+        # allocated OUTSIDE any graph: "fresh" graphs write into it, the others read it (see _step)
+        h, f, g, a, b, c = func_eval(static[0].detach(), static[2].detach(), self.setup, None, self.func_a, self.func_b,
+                                     self.func_c, self.func_h, self.func_f, self.func_g)
+        tmp = loss(self.config['alpha'], a, b, c, h, f, g, self.setup, domain, self.device)
+        if self.world > 1:
+            tmp.N_glob, tmp.Nb_glob = static[0].shape[0] * self.world, static[2].shape[0] * self.world
+        pb = tmp._batch(self.u_net.module, static[0], static[1], static[2])
+        self._graphs = dict(static=static, graphs={}, outs={}, domain=domain, persist=((h, f, g, a, b, c), pb))
 
     def _graph_for(self, phase, vmode, fresh):
         # `fresh`: first sub-step after new data was copied into the static buffers -> this graph contains the
