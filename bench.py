@@ -350,7 +350,8 @@ def run_ours(args):
     prof = hp.PROFILE
     hp.PROFILE = None
     clk = clocks.stop() if rank == 0 else None
-    xnode_impl = lib.cdll.xw_last_xnode_impl()
+    xnode_code = lib.cdll.xw_last_xnode_impl()
+    xnode_impl = (xnode_code >> 4) & 15 or (xnode_code & 15)       # name the step after its BACKWARD kernels
     vimpl = lib.cdll.xw_last_vnet_impl()
     # per-entry-point device time (CUDA events on the launching stream, inside the timed region)
     per_call = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in prof.items()}

@@ -76,8 +76,9 @@ int xw_theta_u_size(const xw_dims* dims);
 int xw_theta_v_size(const xw_dims* dims);
 /* floats in the optional state-history / test-function cache buffers of xw_interior_forward */
 size_t xw_yhist_floats(const xw_dims* dims, int n, int L);
-/* which generation of the XNODE kernels the last XNODE launch of this process used (1 or 2; 0 = none yet):
- * lets tests and bench.py name the kernel that actually ran instead of assuming it */
+/* which generation of the XNODE kernels this process launched last: bits 0-3 = the last XNODE launch of any kind,
+ * bits 4-7 = the last BACKWARD launch (1 = one thread per path, 2 = reduced state / 2 warp roles, 3 = 3 warp roles;
+ * 0 = none yet): lets tests and bench.py name the kernel that actually ran instead of assuming it */
 int xw_last_xnode_impl(void);
 /* same for the test-function net: bits 0-3 = last forward launch, bits 4-7 = last backward launch;
  * 1 = one thread per point (FP32), 2 = FP32 tile engine, 3 = tcgen05 (3xTF32) */

@@ -41,9 +41,8 @@ def run(graph, fused, cache, iters=4, u_rate=None, v_nocache=False):
     return out
 
 
-for tag, kw in (("u_rate=0", dict(u_rate=0.0)), ("v_nocache", dict(v_nocache=True))):
-    base = run(False, False, False, **{k: v for k, v in kw.items() if k == "u_rate"})
-    r = run(True, False, True, **kw)
-    print(tag)
-    for it, (x, y) in enumerate(zip(r, base)):
-        print("  it", it, [" ".join("%.1e" % (abs(a - b) / max(abs(b), 1e-30)) for a, b in zip(p, q)) for p, q in zip(x, y)], flush=True)
+base = run(False, True, True, iters=10)
+for rep in range(3):
+    for graph in (False, True):
+        r = run(graph, True, True, iters=10)
+        print("rep", rep, "graph=%d vs eager" % graph, " | ".join(" ".join("%.0e" % (abs(a[0] - b[0]) / max(abs(b[0]), 1.0)) for a, b in zip(x, y)) for x, y in zip(r, base)), flush=True)

@@ -268,7 +268,8 @@ bool use_x2(const xw_dims* m) {
     const char* e = getenv("XW_XNODE_IMPL");
     return !(e && strcmp(e, "v1") == 0);
 }
-int g_last_xnode_impl = 0;       // 1 / 2: which generation the last XNODE launch used
+int g_last_xnode_impl = 0;       // 1 / 2 / 3: which generation the last XNODE launch used
+int g_last_xnode_bwd = 0;        // same for the last BACKWARD launch (a forward launch follows it in every step)
 int g_last_vnet_fwd = 0, g_last_vnet_bwd = 0;   // 1 points, 2 FP32 tile engine, 3 tcgen05 (last v-net forward / backward launch)
 
 size_t x2_smem_fwd(int d, int L) {
@@ -361,7 +362,7 @@ int x2_run_bwd(const xw_dims* m, xw::x2::BwdArgs a, const X2BwdPlan& p, void* wo
     }
         switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
 #undef XW_CASE
-        g_last_xnode_impl = 3;
+        g_last_xnode_impl = 3; g_last_xnode_bwd = 3;
         if (XW_CHECK_LAUNCH("k_xnode3_bwd")) return 1;
     } else {
 #define XW_CASE(SOLV)                                                                       \
@@ -372,7 +373,7 @@ int x2_run_bwd(const xw_dims* m, xw::x2::BwdArgs a, const X2BwdPlan& p, void* wo
     }
         switch (m->solver) { XW_CASE(0) XW_CASE(1) XW_CASE(2) }
 #undef XW_CASE
-        g_last_xnode_impl = 2;
+        g_last_xnode_impl = 2; g_last_xnode_bwd = 2;
         if (XW_CHECK_LAUNCH("k_xnode2_bwd")) return 1;
     }
     if (!grad_u) return 0;
@@ -406,7 +407,7 @@ size_t xw_yhist_floats(const xw_dims* m, int n, int L) {      // generation 2: (
     if (!m) return 0;
     return (size_t)L * (use_x2(m) ? xw::x2::kZQ + xw::x2::HH * (stages_of(m->solver) - 1) : kH) * n;
 }
-int xw_last_xnode_impl(void) { return g_last_xnode_impl; }
+int xw_last_xnode_impl(void) { return g_last_xnode_impl | (g_last_xnode_bwd << 4); }
 int xw_last_vnet_impl(void) { return g_last_vnet_fwd | (g_last_vnet_bwd << 4); }
 size_t xw_vcache_floats(const xw_dims* m, int n, int L) { return m ? (size_t)4 * n * L + (size_t)n * m->d : 0; }
 
@@ -611,7 +612,7 @@ int xw_boundary_u(const xw_dims* m, const float* theta_u, const float* xb, long 
         q.theta = theta_u; q.x = xb; q.x_sn = xb_sn; q.times = times_b; q.s0 = s0b; q.cot = g; q.gscale = gscale; q.sums = sums;
         return x2_run_bwd<1>(m, q, p2, workspace, grad_u, accumulate, stream);
     }
-    g_last_xnode_impl = 1;
+    g_last_xnode_impl = 1; g_last_xnode_bwd = 1;
     XnodeBwdPlan p;
     if (plan_xnode_bwd(m, nb, Lb, &p)) return 1;
     if (workspace_bytes < p.hist_bytes + p.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, p.hist_bytes + p.part_bytes);
@@ -642,7 +643,7 @@ int xw_interior_backward_u(const xw_dims* m, const float* theta_u, const float* 
         q.coefs = coefs_dev; q.zq = y_hist;
         return x2_run_bwd<0>(m, q, p2, workspace, grad_u, accumulate, stream);
     }
-    g_last_xnode_impl = 1;
+    g_last_xnode_impl = 1; g_last_xnode_bwd = 1;
     XnodeBwdPlan p;
     if (plan_xnode_bwd(m, n, L, &p)) return 1;
     if (workspace_bytes < p.hist_bytes + p.part_bytes) return fail("workspace too small: %zu < %zu", workspace_bytes, p.hist_bytes + p.part_bytes);
