@@ -222,3 +222,21 @@ def test_larger_later_batch_reallocates_the_test_function_cache():
     n0 = s._vc_buf.numel()
     lu, lv = s.train_iteration(dom, big)
     assert s._vc_buf.numel() > n0 and np.isfinite(lu.item()) and np.isfinite(lv.item())
+
+
+def test_prefetched_sample_equals_synchronous_copy():
+    """Comb_loader.prefetch(): the H2D copy on the copy stream, consumed after an event wait, gives the same numbers"""
+    torch.manual_seed(6)
+    np.random.seed(6)
+    s, _ = _rand_case(5, 2048, 1024, 6)
+    dom = s.new_domain()
+    cpu = xw.Comb_loader(2048, 1024, dom, "cpu")
+    host = [t.pin_memory() for t in (cpu.interioru, cpu.interiorv, cpu.boundary)]
+    vals = []
+    for pre in (False, True):
+        pts = xw.Comb_loader.from_tensors(host[0], host[1], host[2], DEV)
+        if pre:
+            pts.prefetch()
+        X, XV, BX = pts[0]
+        vals.append(_loss_and_grads(s, dom, X, XV, BX, "u")[0].item())
+    assert vals[0] == vals[1] or abs(vals[0] - vals[1]) <= 1e-9 * abs(vals[0])

@@ -101,6 +101,13 @@ class Hypercube:
 
 
 _LOADER_UID = [0]
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = torch.cuda.Stream(dev)
+    return _COPY_STREAMS[dev]
 
 
 class Comb_loader:
@@ -136,6 +143,23 @@ class Comb_loader:
         self._cache = {}
         return self
 
+    def prefetch(self, stream=None):
+        """start the host->device copy of this sample on a side stream NOW (pinned host tensors: truly asynchronous), so
+        that it overlaps the previous sample's kernels; the first access makes the consumer's stream wait for it.
+        Returns self.  (The reference copies synchronously at access time, src/dataset.py:321.)"""
+        dev = torch.device(self.device)
+        if dev.type != "cuda" or isinstance(self.interioru, list) or 0 in self._cache:
+            return self
+        stream = stream or _copy_stream(dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))        # the tensors being replaced may still be in use
+        with torch.cuda.stream(stream):
+            trip = (self._dev(self.interioru, "h"), self._dev(self.interiorv, "h"), self._dev(self.boundary, "h"))
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._cache[0] = trip
+        self._pending = (ev, stream, trip)
+        return self
+
     def __len__(self):
         return len(self.interioru) if isinstance(self.interioru, list) else 1
 
@@ -148,6 +172,15 @@ class Comb_loader:
         is_list = isinstance(self.interioru, list)
         if not is_list and idx != 0:
             raise IndexError
+        pend = getattr(self, "_pending", None)
+        if pend is not None:                    # a prefetch is in flight: order the consumer after it, once
+            ev, stream, trip = pend
+            cur = torch.cuda.current_stream(torch.device(self.device))
+            cur.wait_event(ev)
+            for t in trip:                      # the caching allocator must not recycle them while `cur` still reads
+                for part in ((t.times, t.x) if hasattr(t, "times") else (t,)):
+                    part.record_stream(cur)
+            self._pending = None
         if idx not in self._cache:      # one H2D per sample (the reference re-copies on every access)
             if is_list:
                 if idx >= min(len(self.interioru), len(self.boundary)):
