@@ -157,7 +157,8 @@ def config_of(args):
 XNODE_NAMES = {1: ("k_xnode_fwd", "k_xnode_bwd"), 2: ("k_xnode2_fwd", "k_xnode2_bwd (+ k_xnode2_lift, k_xnode2_finish)"),
                3: ("k_xnode2_fwd", "k_xnode3_bwd (+ k_xnode2_fwd<history> in front of the boundary pass, k_xnode2_lift, k_xnode2_finish)")}
 VNET_FWD = {1: "k_vnet_points", 2: "k_vnet_tile_fwd", 3: "k_vnet_tc_fwd (+ k_vnet_tc_row0)"}
-VNET_BWD = {1: "k_vnet_bwd", 2: "k_vnet_tile_bwd", 3: "k_vnet_tc_bwd3"}
+VNET_BWD = {1: "k_vnet_bwd", 2: "k_vnet_tile_bwd", 3: "k_vnet_tc_bwd3",
+            4: "k_vnet_tc_bwd3 on the virtual net of input width Hv (+ k_vv_prep, k_vv_dwx, k_vv_finish)"}
 
 
 def make_solver(xw, d, n_glob, dev, **kw):
@@ -442,7 +443,7 @@ def run_ours(args):
     groups = {
         # kernel (named after what actually launched: xw_last_xnode_impl / xw_last_vnet_impl) -> (C-ABI entries, bound)
         xb: (["xw_boundary_u", "xw_interior_backward_u"], "fp32_fma"),
-        vb: (["xw_interior_backward_v"], "tensor" if (vimpl >> 4) & 15 == 3 else "fp32_fma"),
+        vb: (["xw_interior_backward_v"], "tensor" if (vimpl >> 4) & 15 in (3, 4) else "fp32_fma"),
         "%s + k_weak_combine (interior forward, test-function values cached)" % xf: (["xw_interior_forward:cached_v"], "fp32_fma"),
         "%s + %s (interior forward, test-function net evaluated)" % (xf, vf): (["xw_interior_forward"], "mixed"),
     }

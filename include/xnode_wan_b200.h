@@ -81,7 +81,8 @@ size_t xw_yhist_floats(const xw_dims* dims, int n, int L);
  * 0 = none yet): lets tests and bench.py name the kernel that actually ran instead of assuming it */
 int xw_last_xnode_impl(void);
 /* same for the test-function net: bits 0-3 = last forward launch, bits 4-7 = last backward launch;
- * 1 = one thread per point (FP32), 2 = FP32 tile engine, 3 = tcgen05 (3xTF32) */
+ * 1 = one thread per point (FP32), 2 = FP32 tile engine, 3 = tcgen05 (3xTF32), 4 = tcgen05 on the virtual net of
+ * input width Hv (backward for d > 54) */
 int xw_last_vnet_impl(void);
 size_t xw_vcache_floats(const xw_dims* dims, int n, int L);
 /* upper bound of the scratch any call below needs for n paths of length L */

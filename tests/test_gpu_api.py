@@ -66,9 +66,10 @@ def _loss_and_grads(s, dom, X, XV, BX, phase):
                                     (30, 700 + 9, 300 + 7)])
 def test_mid_size_against_oracle(d, N, Nb):
     """d=20, N=2085 (several CTAs per kernel, ragged tail tiles) and d=100 (BASELINE configs[4]: V = 2^100,
-    float shape_param) vs the fp64 closed-form oracle; d=53 / d=55 straddle the largest input width of the
-    tensor-core backward (k-padded input 56 -> 64: FP32 tile backward, two tile streams in the forward), d=30 is
-    a 32-wide input"""
+    float shape_param) vs the fp64 closed-form oracle; d=53 / d=55 straddle the largest input width the tensor-core
+    backward takes directly (k-padded input 56): above it the backward runs on the VIRTUAL net of input width Hv
+    (per-path projection y = Wx x, xw_vnet_virtual.cuh) -- asserted through xw_last_vnet_impl, not assumed; d=30 is a
+    32-wide input"""
     s, prob = _rand_case(d, N, Nb, 3)
     dom = s.new_domain()
     pts = xw.Comb_loader(N, Nb, dom, DEV)
@@ -89,6 +90,8 @@ def test_mid_size_against_oracle(d, N, Nb):
         assert abs(val.components["I"].item() - o["I"]) <= 1e-4 * abs(o["I"])
         for a, b in zip(grads, o["grads"]):
             assert G.rel(a.cpu().numpy(), b) < 1e-3
+    # which backward kernel of the test-function net ran: 3 = tcgen05 directly, 4 = tcgen05 on the virtual net (d > 54)
+    assert (xw._lib.get().cdll.xw_last_vnet_impl() >> 4) & 15 == (3 if d <= 54 else 4)
 
 
 def test_large_size_properties():

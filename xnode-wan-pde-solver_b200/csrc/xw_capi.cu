@@ -9,6 +9,9 @@
 #include "xw_xnode3.cuh"
 #include "xw_umma.cuh"
 #include "xw_vnet_tc.cuh"
+#ifndef XW_EMU
+#include "xw_vnet_virtual.cuh"
+#endif
 
 #include <algorithm>
 #include <cstdarg>
@@ -179,6 +182,30 @@ int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
     p->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms));
     p->scratch_bytes = align_up((size_t)p->grid * 2 * std::max(m->nv, 1) * 14 * 128 * 16, 256);   // double-buffered (pipelined variant)
     p->part_bytes = align_up((size_t)p->grid * xw::VLayout(m->d, m->Hv).size * 4, 256);
+    return 0;
+}
+#endif
+#ifndef XW_EMU
+// wide inputs (d > 54): the tensor-core backward runs on the VIRTUAL net of input width Hv (xw_vnet_virtual.cuh)
+struct VvPlan { xw_dims mv; VtileBwdPlan pl; int grid_prep, grid_dwx, Pv; size_t y_b, th_b, gv_b, w_b, d0_b, px_b, total; };
+bool vv_wanted(const xw_dims* m) {
+    const char* e = getenv("XW_VNET_WIDE");
+    return !vtc_bwd_ok(m) && m->Hv + 2 <= xw::tc::KP && !(e && strcmp(e, "tile") == 0);
+}
+int plan_vv(const xw_dims* m, int n, int L, VvPlan* p) {
+    p->mv = *m;
+    p->mv.d = m->Hv;
+    if (plan_vtc_bwd(&p->mv, n, L, &p->pl)) return 1;
+    p->Pv = xw::VLayout(m->Hv, m->Hv).size;
+    p->grid_prep = (int)std::max<long long>(1, std::min<long long>(((long long)n + 127) / 128, (long long)device()->sms * 4));
+    p->grid_dwx = (int)std::max<long long>(1, std::min<long long>(((long long)n + xw::vv::kDwxPaths - 1) / xw::vv::kDwxPaths, (long long)device()->sms * 2));
+    p->y_b = align_up((size_t)n * m->Hv * 4, 256);
+    p->th_b = align_up((size_t)p->Pv * 4, 256);
+    p->gv_b = p->th_b;
+    p->w_b = align_up((size_t)n * L * 4, 256);
+    p->d0_b = align_up((size_t)n * L * 52 * 4, 256);
+    p->px_b = align_up((size_t)p->grid_dwx * m->Hv * m->d * 4, 256);
+    p->total = p->pl.scratch_bytes + p->pl.part_bytes + p->y_b + p->th_b + p->gv_b + p->w_b + p->d0_b + p->px_b;
     return 0;
 }
 #endif
@@ -434,6 +461,10 @@ size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
     if (vtc_bwd_ok(m)) {
         if (plan_vtc_bwd(m, n, L, &pv)) return 0;
         bwd_v = std::max(bwd_v, pv.scratch_bytes + pv.part_bytes);
+    } else if (vv_wanted(m)) {
+        VvPlan vp;
+        if (plan_vv(m, n, L, &vp)) return 0;
+        bwd_v = std::max(bwd_v, vp.total);
     }
 #endif
     return std::max(fwd, std::max(bwd_u, bwd_v)) + 1024;
@@ -677,6 +708,49 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
         g_last_vnet_bwd = 3;
         return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
+    }
+    if (use_tc_kernels() && vv_wanted(m)) {
+        // d > 54: tensor-core backward on the virtual net of input width Hv (y_n = Wx x_n per path), see xw_vnet_virtual.cuh
+        VvPlan vp;
+        if (plan_vv(m, n, L, &vp)) return 1;
+        if (workspace_bytes < vp.total) return fail("workspace too small: %zu < %zu", workspace_bytes, vp.total);
+        char* ws = (char*)workspace;
+        float* scratch = (float*)ws;                       ws += vp.pl.scratch_bytes;
+        float* gpart = (float*)ws;                         ws += vp.pl.part_bytes;
+        float* y = (float*)ws;                             ws += vp.y_b;
+        float* thv = (float*)ws;                           ws += vp.th_b;
+        float* gradv = (float*)ws;                         ws += vp.gv_b;
+        float* wbuf = (float*)ws;                          ws += vp.w_b;
+        float* d0 = (float*)ws;                            ws += vp.d0_b;
+        float* px = (float*)ws;
+        xw::vv::PrepArgs pa{};
+        pa.d = m->d; pa.Hvr = m->Hv; pa.n = n; pa.L = L; pa.theta = theta_v; pa.p = view_of(xv);
+        pa.dom_kind = dom->kind; pa.dp0 = dom->p0; pa.dp1 = dom->p1; pa.dp2 = dom->p2;
+        pa.y = y; pa.wbuf = wbuf; pa.theta_virtual = thv;
+        const size_t sm_prep = (size_t)m->d * xw::vv::HVP * 4;
+        if (sm_prep > device()->smem_optin) return fail("dim %d too large for the wide-input test-function backward", m->d);
+        if (XW_SET_SMEM(xw::vv::k_vv_prep, sm_prep)) return 1;
+        xw::vv::k_vv_prep<<<vp.grid_prep, 128, sm_prep, (cudaStream_t)stream>>>(pa);
+        if (XW_CHECK_LAUNCH("k_vv_prep")) return 1;
+        xw::VtileBwdArgs t{};
+        t.d = vp.mv.d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = thv;
+        t.p.t = xv->t; t.p.t_sn = xv->t_sn; t.p.t_sl = xv->t_sl; t.p.x = y; t.p.x_sn = m->Hv; t.p.x_sl = 0;
+        t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
+        t.cot = cot_v; t.coefs = coefs_dev; t.scratch = scratch; t.gpart = gpart; t.wbuf = wbuf; t.delta0_out = d0;
+        if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, vp.pl.smem)) return 1;
+        xw::tc::k_vnet_tc_bwd3<<<vp.pl.grid, 512, vp.pl.smem, (cudaStream_t)stream>>>(t);
+        if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
+        if (reduce_partials(gpart, vp.pl.grid, vp.Pv, gradv, 0, stream)) return 1;
+        xw::vv::DwxArgs da{};
+        da.d = m->d; da.Hvr = m->Hv; da.n = n; da.L = L; da.delta0 = d0; da.x = xv->x; da.x_sn = xv->x_sn; da.part = px;
+        const size_t sm_dwx = (size_t)(xw::vv::kDwxPaths * xw::vv::HVP + xw::vv::kDwxPaths * m->d) * 4;
+        if (m->d > 32 * xw::vv::kDwxJ) return fail("dim %d too large for the wide-input test-function backward (max %d)", m->d, 32 * xw::vv::kDwxJ);
+        xw::vv::k_vv_dwx<<<vp.grid_dwx, 256, sm_dwx, (cudaStream_t)stream>>>(da);
+        if (XW_CHECK_LAUNCH("k_vv_dwx")) return 1;
+        const int P = xw_theta_v_size(m);
+        xw::vv::k_vv_finish<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gradv, px, vp.grid_dwx, m->d, m->Hv, grad_v, accumulate);
+        g_last_vnet_bwd = 4;
+        return XW_CHECK_LAUNCH("k_vv_finish");
     }
 #endif
     {

@@ -561,8 +561,8 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 const float v = vex[j] + vex[128 + j] + w.wz[KP];
                 float G = 0.f;
                 if (valid) {
-                    const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
-                    G = fmaf(k0, __ldcs(a.cot + p), fmaf(k1, v, k2 * W.w));
+                    const float wdom = a.wbuf ? __ldcs(a.wbuf + p) : domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d).w;
+                    G = fmaf(k0, __ldcs(a.cot + p), fmaf(k1, v, k2 * wdom));
                 }
                 gbz += G;
                 uint32_t r[28];
@@ -631,7 +631,17 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 umma::fence_smem_to_async();
                 umma::mbar_arrive(mDPh + hh_);
                 published = true;
-                if (k == 0) break;
+                if (k == 0) {
+                    if (a.delta0_out) {                          // cotangent of the first pre-activation, per point
+                        const long long pp = tix * 128 + j;
+                        if (pp < npts) {
+                            f4* dst = reinterpret_cast<f4*>(a.delta0_out + pp * 52);
+#pragma unroll
+                            for (int c = 0; c < 13; ++c) dst[c] = f4{h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]};
+                        }
+                    }
+                    break;
+                }
                 const f4 mv = ld_scratch(sb + (size_t)((k - 1) * 14 + 13) * 128, pol);
                 const uint32_t m0 = __float_as_uint(mv.x), m1 = __float_as_uint(mv.y);
                 mbar_wait_or_trap(mR, pR);

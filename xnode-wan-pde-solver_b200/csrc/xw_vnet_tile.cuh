@@ -359,6 +359,10 @@ struct VtileBwdArgs {
     const float* cot; const double* coefs;
     float* scratch;          // [gridDim][nv][ROWS*RS] floats
     float* gpart;            // [gridDim][P]
+    // tensor-core backward on a VIRTUAL input (d > 54, xw_capi.cu): domain weight per point from a buffer (the virtual
+    // coordinates are not the spatial ones) and the cotangent of the first pre-activation dumped per point
+    const float* wbuf;       // optional [n*L]
+    float* delta0_out;       // optional [n*L][52]
 };
 
 template <int HV, int QR>

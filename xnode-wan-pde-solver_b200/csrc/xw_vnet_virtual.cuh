@@ -1,0 +1,155 @@
+// xw_vnet_virtual.cuh -- tensor-core backward of the test-function net for WIDE inputs (d > 54).
+//
+// k_vnet_tc_bwd3 keeps the input-layer operands of a tile in tensor memory / shared memory, which caps the padded input
+// width at 56 columns (d <= 54); at BASELINE configs[4] (d = 100) round 1 fell back to the FP32 tile engine (489 of 1251
+// ms per step).  Every path of every reference sampler has ONE spatial point (x repeats along the time axis,
+// /root/reference/src/dataset.py:252-254, :96, :190-201 -- the XNODE already relies on it, src/model.py:99), so the input
+// layer factors:  h_0[n,l] = wt t_l + (Wx x_n) + bi.  With the per-path projection y_n = Wx x_n (Hv numbers) the net is
+// EXACTLY a net of input width Hv with first-layer weights [wt | I]: that one fits the tensor-core kernel for any d.
+// Its weight gradient gives d wt, d bi and everything behind the first layer; the missing piece
+//     dWx = sum_n ( sum_l delta_0[n,l] ) x_n^T
+// comes from the per-point cotangent delta_0 that the kernel dumps (200 B / point) and two small FP32 kernels here.
+#pragma once
+#include "xw_kernels.cuh"
+
+namespace xw {
+namespace vv {
+
+constexpr int HV = 50, HVP = 52;
+
+struct PrepArgs {
+    int d, Hvr, n, L;
+    const float* theta;            // real parameters, VLayout(d, Hvr)
+    PointsView p;
+    int dom_kind; float dp0, dp1, dp2;
+    float* y;                      // [n][Hvr]
+    float* wbuf;                   // [n*L] domain weight
+    float* theta_virtual;          // VLayout(Hvr, Hvr)
+};
+
+// one thread per path: y_n = Wx x_n, w at the path's points; block 0 also writes the virtual parameter vector
+__global__ void k_vv_prep(PrepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* wxt = reinterpret_cast<float*>(smem_raw);               // [d][HVP]: Wi[o][1+j], j-major
+    const VLayout g(a.d, a.Hvr), gv(a.Hvr, a.Hvr);
+    for (int i = threadIdx.x; i < a.d * HVP; i += blockDim.x) wxt[i] = 0.f;
+    __syncthreads();
+    for (int e = threadIdx.x; e < a.Hvr * a.d; e += blockDim.x) {
+        const int o = e / a.d, j = e % a.d;
+        wxt[j * HVP + o] = a.theta[g.Wi + o * g.C + 1 + j];
+    }
+    if (blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < gv.size; e += blockDim.x) {
+            float v;
+            if (e < gv.bi) {                                       // Wi' = [wt | I]
+                const int o = e / gv.C, c = e % gv.C;
+                v = c == 0 ? a.theta[g.Wi + o * g.C] : (c - 1 == o ? 1.f : 0.f);
+            } else {
+                v = a.theta[g.bi + (e - gv.bi)];                   // bi, Wh, bh, Wz, bz follow in the same order
+            }
+            a.theta_virtual[e] = v;
+        }
+    }
+    __syncthreads();
+    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < a.n; n += (long long)gridDim.x * blockDim.x) {
+        const float* xp = a.p.x + n * a.p.x_sn;                    // time-row 0 of the path
+        float acc[HVP];
+#pragma unroll
+        for (int o = 0; o < HVP; ++o) acc[o] = 0.f;
+        for (int j = 0; j < a.d; ++j) {
+            float w[HVP];
+            load_row<HVP>(wxt + j * HVP, w);
+            const float xj = xp[j];
+#pragma unroll
+            for (int o = 0; o < HVP; ++o) acc[o] = fmaf(w[o], xj, acc[o]);
+        }
+        for (int o = 0; o < a.Hvr; ++o) a.y[n * a.Hvr + o] = acc[o];
+        for (int l = 0; l < a.L; ++l) {
+            const float t = a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl];
+            a.wbuf[n * a.L + l] = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, t, xp, a.d).w;
+        }
+    }
+}
+
+struct DwxArgs {
+    int d, Hvr, n, L;
+    const float* delta0;           // [n*L][52]
+    const float* x; long long x_sn;
+    float* part;                   // [gridDim][Hvr*d]
+};
+constexpr int kDwxPaths = 32, kDwxJ = 7, kDwxO = 7;      // thread (jl = tid % 32, og = tid / 32) owns j = jl + 32 a, o = og + 8 b
+
+// D_n = sum_l delta_0[n,l] per path, then dWx += D_n x_n^T over the CTA's paths (register accumulators, one partial per CTA)
+__global__ void __launch_bounds__(256) k_vv_dwx(DwxArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Ds = reinterpret_cast<float*>(smem_raw);                 // [kDwxPaths][HVP]
+    float* Xs = Ds + kDwxPaths * HVP;                               // [kDwxPaths][d]
+    const int jl = threadIdx.x & 31, og = threadIdx.x >> 5;
+    float acc[kDwxO][kDwxJ];
+#pragma unroll
+    for (int b = 0; b < kDwxO; ++b)
+#pragma unroll
+        for (int c = 0; c < kDwxJ; ++c) acc[b][c] = 0.f;
+    const long long ntiles = ((long long)a.n + kDwxPaths - 1) / kDwxPaths;
+    for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const long long n0 = tix * kDwxPaths;
+        __syncthreads();
+        for (int e = threadIdx.x; e < kDwxPaths * HVP; e += blockDim.x) {
+            const int pth = e / HVP, o = e % HVP;
+            const long long n = n0 + pth;
+            float s = 0.f;
+            if (n < a.n) {
+                const float* dp = a.delta0 + (n * a.L) * 52 + o;
+                for (int l = 0; l < a.L; ++l) s += dp[(long long)l * 52];
+            }
+            Ds[e] = s;
+        }
+        for (int e = threadIdx.x; e < kDwxPaths * a.d; e += blockDim.x) {
+            const int pth = e / a.d, j = e % a.d;
+            const long long n = n0 + pth;
+            Xs[e] = n < a.n ? a.x[n * a.x_sn + j] : 0.f;
+        }
+        __syncthreads();
+        for (int pth = 0; pth < kDwxPaths; ++pth) {
+            float dv[kDwxO], xv[kDwxJ];
+#pragma unroll
+            for (int b = 0; b < kDwxO; ++b) dv[b] = Ds[pth * HVP + ((og + 8 * b) < HVP ? (og + 8 * b) : 0)];
+#pragma unroll
+            for (int c = 0; c < kDwxJ; ++c) xv[c] = (jl + 32 * c) < a.d ? Xs[pth * a.d + jl + 32 * c] : 0.f;
+#pragma unroll
+            for (int b = 0; b < kDwxO; ++b)
+#pragma unroll
+                for (int c = 0; c < kDwxJ; ++c) acc[b][c] = fmaf(dv[b], xv[c], acc[b][c]);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < kDwxO; ++b)
+#pragma unroll
+        for (int c = 0; c < kDwxJ; ++c) {
+            const int o = og + 8 * b, j = jl + 32 * c;
+            if (o < a.Hvr && j < a.d) a.part[(size_t)blockIdx.x * a.Hvr * a.d + o * a.d + j] = acc[b][c];
+        }
+}
+
+// real-layout gradient from the virtual net's gradient + the dWx partials:  out[e] = (accumulate ? out[e] : 0) + ...
+__global__ void k_vv_finish(const float* grad_virtual, const float* dwx_part, int nparts, int d, int Hvr, float* out, int accumulate) {
+    const VLayout g(d, Hvr), gv(Hvr, Hvr);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.size) return;
+    double v;
+    if (e < g.bi) {
+        const int o = e / g.C, c = e % g.C;
+        if (c == 0) {
+            v = (double)grad_virtual[gv.Wi + o * gv.C];
+        } else {
+            v = 0.0;
+            for (int b = 0; b < nparts; ++b) v += (double)dwx_part[(size_t)b * Hvr * d + o * d + (c - 1)];
+        }
+    } else {
+        v = (double)grad_virtual[gv.bi + (e - g.bi)];
+    }
+    out[e] = (float)(v + (accumulate ? (double)out[e] : 0.0));
+}
+
+}  // namespace vv
+}  // namespace xw
