@@ -444,11 +444,17 @@ size_t xw_workspace_bytes(const xw_dims* m, int n, int L) {
     int gf = grid_for(n, kBlkFwd, 8);
     size_t fwd = align_up((size_t)n * m->d * 4, 256) + align_up((size_t)n * L * 4, 256) +
                  align_up(fwd_hist_floats(m, L) * gf * kBlkFwd * 4, 256);
+    size_t fwd_virtual = 0;
+#ifndef XW_EMU
+    if (vv_wanted(m))      // tensor-core forward on the virtual net: y[n][Hv], theta', (w, dw/dt) per point
+        fwd_virtual = align_up((size_t)n * m->Hv * 4, 256) + align_up((size_t)xw::VLayout(m->Hv, m->Hv).size * 4, 256) + 2 * align_up((size_t)n * L * 4, 256);
+    fwd += fwd_virtual;
+#endif
     XnodeBwdPlan pb;
     if (plan_xnode_bwd(m, n, L, &pb)) return 0;
     size_t bwd_u = pb.hist_bytes + pb.part_bytes;
     if (use_x2(m)) {
-        fwd = std::max(fwd, align_up((size_t)n * m->d * 4, 256) + align_up((size_t)n * L * 4, 256) + x2_rec_bytes(m, n, L));
+        fwd = std::max(fwd, align_up((size_t)n * m->d * 4, 256) + align_up((size_t)n * L * 4, 256) + x2_rec_bytes(m, n, L) + fwd_virtual);
         X2BwdPlan p2;
         if (x2_plan_bwd(m, n, L, &p2)) return 0;
         bwd_u = std::max(bwd_u, x2_bwd_bytes(p2));
@@ -601,6 +607,32 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     t.c0 = coef->c0; t.c1 = coef->c1; t.u = ubuf; t.h = h; t.f = f; t.sums = sums; t.cot_u = cot_u; t.cot_v = cot_v;
     t.vcache = vcache_mode == 1 ? vcache : nullptr;
 #ifndef XW_EMU
+    xw_dims mvirt = *m;
+    if (use_tc_kernels() && vv_wanted(m)) {
+        // d > 54: the tiled pass runs on the VIRTUAL net of input width Hv (y_n = Wx x_n per path, xw_vnet_virtual.cuh):
+        // the real input width would leave room for ONE tile stream in tensor memory instead of three
+        char* wv = ws + du_b + u_b + hist_b;
+        if (workspace_bytes < du_b + u_b + hist_b + align_up((size_t)n * m->Hv * 4, 256) + align_up((size_t)xw::VLayout(m->Hv, m->Hv).size * 4, 256) + 2 * align_up((size_t)n * L * 4, 256))
+            return fail("workspace too small for the wide-input forward");
+        float* y = (float*)wv;                   wv += align_up((size_t)n * m->Hv * 4, 256);
+        float* thv = (float*)wv;                 wv += align_up((size_t)xw::VLayout(m->Hv, m->Hv).size * 4, 256);
+        float* wbuf = (float*)wv;                wv += align_up((size_t)n * L * 4, 256);
+        float* dwtbuf = (float*)wv;
+        xw::vv::PrepArgs pa{};
+        pa.d = m->d; pa.Hvr = m->Hv; pa.n = n; pa.L = L; pa.theta = theta_v; pa.p = view_of(xv);
+        pa.dom_kind = dom->kind; pa.dp0 = dom->p0; pa.dp1 = dom->p1; pa.dp2 = dom->p2;
+        pa.y = y; pa.wbuf = wbuf; pa.dwtbuf = dwtbuf; pa.theta_virtual = thv;
+        const size_t sm_prep = (size_t)m->d * xw::vv::HVP * 4;
+        if (sm_prep > device()->smem_optin) return fail("dim %d too large for the wide-input test-function forward", m->d);
+        if (XW_SET_SMEM(xw::vv::k_vv_prep, sm_prep)) return 1;
+        const int gp = (int)std::max<long long>(1, std::min<long long>(((long long)n + 127) / 128, (long long)device()->sms * 4));
+        xw::vv::k_vv_prep<<<gp, 128, sm_prep, (cudaStream_t)stream>>>(pa);
+        if (XW_CHECK_LAUNCH("k_vv_prep")) return 1;
+        mvirt.d = m->Hv;
+        t.d = mvirt.d; t.theta = thv; t.wbuf = wbuf; t.dwtbuf = dwtbuf;
+        t.p.x = y; t.p.x_sn = m->Hv; t.p.x_sl = 0;
+        m = &mvirt;
+    }
     if (use_tc_kernels() && xw::tc::kin_of(m->d) <= 224) {
         // generation 3: hidden-layer contractions on the tensor cores (tcgen05, 3xTF32), 64 points per tile
         const int kin = xw::tc::kin_of(m->d), KA = std::max(kin, xw::tc::KP);

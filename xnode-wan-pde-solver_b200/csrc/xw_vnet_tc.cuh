@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
         const float dv_t = __shfl_sync(0xffffffffu, pt, (lane & 15) + 16);
         if (!is_tan && valid) {
             const float v = pv + w.wz[KP];
-            const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
+            DomW W;
+            if (a.wbuf) { W.w = a.wbuf[p]; W.dw_t = a.dwtbuf[p]; }     // (virtual input: the coordinates are not spatial)
+            else W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
             float cu, cv;
             weak_point_terms(v, dv_t, W.w, W.dw_t, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, a.c0, a.c1, accs, cu, cv);
             a.cot_u[p] = cu;
@@ -637,7 +639,8 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                         if (pp < npts) {
                             f4* dst = reinterpret_cast<f4*>(a.delta0_out + pp * 52);
 #pragma unroll
-                            for (int c = 0; c < 13; ++c) dst[c] = f4{h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]};
+                            for (int c = 0; c < 13; ++c)      // streaming stores: written once, read by another kernel -- keep L2 for the scratch
+                                __stcs(reinterpret_cast<float4*>(dst + c), make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]));
                         }
                     }
                     break;

@@ -188,6 +188,8 @@ struct VtileFwdArgs {
     double* sums; float* cot_u; float* cot_v;
     float* vcache;           // optional [n*L] x (v, dv/dt, w, dw/dt): lets later sub-steps on the same sample
                              // and the same theta_v skip the v net entirely (k_weak_combine)
+    const float* wbuf;       // optional [n*L] domain weight and
+    const float* dwtbuf;     // optional [n*L] its time derivative (tensor-core forward on the virtual net, d > 54)
 };
 
 // the weak-form integrands of one point from (v, dv/dt, w, dw/dt) and (u, f, h): src/loss.py:64-73

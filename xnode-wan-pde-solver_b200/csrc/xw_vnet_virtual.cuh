@@ -24,6 +24,7 @@ struct PrepArgs {
     int dom_kind; float dp0, dp1, dp2;
     float* y;                      // [n][Hvr]
     float* wbuf;                   // [n*L] domain weight
+    float* dwtbuf;                 // optional [n*L] its time derivative
     float* theta_virtual;          // VLayout(Hvr, Hvr)
 };
 
@@ -66,7 +67,9 @@ __global__ void k_vv_prep(PrepArgs a) {
         for (int o = 0; o < a.Hvr; ++o) a.y[n * a.Hvr + o] = acc[o];
         for (int l = 0; l < a.L; ++l) {
             const float t = a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl];
-            a.wbuf[n * a.L + l] = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, t, xp, a.d).w;
+            const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, t, xp, a.d);
+            a.wbuf[n * a.L + l] = W.w;
+            if (a.dwtbuf) a.dwtbuf[n * a.L + l] = W.dw_t;
         }
     }
 }
