@@ -151,7 +151,8 @@ def config_of(args):
             "arithmetic": "fp32 results: XNODE kernels FP32 FFMA2 (reduced state z = Wy y, shared layer in registers); "
                           "test-function net on tcgen05 kind::tf32 with 3xTF32 error compensation (1e-6 vs fp64; "
                           "XW_VNET_IMPL=tile selects the pure-FP32 kernels)",
-            "parallelism": "dp%d (paths sharded, 2 small all-reduces per sub-step)" % args.gpus}
+            "parallelism": "dp%d (paths sharded, 2 small all-reduces per sub-step)" % args.gpus,
+            "solver_options": {"use_cuda_graph": bool(getattr(args, "graph", 0)), "fused_optimizer": bool(getattr(args, "fused", 1))}}
 
 
 XNODE_NAMES = {1: ("k_xnode_fwd", "k_xnode_bwd"), 2: ("k_xnode2_fwd", "k_xnode2_bwd (+ k_xnode2_lift, k_xnode2_finish)"),
@@ -301,7 +302,7 @@ def run_ours(args):
         return ms.item() / steps
 
     def workload(n_loc):
-        solver, _ = make_solver(xw, d, n_loc * world, dev)
+        solver, _ = make_solver(xw, d, n_loc * world, dev, use_cuda_graph=bool(args.graph), fused_optimizer=bool(args.fused))
         torch.manual_seed(1000 + rank)
         domain = solver.new_domain(sample_device=dev, collapsed=True)
         points = xw.Comb_loader(n_loc, n_loc, domain, dev)
@@ -546,6 +547,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ttt", action="store_true", help="skip the time-to-target runs (N=1 only)")
     ap.add_argument("--ttt-seeds", type=int, default=5)
+    ap.add_argument("--graph", type=int, default=0, help="1: CUDA-graph replay of the sub-steps (NODE_WAN_solver(use_cuda_graph=True))")
+    ap.add_argument("--fused", type=int, default=1, help="1: flat parameter buffers + single-launch Adam (fused_optimizer=True)")
     ap.add_argument("--nlc-max-gb", type=float, default=8.0, help="skip the [N,L,C]-layout e2e arm above this many GB of pinned host memory")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -324,7 +324,7 @@ struct FwdArgs {
     const float* grad_h; float* du_out; float* rec; double* sums; const float* hloss;
     float* zq;                   // optional: [L][kZQ][n] reduced state history kept for the backward kernels
 };
-constexpr int kFwdThreads = 256;
+constexpr int kFwdThreads = 256;     // (384 threads at 168 registers measured 10 % slower: 4.2 vs 3.8 ms)
 constexpr int kRecWords2 = 4 + HH;
 
 template <int SOLVER, int MODE>

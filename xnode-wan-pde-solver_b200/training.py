@@ -275,6 +275,13 @@ class NODE_WAN_solver:
         pb = tmp._batch(self.u_net.module, static[0], static[1], static[2])
         self._graphs = dict(static=static, graphs={}, outs={}, domain=domain, persist=((h, f, g, a, b, c), pb))
 
+    def _graph_fits(self, batch):
+        """the captured graphs are bound to static copies of one layout ([N,L,C] tensors or CollapsedPaths) and size"""
+        for dst, src in zip(self._graphs["static"], batch):
+            if hasattr(dst, "times") != hasattr(src, "times") or tuple(dst.shape) != tuple(src.shape):
+                return False
+        return True
+
     def _graph_for(self, phase, vmode, fresh):
         # `fresh`: first sub-step after new data was copied into the static buffers -> this graph contains the
         # coefficient evaluation; the graphs of the following sub-steps read its results
@@ -313,6 +320,9 @@ class NODE_WAN_solver:
         as the reference: src/training.py:127-138 / :152-162); returns the last loss tensor"""
         single = not isinstance(points.interioru, list)
         vplan = self._vcache_plan(points)
+        if self.use_cuda_graph and single and self._graphs is not None and not self._graph_fits(points[0]):
+            self._graphs = None                      # another layout / size than the captured one: capture again later
+            self._coef = None
         if self.use_cuda_graph and single and self._graphs is not None:
             val = self._graph_step(phase, points[0], vplan[1])
             self._vcache_commit(phase, points)
