@@ -40,8 +40,11 @@ __device__ __forceinline__ void put_split(float* hi, float* lo, int off, float v
     hi[off] = h;
     lo[off] = v - h;
 }
+// Waits of the production kernels are bounded in TIME (about 10 s of SM clock, xw_mbar_wait in xw_platform.cuh), not in
+// probes: a wrong descriptor or a protocol bug surfaces as a CUDA error instead of a hung GPU, while a phase that is merely
+// slow (contention, MPS, a debugger, throttled clocks) can no longer expire the wait spuriously.
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* mbar, uint32_t& parity) {
-    if (!umma::mbar_wait(mbar, parity, 1 << 24)) __trap();
+    xw_mbar_wait(mbar, parity);
     parity ^= 1u;
 }
 
