@@ -470,3 +470,67 @@ def test_fused_optimizer_follows_torch_adam(emu):
             q.mul_(0.5)
     th = xw.hotpath.flatten_params(sb.u_net.module.kernel_parameters())
     assert torch.equal(th, torch.cat([q.detach().reshape(-1) for q in sb.u_net.module.kernel_parameters()]).float())
+
+
+def test_on_device_cube_sampler_distribution():
+    """`sample_device` draws with torch's generator of that device (same distributions as the reference sampler,
+    src/dataset.py:251-276, another RNG stream): interior uniform in the cube, boundary = int(N_b/d/2) paths per face with
+    exactly one coordinate pinned to top / bot (the remainder goes to the last face), random order, shared time grid with
+    pinned end points; collapsed layout == dense layout"""
+    torch.manual_seed(0)
+    d, N, Nb = 6, 20000, 1203
+    dom = xw.Hypercube((-1.0, 2.0), d, 0.0, 1.0, 20, sample_device="cpu", collapsed=True)
+    X, B = dom.interior(N), dom.boundary(Nb)
+    assert isinstance(X, xw.CollapsedPaths) and X.shape == (N, 20, d + 1) and B.shape == (Nb, 20, d + 1)
+    t = dom.times
+    assert float(t[0]) == 0.0 and float(t[-1]) == 1.0 and bool(torch.all(t[1:] >= t[:-1]))
+    x = X.x
+    assert float(x.min()) >= -1.0 and float(x.max()) < 2.0
+    assert abs(float(x.mean()) - 0.5) < 0.02 and abs(float(x.var()) - 9.0 / 12.0) < 0.02       # U(-1, 2)
+    hist = torch.histc(x[:, 0], bins=10, min=-1.0, max=2.0) / N
+    assert float((hist - 0.1).abs().max()) < 0.012
+    xb = B.x
+    on_top, on_bot = (xb == 2.0), (xb == -1.0)
+    pinned = on_top | on_bot
+    assert bool(torch.all(pinned.sum(1) == 1))                     # exactly one pinned coordinate per boundary path
+    per_face = Nb // d // 2
+    top_counts, bot_counts = on_top.sum(0).tolist(), on_bot.sum(0).tolist()
+    assert top_counts == [per_face] * d
+    assert bot_counts[:-1] == [per_face] * (d - 1) and bot_counts[-1] == Nb - per_face * (2 * d - 1)
+    free = xb[~pinned]
+    assert float(free.min()) > -1.0 and float(free.max()) < 2.0 and abs(float(free.mean()) - 0.5) < 0.05
+    # the permutation mixes the faces: the first block of paths is not all on face 0
+    assert int(on_top[:per_face, 0].sum()) < per_face
+    dense = X.dense()
+    assert torch.equal(dense[:, 3, 1:], x) and torch.equal(dense[5, :, 0], t)
+
+
+@pytest.mark.parametrize("cls", ["NSphere_TCone", "NSphere_THourglass"])
+def test_on_device_sphere_samplers_build_the_reference_groups(cls):
+    """the vectorised group construction used by `sample_device` (torch ops on the sampling device) yields, for the SAME
+    points, exactly the groups of the reference-order CPU sampler (src/dataset.py:81-117, :185-214); and its own draws
+    have the right structure (inside the ball, boundary counts int(N_b scale(t)^d))"""
+    Dom = getattr(xw, cls)
+    torch.manual_seed(2)
+    np.random.seed(2)
+    dom = Dom(1.0, 5, 0.0, 1.0, 20)
+    st = np.random.get_state()
+    pts = dom._ball(400)                                   # [dim, N] as the CPU sampler draws them
+    np.random.set_state(st)
+    ref = dom.interior(400)
+    got = dom._groups_from(torch.from_numpy(pts).transpose(0, 1).contiguous())
+    assert [tuple(g.shape) for g in got] == [tuple(g.shape) for g in ref]
+    for a, b in zip(got, ref):
+        assert a.dtype == b.dtype == torch.float64 and torch.equal(a, b)
+    dev = Dom(1.0, 5, 0.0, 1.0, 20, times=dom.times, sample_device="cpu")
+    groups = dev.interior(3000)
+    assert sum(g.shape[0] for g in groups if float(g[0, 0, 0]) == 0.0) == 3000        # every path has a segment from T0
+    lens = [g.shape[1] for g in groups]
+    assert lens == sorted(lens)
+    for g in groups:
+        assert bool(torch.all(dev.func_w(g) > 0) if cls == "NSphere_TCone" else torch.all(dev.func_w(g[:, 1:] if float(g[0, 0, 0]) != 0.0 else g) > 0))
+    bd = dev.boundary(500)
+    want = [int(500 * dev._radius_scale(t) ** 5) for t in dev.times.numpy()]
+    assert [g.shape[0] for g in bd] == [n for n in want if n]
+    for g in bd:
+        assert g.shape[1] == 1 and float(dev.func_w(g).abs().max()) < 1e-9           # on the sphere of that time

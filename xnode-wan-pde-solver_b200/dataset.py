@@ -203,12 +203,28 @@ class _SphereDomain:
     Random numbers are drawn in the reference's order (numpy normal for the directions, numpy rand
     for the radii, torch uniform for the time grid), so seeded runs reproduce its groups exactly."""
 
-    def __init__(self, r: float, dim: int, T0: float, T: float, N_t: int, times=None):
+    def __init__(self, r: float, dim: int, T0: float, T: float, N_t: int, times=None, sample_device=None):
         self.r, self.dim, self.T0, self.T, self.N_t = r, dim, T0, T, N_t
         if times is None:
             times = torch.empty(N_t).uniform_(T0, T).sort(0).values
             times[0], times[-1] = T0, T
         self.times = times
+        # sample_device: draw the points with torch's generator of that device and build the groups with vectorised
+        # tensor ops there (same distributions and group structure, another RNG stream than the reference's numpy one)
+        self.sample_device = sample_device
+
+    def _surf_t(self, N: int):
+        """N points on the sphere of radius r, [N, dim] float64 on the sampling device"""
+        z = torch.randn(N, self.dim, dtype=torch.float64, device=self.sample_device)
+        return self.r * z / z.norm(dim=1, keepdim=True)
+
+    def _ball_t(self, N: int):
+        return self._surf_t(N) * torch.rand(N, 1, dtype=torch.float64, device=self.sample_device) ** (1.0 / self.dim)
+
+    def _group(self, tt, x):
+        """[n, k, C] float64 group: times tt[k] (shared) next to the points x[n, dim]"""
+        n, k = x.shape[0], tt.shape[0]
+        return torch.cat((tt.view(1, k, 1).expand(n, k, 1), x.unsqueeze(1).expand(n, k, x.shape[1])), 2)
 
     def surf(self, N: int):
         """N points on the sphere of radius r, [dim, N] (normalised normal deviates)"""
@@ -229,6 +245,11 @@ class _SphereDomain:
         for t in self.times.numpy():
             sc = self._radius_scale(t)
             n = int(N_b * sc ** self.dim)
+            if self.sample_device is not None:
+                if n != 0:
+                    tt = torch.full((1,), float(t), dtype=torch.float64, device=self.sample_device)
+                    groups.append(self._group(tt, self._surf_t(n) * float(sc)))
+                continue
             x = torch.from_numpy(self.surf(n) * sc).transpose(0, 1).unsqueeze(1)
             if n != 0:
                 groups.append(torch.cat((t * torch.ones(n, 1, 1), x), 2))
@@ -248,6 +269,8 @@ class NSphere_TCone(_SphereDomain):
     def interior(self, N_r: int):
         """a path lives on times[0:k) where k = number of grid times with |x| < r (1 - t); paths of equal k
         form one group [n, k, C]; groups in ascending k"""
+        if self.sample_device is not None:
+            return self._groups_from(self._ball_t(N_r))
         pts = self._ball(N_r)                                       # [dim, N_r]
         grid = self.times.repeat(N_r, 1).unsqueeze(2)               # [N_r, N_t, 1]
         groups = []
@@ -260,6 +283,13 @@ class NSphere_TCone(_SphereDomain):
                 groups.append(torch.cat((grid[:x.shape[0], :k], x), 2))
             k -= 1
         return groups[::-1]
+
+    def _groups_from(self, pts):
+        """the same groups from given points pts[N, dim] with tensor ops on pts' device: the radius shrinks with t, so
+        a path's length is the NUMBER of grid times at which it is inside; original order inside a group"""
+        tt = self.times.to(pts.device).double()
+        k_n = (pts.norm(dim=1).unsqueeze(1) < self.r * (1 - tt).unsqueeze(0)).sum(1)
+        return [self._group(tt[:k], pts[k_n == k]) for k in torch.unique(k_n).tolist() if k > 0]
 
     def func_w(self, x: torch.Tensor):
         return self.r * (1 - x[:, :, 0]) - x[:, :, 1:].pow(2).sum(2).sqrt()
@@ -286,6 +316,8 @@ class NSphere_THourglass(_SphereDomain):
         back: it contributes a first segment (times before the exit) and, if it was ever outside, a second
         segment (times after the re-entry) that gets one extra leading row at the exact entry time
         t = |x| / r.  Segments of equal length are concatenated into groups, ascending length."""
+        if self.sample_device is not None:
+            return self._groups_from(self._ball_t(N_r))
         pts = torch.from_numpy(self._ball(N_r)).transpose(0, 1)    # [N_r, dim] float64
         grid = self.times.repeat(N_r, 1)                            # [N_r, N_t]
         half = (self.T - self.T0) / 2
@@ -311,6 +343,29 @@ class NSphere_THourglass(_SphereDomain):
                 out.setdefault(sgm.shape[1], []).append(sgm)
             return [torch.cat(v, 0) for _, v in sorted(out.items())]
         return sorted(grouped(first) + grouped(second), key=lambda z: z.shape[1])
+
+    def _groups_from(self, pts):
+        """the same groups from given points pts[N, dim] with tensor ops on pts' device.  The radius is V-shaped in t,
+        so the times a path spends outside form one interval: a = length of the inside prefix, b = of the inside suffix"""
+        tt = self.times.to(pts.device).double()
+        N_t, span = self.N_t, self.T - self.T0
+        nrm = pts.pow(2).sum(1).sqrt()                 # (the reference's formula, bit for bit: it becomes the entry time)
+        radius = torch.where(self.times.to(pts.device) <= span / 2, self.r * (span - tt), self.r * tt)
+        inside = nrm.unsqueeze(1) < radius.unsqueeze(0)                       # [N, N_t]
+        a_n = torch.cumprod(inside.long(), 1).sum(1)
+        b_n = torch.cumprod(inside.flip(1).long(), 1).sum(1)
+        never_out = a_n == N_t
+        first, second = [], []
+        for a in torch.unique(a_n).tolist():
+            if a > 0:
+                first.append(self._group(tt[:a], pts[a_n == a]))
+        for b in torch.unique(b_n[~never_out]).tolist():
+            sel = (~never_out) & (b_n == b)
+            x = pts[sel]
+            seg = self._group(tt[N_t - b:], x)
+            entry = torch.cat(((nrm[sel] / self.r).view(-1, 1, 1), x.unsqueeze(1)), 2)
+            second.append(torch.cat((entry, seg), 1))
+        return sorted(first + second, key=lambda z: z.shape[1])
 
     def func_w(self, x: torch.Tensor):
         t = x[:, :, 0]

@@ -155,8 +155,8 @@ class NODE_WAN_solver:
         s = self.setup
         if getattr(self, "sample_on_device", False):
             kw.setdefault("sample_device", self.device)
-        if getattr(self, "collapsed_layout", False):
-            kw.setdefault("collapsed", True)
+        if getattr(self, "collapsed_layout", False) and self.domain is _dataset.Hypercube:
+            kw.setdefault("collapsed", True)       # (only the cube repeats ONE time grid for every path)
         dom = self.domain(s['shape_param'], s['dim'], s['T0'], s['T'], s['N_t'], **kw)
         if getattr(self, "world", 1) > 1:          # the time grid must be the same on every rank
             t = dom.times.to(self.device)
