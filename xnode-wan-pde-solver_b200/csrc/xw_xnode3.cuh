@@ -36,7 +36,8 @@ constexpr int kPartA = x2::kPartA;
 struct Sm {
     static constexpr int RED = 0;                       // reduced image x2::R
     static constexpr int WST = RED + R::size;           // [HH][HHP]  Ws in-major (staging for the register copy)
-    static constexpr int BS = WST + HH * HHP;           // [HHP]
+    static constexpr int WSO = WST + HH * HHP;          // [HH][HHP]  Ws out-major: row o = Ws[o][:] (register copy of the R role)
+    static constexpr int BS = WSO + HH * HHP;           // [HHP]
     static constexpr int WT = BS + HHP;                 // [HHP]  Wa[:, d]
     static constexpr int BA = WT + HHP;                 // [HHP]
     static constexpr int BO = BA + HHP;                 // [4]
@@ -73,6 +74,7 @@ XW_DEV void stage(float* sm, const float* XW_RESTRICT th, int d, int Hr, int HHr
         sr[R::MT + i * HHP + o] = m;
         sr[R::MO + o * HHP + i] = m;
         sm[Sm::WST + i * HHP + o] = th[g.Ws + o * HHr + i];
+        sm[Sm::WSO + o * HHP + i] = th[g.Ws + o * HHr + i];
     }
     for (int o = XW_TID; o < HHr; o += XW_BDIM) {
         float c = 0.f, v = 0.f;
@@ -97,6 +99,57 @@ XW_DEV void stage(float* sm, const float* XW_RESTRICT th, int d, int Hr, int HHr
         sm[Sm::WXT + j * HHP + o] = th[g.Wa + o * g.lda + j];
     }
     XW_SYNCTHREADS();
+}
+
+// The R role runs reverse passes only, so it keeps the shared layer in the TRANSPOSED pairing
+// wT[o][ip] = (Ws[o][2ip], Ws[o][2ip+1]):  dn[i] = sum_o Ws[o][i] dl[o]  becomes, per o, five FFMA2 with dl[o] as the
+// broadcast operand, and the packed accumulators ARE (dn[2ip], dn[2ip+1]) -- no final lo+hi adds; the relu mask is one
+// packed multiply per pair and the next layer reads its broadcast scalars straight from the register halves.
+struct CoreRegsT {
+    fpair wT[HH][HH / 2];
+};
+XW_DEV void load_core_t(const float* wso, CoreRegsT& cr) {
+#pragma unroll
+    for (int o = 0; o < HH; ++o)
+#pragma unroll
+        for (int ip = 0; ip < HH / 2; ++ip) {
+            const f2 v = ld2(wso + o * HHP + 2 * ip);
+            cr.wT[o][ip] = pack2(v.x, v.y);
+        }
+}
+XW_DEV void st_pairs10(float* p, const fpair (&d)[HH / 2]) {
+    float v[HH];
+#pragma unroll
+    for (int ip = 0; ip < HH / 2; ++ip) unpack2(d[ip], v[2 * ip], v[2 * ip + 1]);
+    x2::st_vec10(p, v, 0.f);
+}
+// d = cotangent of a_nsh (packed pairs) -> cotangent of a_0; delta_j goes to the delta-tile slot j-1, the mask of layer
+// j-1 comes from its recorded output in the r-tile (loaded before the FFMA2 block)
+XW_DEV void core_rev_t(const CoreRegsT& cr, fpair (&d)[HH / 2], int nsh, const float* rrow, float* drow) {
+#pragma unroll 1
+    for (int j = nsh; j > 0; --j) {
+        st_pairs10(drow + kSlot * (j - 1), d);
+        float rm[HH];
+        x2::ld_vec10(rrow + kSlot * (j - 1), rm);
+        fpair acc[HH / 2];
+#pragma unroll
+        for (int ip = 0; ip < HH / 2; ++ip) acc[ip] = pack2(0.f, 0.f);
+#pragma unroll
+        for (int op = 0; op < HH / 2; ++op) {
+            float d0, d1;
+            unpack2(d[op], d0, d1);
+            const fpair b0 = pack2(d0, d0), b1 = pack2(d1, d1);
+#pragma unroll
+            for (int ip = 0; ip < HH / 2; ++ip) acc[ip] = fma2(cr.wT[2 * op][ip], b0, acc[ip]);
+#pragma unroll
+            for (int ip = 0; ip < HH / 2; ++ip) acc[ip] = fma2(cr.wT[2 * op + 1][ip], b1, acc[ip]);
+        }
+#pragma unroll
+        for (int ip = 0; ip < HH / 2; ++ip) {
+            const fpair m = pack2(rm[2 * ip] > 0.f ? 1.f : 0.f, rm[2 * ip + 1] > 0.f ? 1.f : 0.f);
+            d[ip] = fma2(acc[ip], m, pack2(0.f, 0.f));
+        }
+    }
 }
 
 template <int SOLVER, int MODE>
@@ -174,8 +227,8 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kThreads, 1) k_xnode3_bwd(Args a) {
     } else if (role == 1) {
         // ================================================================================== R: reverse sweep
         XW_SETMAXNREG_INC(192);     // 168 (F) + 192 (R) + 144 (G) = 3 x 168: the pool is what the CTA was launched with
-        x2::CoreRegs cr;
-        x2::load_core_from(sm + Sm::WST, sm + Sm::BS, cr);
+        CoreRegsT cr;
+        load_core_t(sm + Sm::WSO, cr);
         const float bo = sm[Sm::BO];
         float k0 = 0.f, k1 = 0.f, k2 = 0.f;
         if (MODE == 0) { k0 = (float)a.coefs[0]; k1 = (float)a.coefs[1]; k2 = (float)a.coefs[2]; }
@@ -234,7 +287,22 @@ XW_GLOBAL void XW_LAUNCH_BOUNDS(kThreads, 1) k_xnode3_bwd(Args a) {
                     if (u >= 1) XW_MBAR_WAIT(empty_d + b, (u - 1) & 1u);           // G is done with the previous use of this tile
                     x2::st_vec10(rec.drow + kSlot * (kSlots - 1), kbar[s], 0.f);
                     float dl[HH];
-                    x2::stage_rev(cr, sr, kbar[s], pbar, tau, nsh, dl, rec);
+                    {
+                        // cotangent of tanh's input: (M^T kbar + v pbar) (1 - tau^2), then the shared-layer stack in reverse
+                        float v[HH];
+                        load_row<HH>(sr + R::VV, v);
+#pragma unroll
+                        for (int i = 0; i < HH; ++i) dl[i] = v[i] * pbar;
+                        matvec_acc<HH, HH, HHP>(sr + R::MO, kbar[s], dl);
+                        fpair dp[HH / 2];
+#pragma unroll
+                        for (int ip = 0; ip < HH / 2; ++ip)
+                            dp[ip] = pack2(dl[2 * ip] * fmaf(-tau[2 * ip], tau[2 * ip], 1.f),
+                                           dl[2 * ip + 1] * fmaf(-tau[2 * ip + 1], tau[2 * ip + 1], 1.f));
+                        core_rev_t(cr, dp, nsh, rec.rrow, rec.drow);
+#pragma unroll
+                        for (int ip = 0; ip < HH / 2; ++ip) unpack2(dp[ip], dl[2 * ip], dl[2 * ip + 1]);
+                    }
                     XW_MBAR_ARRIVE(full_d + b);
                     ++e;
 #pragma unroll
