@@ -192,6 +192,7 @@ def time_to_target(xw, dev, seeds, max_outer=600):
             trace.append(r)
             return r < 0.01
         solver.stop = stop
+        solver.keep_l2_history = False           # (the per-iteration L2 on a fresh sample is logging only; stop() is what counts)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         import contextlib

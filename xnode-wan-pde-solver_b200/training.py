@@ -145,6 +145,7 @@ class NODE_WAN_solver:
         self._warm = 0                   # completed eager iterations (the first one warms up before graph capture)
         self.reuse_v = True              # cache the test-function values across the sub-steps of one iteration
         self._vc_buf, self._vc_key, self._theta_v_gen = None, None, 0
+        self.keep_l2_history = True      # False: skip the per-iteration L2 evaluation on a fresh sample when nothing logs it
         self._coef = None                # (sample token, (h, f, g, a, b, c), hotpath.Batch) of the sample in flight
         self._load_gen = 0               # bumped whenever new data lands in the graphs' static buffers
         self.best_l = float('inf')
@@ -289,13 +290,23 @@ class NODE_WAN_solver:
         if key not in self._graphs["graphs"]:
             g = torch.cuda.CUDAGraph()
             opt = self.optimizer_u if phase == "u" else self.optimizer_v
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                opt.zero_grad(set_to_none=True)
-                if fresh:
-                    self._coef = None
-                self._graphs["outs"][key] = self._step(phase, self._graphs["domain"], self._graphs["static"],
-                                                       (self._vc_buf, vmode), token=("graph", id(self._graphs)))
+            # capture on a side stream with the low-level API: `with torch.cuda.graph(g)` runs gc.collect() and
+            # torch.cuda.empty_cache() on entry (~0.15 s per capture, 4 captures per solver: a third of a short training run)
+            dev = torch.device(self.device)
+            side = self._graphs.setdefault("stream", torch.cuda.Stream(dev))
+            cur = torch.cuda.current_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                try:
+                    opt.zero_grad(set_to_none=True)
+                    if fresh:
+                        self._coef = None
+                    self._graphs["outs"][key] = self._step(phase, self._graphs["domain"], self._graphs["static"],
+                                                           (self._vc_buf, vmode), token=("graph", id(self._graphs)))
+                finally:
+                    g.capture_end()
+            cur.wait_stream(side)
             self._graphs["graphs"][key] = g
         return key
 
@@ -390,7 +401,8 @@ class NODE_WAN_solver:
                 loss_v = self.sub_step("v", domain, points)
             self._warm += 1
             L2 = None
-            if self.func_u_sol is not None:
+            if self.func_u_sol is not None and (self.log_json or report or self.keep_l2_history):
+                # (reference src/training.py:165-170: a fresh sample and one more forward, for logging only)
                 fresh = Comb_loader(n_r, n_b, domain, self.device)
                 L2 = L_norm(fresh.interioru, self.u_net, self.p, self.func_u_sol, domain.V(), n_r)
                 if self.world > 1:         # shards of equal size: the global L^p error is the p-mean of the shard errors
