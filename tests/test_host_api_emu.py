@@ -241,8 +241,14 @@ def test_sphere_samplers_reproduce_reference_groups():
         pts = xw.Comb_loader(300, 300, dom, "cpu")
         X, XV, BX = pts[case["meta"]["group"]]
         z = case["z"]
-        assert torch.equal(X, torch.from_numpy(z["X"])) and torch.equal(XV, torch.from_numpy(z["XV"]))
-        assert torch.equal(BX, torch.from_numpy(z["BX"]))
+        # spatial coordinates and grid times bit for bit; the hourglass' computed entry time |x| / r (row 0 of a
+        # re-entry segment) to the last bit or two: torch's vectorised sum over the d coordinates associates
+        # differently on AVX2 and AVX-512 hosts, and the golden comes from whichever host generated it
+        for mine, ref in ((X, z["X"]), (XV, z["XV"]), (BX, z["BX"])):
+            ref = torch.from_numpy(ref)
+            assert mine.shape == ref.shape and torch.equal(mine[..., 1:], ref[..., 1:])
+            assert torch.equal(mine[:, 1:, 0], ref[:, 1:, 0])
+            assert float((mine[:, 0, 0] - ref[:, 0, 0]).abs().max()) <= 4.5e-16
 
 
 def test_training_iteration_on_cone_domain(emu):

@@ -173,10 +173,13 @@ int plan_vtile_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
 }
 #ifndef XW_EMU
 // tensor-core backward: one 128-point tile per CTA iteration, one CTA per SM (tensor memory: 512 columns)
+// test hook: XW_TC_TMEM_PACKED=1 runs k_vnet_tc_bwd3 on the fully packed tensor-memory layout for every input width
+// (the layout kin = 56 needs anyway), so that the parity tests of the narrow configs cover it too
+int tc_tmem_packed() { static const int v = []() { const char* e = getenv("XW_TC_TMEM_PACKED"); return e && e[0] == '1' ? 1 : 0; }(); return v; }
 bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
 int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
     const int kin = xw::tc::kin_of(m->d);
-    p->smem = (size_t)(4 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64 + 4 * xw::tc::TIMG + xw::tc::KP * (xw::tc::KP + kin) + 512 + 64 + 256) * 4 + 128;
+    p->smem = (size_t)(4 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64 + 2 * xw::tc::TIMG2 + xw::tc::KP * (xw::tc::KP + kin + 1) + 512 + 64 + 256) * 4 + 128;
     if (p->smem > device()->smem_optin) return fail("tensor-core v-net backward needs %zu B shared memory (> %zu)", p->smem, device()->smem_optin);
     const long long ntiles = ((long long)n * L + 127) / 128;
     p->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)device()->sms));
@@ -735,6 +738,7 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
         t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
         t.cot = cot_v; t.coefs = coefs_dev; t.scratch = (float*)workspace; t.gpart = (float*)((char*)workspace + pl.scratch_bytes);
+        t.tm_packed = tc_tmem_packed();
         if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, pl.smem)) return 1;
         xw::tc::k_vnet_tc_bwd3<<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
         if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
@@ -769,6 +773,7 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         t.p.t = xv->t; t.p.t_sn = xv->t_sn; t.p.t_sl = xv->t_sl; t.p.x = y; t.p.x_sn = m->Hv; t.p.x_sl = 0;
         t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
         t.cot = cot_v; t.coefs = coefs_dev; t.scratch = scratch; t.gpart = gpart; t.wbuf = wbuf; t.delta0_out = d0;
+        t.tm_packed = tc_tmem_packed();
         if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, vp.pl.smem)) return 1;
         xw::tc::k_vnet_tc_bwd3<<<vp.pl.grid, 512, vp.pl.smem, (cudaStream_t)stream>>>(t);
         if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;

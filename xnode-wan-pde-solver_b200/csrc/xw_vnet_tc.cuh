@@ -332,35 +332,61 @@ __device__ __forceinline__ void issue_pop(uint32_t tD, const float* a_hi, const 
 // hand-off is an mbarrier with a bounded wait; F's activations and relu masks travel through a
 // double-buffered per-CTA scratch in global memory (L2 resident).
 // =============================================================================================
-constexpr int P3_DF = 0, P3_AF = 64, P3_DR = 176, P3_AR = 240, P3_WH = 352, P3_WI = 416;
+// Tensor-memory columns of k_vnet_tc_bwd3 (512 in all): accumulators D_f (56), D_r (56), dWh (112: the r_hi | r_lo blocks),
+// dWi (kin) and the TS-form A operands A_f, A_r (hi | lo, 112 each) = 448 + kin.  Up to kin = 48 every accumulator starts on a
+// multiple of 16 columns; the widest input (kin = 56: d = 47..54 and the virtual net of 4.1c) only fits fully packed, on
+// multiples of 8.
+struct P3Cols { int DF, AF, DR, AR, WH, WI; };
+__device__ __forceinline__ P3Cols p3_cols(int kin, int packed) {
+    P3Cols c;
+    if (kin > 48 || packed) { c.WH = 0; c.WI = 112; c.DF = 168; c.DR = 224; c.AF = 280; c.AR = 392; }
+    else { c.WH = 0; c.DF = 112; c.DR = 176; c.AF = 240; c.AR = 352; c.WI = 464; }
+    return c;
+}
 
+// Stacked transposed images of the weight-gradient MMAs (P-op).  dWh[o][i] = sum_p delta[p][o] r[p][i] has only 56 rows and 56
+// columns, both operands are per-point data (shared memory, SS form) and the 3xTF32 scheme needs the hi/lo cross terms.
+// Instead of three M = 64 MMAs per k-step (each re-reading one image of A and one of B: 3 x 3840 B of operand traffic, and
+// M = 64 occupies the tensor pipe as long as M = 128 does) the hi and lo rows are STACKED: A = [delta_hi ; delta_lo]
+// (M = 128: rows 0..55 | 56..111), B = [r_hi ; r_lo] (N = 112).  ONE MMA per k-step of 8 points then yields all four
+// hi/lo products in four accumulator blocks (7680 B of operand traffic, 56 instead of 84 pipe cycles, 16 instead of 48
+// instructions per layer and tile); the blocks are summed when a tile's accumulators are flushed.
+// Image element (row, point r): 16-byte chunks of 4 consecutive points, 8-row core matrices (128 B), 14 row groups per
+// chunk, chunk stride padded to 452 floats (= 4 mod 32: the 32 lanes of a warp hit 32 banks with their scalar stores).
+constexpr int TCS2 = 14 * 32 + 4;            // chunk stride of a stacked image (floats)
+constexpr int THALF2 = 16 * TCS2;            // one half image: 64 points = 16 chunks
+constexpr int TIMG2 = 2 * THALF2;
+__device__ __forceinline__ int ts_off(int row, int r) { return (r >> 6) * THALF2 + ((r & 63) >> 2) * TCS2 + (row >> 3) * 32 + (row & 7) * 4 + (r & 3); }
 
-// one HALF of a P-op: the 64 points of half h (8 k-steps of 8 points), all three terms.  The two halves have their own
-// images, barriers and issuing threads: while one half's MMAs run, the other half's images are being rewritten.
-__device__ __forceinline__ void issue_pop_half(uint32_t tD, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
-                                               uint32_t idesc) {
-    constexpr uint64_t kStep = (2 * TCS * 4) >> 4;
-    const uint64_t ah = umma::smem_desc(a_hi, TCS * 4, 128), al = umma::smem_desc(a_lo, TCS * 4, 128);
-    const uint64_t bh = umma::smem_desc(b_hi, TCS * 4, 128), bl = umma::smem_desc(b_lo, TCS * 4, 128);
+// one HALF of a P-op (64 points = 8 k-steps).  The two halves have their own image halves, barriers and issuing threads:
+// while one half's MMAs run, the other half's images are being rewritten.
+__device__ __forceinline__ void issue_pop_half_stacked(uint32_t tD, const float* a_img, const float* b_img, uint32_t idesc) {
+    constexpr uint64_t kStep = (2 * TCS2 * 4) >> 4;
+    const uint64_t ad = umma::smem_desc(a_img, TCS2 * 4, 128), bd = umma::smem_desc(b_img, TCS2 * 4, 128);
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
+    for (int ks = 0; ks < 8; ++ks) umma::mma_tf32(tD, ad + kStep * ks, bd + kStep * ks, idesc, 1u);
+}
+// input layer: B = (t, x, 1) with hi rows [0, kin) and lo rows [56, 56 + kin); N = kin per MMA, both into the same columns
+__device__ __forceinline__ void issue_pop_half_in(uint32_t tD, const float* a_img, const float* b_img, uint32_t idesc) {
+    constexpr uint64_t kStep = (2 * TCS2 * 4) >> 4;
+    const uint64_t ad = umma::smem_desc(a_img, TCS2 * 4, 128);
+    const uint64_t bh = umma::smem_desc(b_img, TCS2 * 4, 128), bl = umma::smem_desc(b_img + 7 * 32, TCS2 * 4, 128);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-            umma::mma_tf32(tD, (t == 0 ? al : ah) + kStep * ks, (t == 1 ? bl : bh) + kStep * ks, idesc, 1u);
+    for (int ks = 0; ks < 8; ++ks) {
+        umma::mma_tf32(tD, ad + kStep * ks, bh + kStep * ks, idesc, 1u);
+        umma::mma_tf32(tD, ad + kStep * ks, bl + kStep * ks, idesc, 1u);
     }
 }
 // clears this thread's lane of the dWh / dWi accumulator columns
-__device__ __forceinline__ void zero_acc(uint32_t lane_addr, int kin) {
+__device__ __forceinline__ void zero_acc(uint32_t lane_wh, uint32_t lane_wi, int kin) {
     uint32_t z[KP];
 #pragma unroll
     for (int i = 0; i < KP; ++i) z[i] = 0u;
-    umma::tmem_st56(lane_addr + 352, z);
+    umma::tmem_st56(lane_wh, z);
+    umma::tmem_st56(lane_wh + KP, z);
     float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int c8 = 0; c8 < kin; c8 += 8) umma::tmem_st8(lane_addr + 416 + c8, z8);
+    for (int c8 = 0; c8 < kin; c8 += 8) umma::tmem_st8(lane_wi + c8, z8);
 }
-constexpr int THALF = 16 * TCS;              // floats of one half image (64 points = 16 chunks)
-// element (row, point r) of half (r >> 6) of an image
-__device__ __forceinline__ int th_off(int row, int r) { return (r >> 6) * THALF + ((r & 63) >> 2) * TCS + (row >> 3) * 32 + (row & 7) * 4 + (r & 3); }
 
 // relu masks of half a row (28 units) as sign bits: bit (31 - i) = sign of v[i]
 __device__ __forceinline__ uint32_t sign_mask28(const float (&v)[28]) {
@@ -412,10 +438,24 @@ __device__ __forceinline__ f4 ld_scratch(const f4* ptr, uint64_t pol) {
     return v;
 }
 
+// XW_TC_PROF (tools/tc_prof.py builds a separate library with it): SM cycles each role of k_vnet_tc_bwd3 spends in each of
+// its waits, summed over the CTAs -- which hand-off a role is actually blocked on.  Not compiled into the product library.
+#ifdef XW_TC_PROF
+__device__ unsigned long long g_tc_prof[8][8];
+#define XW_PF_DECL long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long pf_t0_ = clock64();
+#define XW_PF(slot, stmt) { const long long t_ = clock64(); stmt; pf_[slot] += clock64() - t_; }
+#define XW_PF_END(role) { pf_[7] = clock64() - pf_t0_; for (int s_ = 0; s_ < 8; ++s_) atomicAdd(&g_tc_prof[role][s_], (unsigned long long)pf_[s_]); }
+#else
+#define XW_PF_DECL
+#define XW_PF(slot, stmt) { stmt; }
+#define XW_PF_END(role) {}
+#endif
+
 __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int C = a.d + 1, kin = kin_of(a.d), GS = KP + kin;
+    const int C = a.d + 1, kin = kin_of(a.d), GS = KP + kin + 1;     // (odd row stride: the per-row flushes hit 32 banks)
     const VLayout g(a.d, a.Hvr);
+    const P3Cols tc = p3_cols(kin, a.tm_packed);
     WImages w;
     w.wh_hi = reinterpret_cast<float*>(smem_raw);
     w.wh_lo = w.wh_hi + KP * NP;
@@ -424,11 +464,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     w.wi_hi = w.wht_lo + KP * NP;
     w.wi_lo = w.wi_hi + kin * NP;
     w.wz = w.wi_lo + kin * NP;
-    float* dT_hi = w.wz + 64;
-    float* dT_lo = dT_hi + TIMG;
-    float* rT_hi = dT_lo + TIMG;
-    float* rT_lo = rT_hi + TIMG;
-    float* gimg = rT_lo + TIMG;                                  // [56][GS] (+512: overrun pad of the M = 128 reads)
+    float* dT = w.wz + 64;                                       // stacked image of delta_k   (A operand of the P-op)
+    float* rT = dT + TIMG2;                                      // stacked image of (r_{k-1} | 1) / (t, x, 1)   (B operand)
+    float* gimg = rT + TIMG2;                                    // [56][GS] (+512: overrun pad of the M = 128 reads)
     float* zacc = gimg + KP * GS + 512;                          // [64] dWz | dbz
     float* vex = zacc + 64;                                      // [2][128] partial output dot products of the two F column halves
     uint64_t* mb = reinterpret_cast<uint64_t*>(vex + 256);
@@ -438,7 +476,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     uint32_t* slot = reinterpret_cast<uint32_t*>(mb + 12);
     // roles: F = warps 0-7 (two warps per lane quadrant, 28 columns each), R = warps 8-11, P = warps 12-15
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid < 256 ? 0 : (tid >> 7) - 1, j = tid & 127;
-    for (int i = tid; i < 4 * TIMG + KP * GS + 512 + 64; i += blockDim.x) dT_hi[i] = 0.f;
+    for (int i = tid; i < 2 * TIMG2 + KP * GS + 512 + 64; i += blockDim.x) dT[i] = 0.f;
     stage_images(w, a.theta, a.d, a.Hvr, kin);
     if (tid == 0) {
         umma::mbar_init(mF, 1); umma::mbar_init(mR, 1); umma::mbar_init(mPh, 1); umma::mbar_init(mPh + 1, 1);
@@ -452,9 +490,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     const uint32_t lane_addr = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
     const uint32_t idesc = umma::idesc_tf32(128, NP);
     const int hh_ = j >> 6;                                      // which 64-point half this thread's row belongs to
-    // weight-gradient MMAs: M = 64 (56 output units): half the shared-memory operand reads of M = 128;
-    // accumulator row o lands in tensor-memory lane 32 * (o / 16) + o % 16
-    const uint32_t idesc_p = umma::idesc_tf32(64, NP), idesc_pin = umma::idesc_tf32(64, kin);
+    // weight-gradient MMAs on the stacked images: M = 128 (delta_hi rows | delta_lo rows), N = 112 (r_hi | r_lo); accumulator
+    // row m lands in tensor-memory lane m
+    const uint32_t idesc_p = umma::idesc_tf32(128, 2 * NP), idesc_pin = umma::idesc_tf32(128, kin);
     const long long npts = (long long)a.n * a.L;
     const long long ntiles = (npts + 127) / 128;
     const int L = a.L, nv = a.nv, nvs = nv > 0 ? nv : 1;
@@ -468,6 +506,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
         const float k0 = (float)a.coefs[0], k1 = (float)a.coefs[1], k2 = (float)a.coefs[2];
         uint32_t pF = 0, pFC = 0, pPC = 0;
         int it = 0;
+        XW_PF_DECL
         float gwz[28], gbz = 0.f;                                 // dWz | dbz of this thread's row and units, over all its tiles
 #pragma unroll
         for (int i = 0; i < 28; ++i) gwz[i] = 0.f;
@@ -490,25 +529,25 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     hi[e] = umma::tf32_hi(v);
                     lo[e] = v - hi[e];
                 }
-                umma::tmem_st8(lane_addr + P3_AF + c8, hi);
-                umma::tmem_st8(lane_addr + P3_AF + KP + c8, lo);
+                umma::tmem_st8(lane_addr + tc.AF + c8, hi);
+                umma::tmem_st8(lane_addr + tc.AF + KP + c8, lo);
             }
             umma::tmem_wait_st();
             umma::fence_before();
             if (it > 0) {                                         // R has taken the previous tile out of the mailbox,
-                mbar_wait_or_trap(mFC, pFC);                      // and P has seen its activations land
-                mbar_wait_or_trap(mPC, pPC);
+                XW_PF(0, mbar_wait_or_trap(mFC, pFC))             // and P has seen its activations land
+                XW_PF(0, mbar_wait_or_trap(mPC, pPC))
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            XW_PF(1, asm volatile("bar.sync 1, 256;" ::: "memory"))
             if (tid == 0) {
                 umma::fence_after();
-                issue_3xtf32<0>(tbase + P3_DF, tbase + P3_AF, tbase + P3_AF + KP, w.wi_hi, w.wi_lo, kin / 8, idesc);
+                issue_3xtf32<0>(tbase + tc.DF, tbase + tc.AF, tbase + tc.AF + KP, w.wi_hi, w.wi_lo, kin / 8, idesc);
                 umma::commit(mF);
             }
             float h[28];
-            mbar_wait_or_trap(mF, pF);
+            XW_PF(2, mbar_wait_or_trap(mF, pF))
             umma::fence_after();
-            umma::tmem_ld28(lane_addr + P3_DF + cb, h);
+            umma::tmem_ld28(lane_addr + tc.DF + cb, h);
 #pragma unroll 1
             for (int layer = 0; layer < nv; ++layer) {
                 const uint32_t m = sign_mask28(h);
@@ -537,19 +576,18 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     rh[i] = __float_as_uint(v) & 0xFFFFE000u;
                     rl[i] = __float_as_uint(v - __uint_as_float(rh[i]));
                 }
-                umma::tmem_st28(lane_addr + P3_AF + cb, rh);
-                umma::tmem_st28(lane_addr + P3_AF + KP + cb, rl);
+                umma::tmem_st28(lane_addr + tc.AF + cb, rh);
+                umma::tmem_st28(lane_addr + tc.AF + KP + cb, rl);
                 umma::tmem_wait_st();
                 umma::fence_before();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                XW_PF(3, asm volatile("bar.sync 1, 256;" ::: "memory"))
                 if (tid == 0) {
                     umma::fence_after();
-                    issue_3xtf32<KP / 8>(tbase + P3_DF, tbase + P3_AF, tbase + P3_AF + KP, w.wh_hi, w.wh_lo, 0, idesc);
-                    umma::commit(mF);
+                    XW_PF(6, issue_3xtf32<KP / 8>(tbase + tc.DF, tbase + tc.AF, tbase + tc.AF + KP, w.wh_hi, w.wh_lo, 0, idesc); umma::commit(mF))
                 }
-                mbar_wait_or_trap(mF, pF);
+                XW_PF(4, mbar_wait_or_trap(mF, pF))
                 umma::fence_after();
-                umma::tmem_ld28(lane_addr + P3_DF + cb, h);
+                umma::tmem_ld28(lane_addr + tc.DF + cb, h);
             }
             // output layer, cotangent G, dWz | dbz, delta_nv -> mailbox
             {
@@ -562,7 +600,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     }
                 }
                 vex[ch * 128 + j] = vp;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                XW_PF(5, asm volatile("bar.sync 1, 256;" ::: "memory"))
                 const float v = vex[j] + vex[128 + j] + w.wz[KP];
                 float G = 0.f;
                 if (valid) {
@@ -580,12 +618,14 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                         r[i] = __float_as_uint(G * w.wz[cb + i] * (1.f - t * t));
                     }
                 }
-                umma::tmem_st28(lane_addr + P3_DF + cb, r);
+                umma::tmem_st28(lane_addr + tc.DF + cb, r);
                 umma::tmem_wait_st();
                 umma::fence_before();
                 umma::mbar_arrive(mFD);
             }
         }
+        if (tid == 0) XW_PF_END(0)
+        if (tid == 32) XW_PF_END(4)
         // per-thread dWz | dbz -> the CTA's accumulators (once per kernel)
 #pragma unroll
         for (int i = 0; i < 28; ++i) {
@@ -605,33 +645,33 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
         uint32_t pR = 0, pFD = 0, pPr = 0;
         bool published = false;
         int it = 0;
+        XW_PF_DECL
         for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, ++it) {
             const f4* sb = scr + (size_t)(it & 1) * nvs * 14 * 128;
             float h[KP];
-            mbar_wait_or_trap(mFD, pFD);
+            XW_PF(0, mbar_wait_or_trap(mFD, pFD))
             umma::fence_after();
-            umma::tmem_ld56(lane_addr + P3_DF, h);
+            umma::tmem_ld56(lane_addr + tc.DF, h);
             umma::fence_before();
             umma::mbar_arrive(mFC);
 #pragma unroll 1
             for (int k = nv; k >= 0; --k) {
                 if (k > 0) {                                     // R-op first: it does not depend on the images
-                    store_a_row_chunked(lane_addr + P3_AR, lane_addr + P3_AR + KP, h);
+                    store_a_row_chunked(lane_addr + tc.AR, lane_addr + tc.AR + KP, h);
                     umma::tmem_wait_st();
                     umma::fence_before();
-                    umma::group_sync(2);
+                    XW_PF(1, umma::group_sync(2))
                     if (j == 0) {
                         umma::fence_after();
-                        issue_3xtf32<KP / 8>(tbase + P3_DR, tbase + P3_AR, tbase + P3_AR + KP, w.wht_hi, w.wht_lo, 0, idesc);
-                        umma::commit(mR);
+                        XW_PF(6, issue_3xtf32<KP / 8>(tbase + tc.DR, tbase + tc.AR, tbase + tc.AR + KP, w.wht_hi, w.wht_lo, 0, idesc); umma::commit(mR))
                     }
                 }
-                if (published) mbar_wait_or_trap(mPh + hh_, pPr);   // this half's P-op on the previous delta image is done
+                if (published) XW_PF(2, mbar_wait_or_trap(mPh + hh_, pPr))   // this half's P-op on the previous delta image is done
 #pragma unroll
                 for (int o = 0; o < HV; ++o) {
                     const float hi = umma::tf32_hi(h[o]);
-                    dT_hi[th_off(o, j)] = hi;
-                    dT_lo[th_off(o, j)] = h[o] - hi;
+                    dT[ts_off(o, j)] = hi;
+                    dT[ts_off(KP + o, j)] = h[o] - hi;
                 }
                 umma::fence_smem_to_async();
                 umma::mbar_arrive(mDPh + hh_);
@@ -650,21 +690,24 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 }
                 const f4 mv = ld_scratch(sb + (size_t)((k - 1) * 14 + 13) * 128, pol);
                 const uint32_t m0 = __float_as_uint(mv.x), m1 = __float_as_uint(mv.y);
-                mbar_wait_or_trap(mR, pR);
+                XW_PF(3, mbar_wait_or_trap(mR, pR))
                 umma::fence_after();
-                umma::tmem_ld56(lane_addr + P3_DR, h);
+                umma::tmem_ld56(lane_addr + tc.DR, h);
                 umma::fence_before();
                 apply_sign_masks_2x28(h, m0, m1);
 #pragma unroll
                 for (int o = HV; o < KP; ++o) h[o] = 0.f;
             }
         }
+        if (j == 0) XW_PF_END(1)
+        if (j == 32) XW_PF_END(5)
     } else {
         // ======================================================================== P: weight gradients
         uint32_t pP = 0, pDP = 0, pFDp = 0;
         bool pending = false;
         int it = 0;
-        zero_acc(lane_addr, kin);
+        XW_PF_DECL
+        zero_acc(lane_addr + tc.WH, lane_addr + tc.WI, kin);
         umma::tmem_wait_st();
         umma::fence_before();
         umma::group_sync(3);
@@ -676,7 +719,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
             const float* xr = a.p.x + n * a.p.x_sn + (long long)l * a.p.x_sl;
             const float tval = valid ? a.p.t[n * a.p.t_sn + (long long)l * a.p.t_sl] : 0.f;
             const f4* sb = scr + (size_t)(it & 1) * nvs * 14 * 128;
-            mbar_wait_or_trap(mFD, pFDp);                      // F's scratch writes of this tile are visible from here on
+            XW_PF(0, mbar_wait_or_trap(mFD, pFDp))             // F's scratch writes of this tile are visible from here on
             umma::mbar_arrive(mPC);                            // (F may not finish the NEXT tile before P has seen this one)
 #pragma unroll 1
             for (int k = nv; k >= 0; --k) {
@@ -686,7 +729,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
 #pragma unroll
                     for (int c = 0; c < 13; ++c) rv4[c] = ld_scratch(sb + (size_t)((k - 1) * 14 + c) * 128, pol);
                 }
-                if (pending) { mbar_wait_or_trap(mPh + hh_, pP); pending = false; }     // this half's images are free again
+                if (pending) { XW_PF(1, mbar_wait_or_trap(mPh + hh_, pP)) pending = false; }     // this half's images are free again
                 if (k > 0) {
 #pragma unroll
                     for (int c = 0; c < 13; ++c) {
@@ -696,66 +739,93 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                             const int o = 4 * c + e;
                             if (o < HV) {
                                 const float hi = umma::tf32_hi(rv[e]);
-                                rT_hi[th_off(o, j)] = hi;
-                                rT_lo[th_off(o, j)] = rv[e] - hi;
+                                rT[ts_off(o, j)] = hi;
+                                rT[ts_off(KP + o, j)] = rv[e] - hi;
                             }
                         }
                     }
-                    rT_hi[th_off(BIASC, j)] = 1.f; rT_lo[th_off(BIASC, j)] = 0.f;
+                    rT[ts_off(BIASC, j)] = 1.f; rT[ts_off(KP + BIASC, j)] = 0.f;
+                    if (kin > BIASC + 1) {                    // (rows a wide input layer of the previous tile has written)
 #pragma unroll
-                    for (int o = BIASC + 1; o < KP; ++o) { rT_hi[th_off(o, j)] = 0.f; rT_lo[th_off(o, j)] = 0.f; }
+                        for (int o = BIASC + 1; o < KP; ++o) { rT[ts_off(o, j)] = 0.f; rT[ts_off(KP + o, j)] = 0.f; }
+                    }
                 } else {
 #pragma unroll 1
                     for (int c = 0; c < kin; ++c) {
                         float v = 0.f;
                         if (valid) v = c == 0 ? tval : (c <= a.d ? __ldcs(xr + c - 1) : (c == C ? 1.f : 0.f));
                         const float hi = umma::tf32_hi(v);
-                        rT_hi[th_off(c, j)] = hi;
-                        rT_lo[th_off(c, j)] = v - hi;
+                        rT[ts_off(c, j)] = hi;
+                        rT[ts_off(KP + c, j)] = v - hi;
                     }
                 }
                 umma::fence_smem_to_async();
-                mbar_wait_or_trap(mDPh + hh_, pDP);            // R has written this half's delta_k image
-                asm volatile("bar.sync %0, 64;" ::"r"(4 + hh_) : "memory");       // the 64 threads of this half
+                XW_PF(2, mbar_wait_or_trap(mDPh + hh_, pDP))   // R has written this half's delta_k image
+                XW_PF(3, asm volatile("bar.sync %0, 64;" ::"r"(4 + hh_) : "memory"))       // the 64 threads of this half
                 if ((j & 63) == 0) {
                     umma::fence_after();
-                    const int ho = hh_ * THALF;
-                    issue_pop_half(tbase + (k > 0 ? P3_WH : P3_WI), dT_hi + ho, dT_lo + ho, rT_hi + ho, rT_lo + ho, k > 0 ? idesc_p : idesc_pin);
-                    umma::commit(mPh + hh_);
+                    const int ho = hh_ * THALF2;
+                    XW_PF(6, if (k > 0) issue_pop_half_stacked(tbase + tc.WH, dT + ho, rT + ho, idesc_p);
+                             else issue_pop_half_in(tbase + tc.WI, dT + ho, rT + ho, idesc_pin);
+                             umma::commit(mPh + hh_))
                 }
                 pending = true;
             }
-            mbar_wait_or_trap(mPh + hh_, pP);
+            XW_PF(4, mbar_wait_or_trap(mPh + hh_, pP))
             pending = false;
+#ifdef XW_TC_PROF
+            const long long tfl_ = clock64();
+#endif
             umma::group_sync(3);                                  // both halves' last P-ops are complete
             umma::fence_after();
-            {                                                     // lanes 0..15 of warp q hold accumulator rows 16 q + lane
-                const int orow = 16 * (warp & 3) + lane;
-                const bool has = lane < 16 && orow < KP;
-                float* grow = gimg + (has ? orow : 0) * GS;
+            {
+                // accumulator lane m = image row m: lanes 0..55 hold the delta_hi rows, lanes 56..111 the delta_lo rows of the
+                // 56 output units; columns [0, 56) the r_hi block, [56, 112) the r_lo block.  Each thread sums its two
+                // column blocks; the hi-row owners add into the CTA's gradient image first, the lo-row owners second.
+                const bool row_hi = j < KP, row_lo = j >= KP && j < 2 * KP;
+                float* grow = gimg + (row_hi ? j : (row_lo ? j - KP : 0)) * GS;
                 float acc[KP];
-                umma::tmem_ld56(lane_addr + P3_WH, acc);
-                if (has && nv > 0) {
 #pragma unroll
-                    for (int i = 0; i < KP; ++i) grow[i] += acc[i];
+                for (int c8 = 0; c8 < KP; c8 += 8) {              // (8 columns at a time: two full rows would not fit the registers)
+                    float a8[8], b8[8];
+                    umma::tmem_ld8(lane_addr + tc.WH + c8, a8);
+                    umma::tmem_ld8(lane_addr + tc.WH + KP + c8, b8);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[c8 + e] = a8[e] + b8[e];
                 }
 #pragma unroll 1
-                for (int c8 = 0; c8 < kin; c8 += 8) {
-                    float a8[8];
-                    umma::tmem_ld8(lane_addr + P3_WI + c8, a8);
-                    if (has) {
+                for (int pass = 0; pass < 2; ++pass) {
+                    const bool mine = pass == 0 ? row_hi : row_lo;
+                    if (mine && nv > 0) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) grow[KP + c8 + e] += a8[e];
+                        for (int i = 0; i < KP; ++i) grow[i] += acc[i];
                     }
+#pragma unroll 1
+                    for (int c8 = 0; c8 < kin; c8 += 8) {
+                        float a8[8];
+                        umma::tmem_ld8(lane_addr + tc.WI + c8, a8);
+                        if (mine) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) grow[KP + c8 + e] += a8[e];
+                        }
+                    }
+                    umma::group_sync(3);
                 }
                 // every P-op accumulates (two issuers, no defined first MMA): clear the accumulators for the next tile
-                zero_acc(lane_addr, kin);
+                zero_acc(lane_addr + tc.WH, lane_addr + tc.WI, kin);
             }
             umma::tmem_wait_st();
             umma::fence_before();
             umma::group_sync(3);
             umma::fence_before();
+#ifdef XW_TC_PROF
+            pf_[5] += clock64() - tfl_;
+#endif
         }
+        if (j == 0) XW_PF_END(2)
+        if (j == 64) XW_PF_END(3)
+        if (j == 32) XW_PF_END(6)
+        if (j == 96) XW_PF_END(7)
     }
     umma::fence_before();
     __syncthreads();

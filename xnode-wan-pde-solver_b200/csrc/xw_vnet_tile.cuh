@@ -365,6 +365,7 @@ struct VtileBwdArgs {
     // coordinates are not the spatial ones) and the cotangent of the first pre-activation dumped per point
     const float* wbuf;       // optional [n*L]
     float* delta0_out;       // optional [n*L][52]
+    int tm_packed;           // k_vnet_tc_bwd3: force the fully packed tensor-memory layout (test hook, XW_TC_TMEM_PACKED=1)
 };
 
 template <int HV, int QR>
