@@ -163,7 +163,8 @@ def test_single_time_group_matches_golden_on_gpu(name):
             assert G.rel(a, b) < 1e-6 or np.linalg.norm(b) == 0.0
 
 
-@pytest.mark.parametrize("name", ["pad_cube_d3_rk4", "pad_cube_d5_midpoint", "pad_cone_d5"])
+@pytest.mark.parametrize("name", ["pad_cube_d3_rk4", "pad_cube_d5_midpoint", "pad_cone_d5", "pad_hourglass_d5_early",
+                                  "pad_hourglass_d5_late", "pad_hourglass_d5_late_onbdry"])
 def test_evaluation_from_inside_the_domain_on_gpu(name):
     """u_net(X) for paths that start inside the domain after T0 (bound_pad / fillt branch of the reference)"""
     import os
@@ -172,6 +173,7 @@ def test_evaluation_from_inside_the_domain_on_gpu(name):
     s, _ = make_solver(case, DEV)
     with torch.no_grad():
         u = s.u_net(torch.from_numpy(z["X"]).to(DEV))
+    assert u.shape == z["u"].shape + (1,)
     assert np.abs(u.cpu().numpy()[..., 0] - z["u"]).max() < 2e-5
 
 

@@ -284,7 +284,29 @@ def test_product_library_carries_tcgen05_code():
         assert mnemonic in sass, mnemonic
 
 
-@pytest.mark.parametrize("name", ["pad_cube_d3_rk4", "pad_cube_d5_midpoint", "pad_cone_d5"])
+PAD_CASES = ["pad_cube_d3_rk4", "pad_cube_d5_midpoint", "pad_cone_d5", "pad_hourglass_d5_early", "pad_hourglass_d5_late",
+             "pad_hourglass_d5_late_onbdry"]
+
+
+@pytest.mark.parametrize("name", PAD_CASES[3:])
+def test_hourglass_bound_pad_builds_the_reference_groups(name):
+    """per-path entry times, filled grids, grouping by grid length and the first-path-represents-the-group rule of the
+    reference's hourglass bound_pad (src/dataset.py:127-152); groups / positions / grids stored by the unmodified
+    reference (tests/golden/make_pad_golden.py)"""
+    z = np.load(os.path.join(G.GOLDEN_DIR, "extra", name + ".npz"))
+    case = G.load(str(z["base"]))
+    s, _ = make_solver_for_rng(case)
+    dom = s.new_domain()
+    dom.times = torch.from_numpy(z["dom_times"])
+    path_i, pos, grids = dom.bound_pad(torch.from_numpy(z["X"]))
+    assert len(grids) == int(z["n_groups"])
+    assert np.array_equal(np.concatenate([q.numpy() for q in path_i]), z["order"])
+    for k in range(len(grids)):
+        assert np.array_equal(pos[k].numpy(), z["pos%d" % k])
+        assert np.allclose(grids[k].numpy(), z["grid%d" % k], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", PAD_CASES)
 def test_evaluation_from_inside_the_domain_matches_reference(emu, name):
     """u_net(X) for paths that start inside the domain after T0: the reference pads the time grid back to T0 and
     fills the gaps (bound_pad / fillt, src/model.py:92-94, src/dataset.py:13-32); golden vectors from the unmodified
@@ -294,7 +316,7 @@ def test_evaluation_from_inside_the_domain_matches_reference(emu, name):
     s, _ = make_solver(case)
     with torch.no_grad():
         u = s.u_net(torch.from_numpy(z["X"]))
-    assert u.shape == z["X"].shape[:2] + (1,)
+    assert u.shape == z["u"].shape + (1,)       # (the early-time hourglass batch also returns u at T0: reference quirk)
     assert np.abs(u.numpy()[..., 0] - z["u"]).max() < 2e-5
 
 

@@ -1,0 +1,12 @@
+#!/bin/bash
+# flush-every-4 + stacked P-op + hourglass bound_pad: full GPU suite (+ flush 1 and packed layout on the v-net tests), bench
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+XW_TC_FLUSH=1 XW_TC_TMEM_PACKED=1 timeout 600 python -m pytest tests/test_gpu_capi.py tests/test_gpu_tc.py -m gpu -x -q 2>&1 | tail -3
+timeout 500 python bench.py --steps 5 --warmup 3 --no-cpu --no-ttt > gpurun_out/r02aa_bench.json 2> gpurun_out/r02aa_bench.err; echo rc=$?
+python - <<'PY'
+import json
+for f in ("r02aa_bench",):
+    try:
+        j=json.load(open("gpurun_out/%s.json" % f)); print(f, round(j["ms_per_step"],2), "%.4g"%j["value"], j["e2e"]["ms_per_step"], {k:round(v,2) for k,v in j["kernels_ms_per_call"].items()})
+    except Exception as e: print(f, "ERR", e)
+PY

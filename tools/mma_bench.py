@@ -20,3 +20,15 @@ for mode, M, N, a_rows in ((0, 128, 56, 128), (0, 128, 112, 128), (0, 128, 24, 1
         rows.append({"mode": "TS" if mode == 0 else "SS", "M": M, "N": N, "nacc": nacc, "floor": max(M, 128) * N / 256,
                      "issue_cyc_per_mma": round(o[4] / count, 1), "done_cyc_per_mma": round(o[5] / count, 1)})
         print(rows[-1], flush=True)
+
+# several issuing warps at once: total MMAs / cycles
+lib.tcb_mma_bench_multi.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+for N in (24, 56, 112):
+    for nissue in (1, 2, 3, 4):
+        if nissue * N > 440:
+            continue
+        out.zero_()
+        assert lib.tcb_mma_bench_multi(128, N, nissue, count, out.data_ptr(), st) == 0
+        torch.cuda.synchronize()
+        o = out.cpu().tolist()
+        print({"multi_issuer": nissue, "N": N, "floor": 128 * N / 256, "cyc_per_mma_overall": round(max(o[:nissue]) / (count * nissue), 1)}, flush=True)

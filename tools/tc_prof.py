@@ -17,10 +17,11 @@ PKG = os.path.join(ROOT, "xnode-wan-pde-solver_b200")
 TCB = os.path.join(ROOT, "tools", "tcb")
 
 _F = ["prev tile consumed (mFC, mPC)", "bar: input operand stored", "mF input-layer MMAs", "bar: layer operand stored",
-      "mF hidden-layer MMAs", "bar: output dot", "MMA issue", "total"]
-_R = ["mFD (F's delta_nv)", "bar: A_r stored", "mPh (P done with the delta image)", "mR R-op MMAs", "-", "-", "MMA issue", "total"]
+      "mF hidden-layer MMAs", "bar: output dot", "MMA issue", "total", "tmem_ld28", "tmem_st A_f + wait::st", "-", "-"]
+_R = ["mFD (F's delta_nv)", "bar: A_r stored", "mPh (P done with the delta image)", "mR R-op MMAs", "-", "-", "MMA issue", "total",
+      "split + tmem_st A_r + wait::st", "delta image STS + fence", "tmem_ld56", "apply masks"]
 _P = ["mFD (F's tile)", "mPh own previous P-op", "mDPh delta image", "bar: half images stored", "mPh tile end", "flush",
-      "MMA issue", "total"]
+      "MMA issue", "total", "r image STS + fence", "-", "-", "-"]
 SLOTS = {"F issuer": _F, "R issuer": _R, "P half 0 issuer": _P, "P half 1 issuer": _P,
          "F warp 1": _F, "R warp 1": _R, "P half 0 warp 1": _P, "P half 1 warp 3": _P}
 
@@ -37,7 +38,7 @@ def build():
         print(os.path.join(TCB, name))
 
 
-def run(log2n=20, d=20, L=20, reps=3, packed=0):
+def run(log2n=20, d=20, L=20, reps=3, packed=0, flush=4):
     import numpy as np
     import torch
     dev = torch.device("cuda:0")
@@ -52,23 +53,23 @@ def run(log2n=20, d=20, L=20, reps=3, packed=0):
     kv = torch.tensor([1e-3, 1e-3, 1.0], dtype=torch.float64, device=dev)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     st = torch.cuda.current_stream().cuda_stream
-    out = {"log2n": log2n, "dim": d, "packed": packed}
+    out = {"log2n": log2n, "dim": d, "packed": packed, "flush_tiles": flush}
     for name in ("libtcb.so", "libtcb_prof.so"):
         lib = C.CDLL(os.path.join(TCB, name))
         lib.tcb_workspace_bytes.restype = C.c_size_t
         lib.tcb_run.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
-                                               C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+                                               C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         ws = torch.zeros(lib.tcb_workspace_bytes(d, Hv, nv, sms), dtype=torch.uint8, device=dev)
 
         def call():
             rc = lib.tcb_run(d, Hv, nv, n, L, thv.data_ptr(), times.data_ptr(), 0, 1, x.data_ptr(), d, 0, cot.data_ptr(),
-                             kv.data_ptr(), ws.data_ptr(), packed, st)
+                             kv.data_ptr(), ws.data_ptr(), packed, flush, None, st)
             assert rc == 0
         for _ in range(2):
             call()
         torch.cuda.synchronize()
         prof = name.endswith("prof.so")
-        buf = (C.c_ulonglong * 64)()
+        buf = (C.c_ulonglong * 96)()
         if prof:
             lib.tcb_prof_read(C.cast(buf, C.c_void_p))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -83,19 +84,77 @@ def run(log2n=20, d=20, L=20, reps=3, packed=0):
             continue
         out["ms_per_call_instrumented"] = ms
         lib.tcb_prof_read(C.cast(buf, C.c_void_p))
-        v = np.array(list(buf), dtype=np.float64).reshape(8, 8)
+        v = np.array(list(buf), dtype=np.float64).reshape(8, 12)
         ntiles = (n * L + 127) // 128
         out["tiles_per_cta"] = ntiles / sms
         out["roles"] = {}
         for r, rname in enumerate(SLOTS):
             tot = v[r, 7]
             out["roles"][rname] = {"cycles_per_tile": round(tot / reps / ntiles, 1),
-                                   "wait_share": {SLOTS[rname][s]: round(v[r, s] / tot, 4) for s in range(7) if SLOTS[rname][s] != "-"}}
+                                   "wait_share": {SLOTS[rname][s]: round(v[r, s] / tot, 4) for s in range(12) if s != 7 and SLOTS[rname][s] != "-"}}
     print(json.dumps(out, indent=1))
+
+
+def acc(log2n=18, d=20, L=20, flushes=(1, 2, 4, 8, 1 << 30)):
+    """gradient of the kernel (per-CTA partials summed in fp64) against a PyTorch fp64 autograd evaluation of the same net
+    on the same points, per parameter tensor (rel-L2), for several flush intervals of the weight-gradient accumulators"""
+    import torch
+    dev = torch.device("cuda:0")
+    n = 1 << log2n
+    Hv, nv, Cc = 50, 9, d + 1
+    g = torch.Generator(device=dev).manual_seed(1)
+    sizes = [("Wi", Hv * Cc), ("bi", Hv), ("Wh", Hv * Hv), ("bh", Hv), ("Wz", Hv), ("bz", 1)]
+    Pv = sum(k for _, k in sizes)
+    thv = (torch.rand(Pv, device=dev, generator=g) - 0.5) * 0.35
+    x = torch.rand(n, d, device=dev, generator=g) * 2 - 1
+    times = torch.sort(torch.rand(L, device=dev, generator=g))[0].contiguous()
+    cot = torch.randn(n * L, device=dev, generator=g)
+    k0, k1 = 1e-3, 2e-3
+    kv = torch.tensor([k0, k1, 0.0], dtype=torch.float64, device=dev)
+    # fp64 reference, in chunks of paths
+    th = thv.double().requires_grad_(True)
+    parts, o = {}, 0
+    for name, k in sizes:
+        parts[name] = th[o:o + k]; o += k
+    Wi, Wh = parts["Wi"].view(Hv, Cc), parts["Wh"].view(Hv, Hv)
+    ref = torch.zeros(Pv, dtype=torch.float64, device=dev)
+    ch = 1 << 14
+    for s0 in range(0, n, ch):
+        xs = x[s0:s0 + ch].double()
+        pts = torch.cat((times.double().view(1, L, 1).expand(xs.shape[0], L, 1), xs.unsqueeze(1).expand(-1, L, -1)), 2).reshape(-1, Cc)
+        a = pts @ Wi.T + parts["bi"]
+        for _ in range(nv):
+            a = torch.relu(a) @ Wh.T + parts["bh"]
+        v = torch.tanh(a) @ parts["Wz"] + parts["bz"]
+        G = (k0 * cot[s0 * L:(s0 + xs.shape[0]) * L].double() + k1 * v).detach()
+        ref += torch.autograd.grad((G * v).sum(), th)[0]
+    lib = C.CDLL(os.path.join(TCB, "libtcb.so"))
+    lib.tcb_workspace_bytes.restype = C.c_size_t
+    lib.tcb_run.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
+                                           C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    ws = torch.zeros(lib.tcb_workspace_bytes(d, Hv, nv, sms), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    res = {"log2n": log2n, "dim": d, "tiles_per_cta": (n * L + 127) // 128 / sms, "rel_l2_vs_fp64": {}}
+    for fl in flushes:
+        gv = torch.zeros(Pv, device=dev)
+        rc = lib.tcb_run(d, Hv, nv, n, L, thv.data_ptr(), times.data_ptr(), 0, 1, x.data_ptr(), d, 0, cot.data_ptr(),
+                         kv.data_ptr(), ws.data_ptr(), 0, fl, gv.data_ptr(), st)
+        assert rc == 0
+        torch.cuda.synchronize()
+        e, o = {}, 0
+        for name, k in sizes:
+            r_ = ref[o:o + k]
+            e[name] = float((gv[o:o + k].double() - r_).norm() / r_.norm()); o += k
+        res["rel_l2_vs_fp64"]["flush_every_%s" % ("never" if fl >= 1 << 30 else fl)] = e
+    print(json.dumps(res, indent=1))
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "build":
         build()
+    elif len(sys.argv) > 1 and sys.argv[1] == "acc":
+        acc(*(int(a) for a in sys.argv[2:4]))
     else:
-        run(*(int(a) for a in sys.argv[1:3]), packed=int(os.environ.get("XW_TC_TMEM_PACKED", "0")))
+        run(*(int(a) for a in sys.argv[1:3]), packed=int(os.environ.get("XW_TC_TMEM_PACKED", "0")),
+            flush=int(os.environ.get("XW_TC_FLUSH", "4")))

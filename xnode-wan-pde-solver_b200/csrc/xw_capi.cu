@@ -175,6 +175,12 @@ int plan_vtile_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
 // tensor-core backward: one 128-point tile per CTA iteration, one CTA per SM (tensor memory: 512 columns)
 // test hook: XW_TC_TMEM_PACKED=1 runs k_vnet_tc_bwd3 on the fully packed tensor-memory layout for every input width
 // (the layout kin = 56 needs anyway), so that the parity tests of the narrow configs cover it too
+// tiles per flush of k_vnet_tc_bwd3's weight-gradient accumulators (tensor memory -> the CTA's fp32 image).  The tensor core
+// truncates when it accumulates, so the error of dWh grows linearly with the number of tiles summed in one accumulator
+// (measured against fp64 at 2^20 paths, tools/tc_prof.py acc: 4.4e-6 / 6.8e-6 / 1.2e-5 / 2.1e-5 rel-L2 at 1 / 2 / 4 / 8
+// tiles, 2.7e-3 without flushing); 4 keeps it at the level of the other tensors (dWi 8.6e-6) and takes the flush off the
+// critical path (26.8 -> 25.2 ms).  XW_TC_FLUSH overrides (tests).
+int tc_flush_tiles() { static const int v = []() { const char* e = getenv("XW_TC_FLUSH"); const int k = e ? atoi(e) : 4; return k > 0 ? k : 4; }(); return v; }
 int tc_tmem_packed() { static const int v = []() { const char* e = getenv("XW_TC_TMEM_PACKED"); return e && e[0] == '1' ? 1 : 0; }(); return v; }
 bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
 int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
@@ -738,7 +744,7 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
         t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
         t.cot = cot_v; t.coefs = coefs_dev; t.scratch = (float*)workspace; t.gpart = (float*)((char*)workspace + pl.scratch_bytes);
-        t.tm_packed = tc_tmem_packed();
+        t.tm_packed = tc_tmem_packed(); t.flush_tiles = tc_flush_tiles();
         if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, pl.smem)) return 1;
         xw::tc::k_vnet_tc_bwd3<<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
         if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
@@ -773,7 +779,7 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         t.p.t = xv->t; t.p.t_sn = xv->t_sn; t.p.t_sl = xv->t_sl; t.p.x = y; t.p.x_sn = m->Hv; t.p.x_sl = 0;
         t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
         t.cot = cot_v; t.coefs = coefs_dev; t.scratch = scratch; t.gpart = gpart; t.wbuf = wbuf; t.delta0_out = d0;
-        t.tm_packed = tc_tmem_packed();
+        t.tm_packed = tc_tmem_packed(); t.flush_tiles = tc_flush_tiles();
         if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, vp.pl.smem)) return 1;
         xw::tc::k_vnet_tc_bwd3<<<vp.pl.grid, 512, vp.pl.smem, (cudaStream_t)stream>>>(t);
         if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;

@@ -441,10 +441,10 @@ __device__ __forceinline__ f4 ld_scratch(const f4* ptr, uint64_t pol) {
 // XW_TC_PROF (tools/tc_prof.py builds a separate library with it): SM cycles each role of k_vnet_tc_bwd3 spends in each of
 // its waits, summed over the CTAs -- which hand-off a role is actually blocked on.  Not compiled into the product library.
 #ifdef XW_TC_PROF
-__device__ unsigned long long g_tc_prof[8][8];
-#define XW_PF_DECL long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long pf_t0_ = clock64();
+__device__ unsigned long long g_tc_prof[8][12];
+#define XW_PF_DECL long long pf_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long pf_t0_ = clock64();
 #define XW_PF(slot, stmt) { const long long t_ = clock64(); stmt; pf_[slot] += clock64() - t_; }
-#define XW_PF_END(role) { pf_[7] = clock64() - pf_t0_; for (int s_ = 0; s_ < 8; ++s_) atomicAdd(&g_tc_prof[role][s_], (unsigned long long)pf_[s_]); }
+#define XW_PF_END(role) { pf_[7] = clock64() - pf_t0_; for (int s_ = 0; s_ < 12; ++s_) atomicAdd(&g_tc_prof[role][s_], (unsigned long long)pf_[s_]); }
 #else
 #define XW_PF_DECL
 #define XW_PF(slot, stmt) { stmt; }
@@ -576,10 +576,10 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     rh[i] = __float_as_uint(v) & 0xFFFFE000u;
                     rl[i] = __float_as_uint(v - __uint_as_float(rh[i]));
                 }
-                umma::tmem_st28(lane_addr + tc.AF + cb, rh);
+                XW_PF(9, umma::tmem_st28(lane_addr + tc.AF + cb, rh);
                 umma::tmem_st28(lane_addr + tc.AF + KP + cb, rl);
                 umma::tmem_wait_st();
-                umma::fence_before();
+                umma::fence_before())
                 XW_PF(3, asm volatile("bar.sync 1, 256;" ::: "memory"))
                 if (tid == 0) {
                     umma::fence_after();
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 }
                 XW_PF(4, mbar_wait_or_trap(mF, pF))
                 umma::fence_after();
-                umma::tmem_ld28(lane_addr + tc.DF + cb, h);
+                XW_PF(8, umma::tmem_ld28(lane_addr + tc.DF + cb, h))
             }
             // output layer, cotangent G, dWz | dbz, delta_nv -> mailbox
             {
@@ -657,9 +657,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
 #pragma unroll 1
             for (int k = nv; k >= 0; --k) {
                 if (k > 0) {                                     // R-op first: it does not depend on the images
-                    store_a_row_chunked(lane_addr + tc.AR, lane_addr + tc.AR + KP, h);
+                    XW_PF(8, store_a_row_chunked(lane_addr + tc.AR, lane_addr + tc.AR + KP, h);
                     umma::tmem_wait_st();
-                    umma::fence_before();
+                    umma::fence_before())
                     XW_PF(1, umma::group_sync(2))
                     if (j == 0) {
                         umma::fence_after();
@@ -667,6 +667,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     }
                 }
                 if (published) XW_PF(2, mbar_wait_or_trap(mPh + hh_, pPr))   // this half's P-op on the previous delta image is done
+#ifdef XW_TC_PROF
+                const long long tim_ = clock64();
+#endif
 #pragma unroll
                 for (int o = 0; o < HV; ++o) {
                     const float hi = umma::tf32_hi(h[o]);
@@ -674,6 +677,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     dT[ts_off(KP + o, j)] = h[o] - hi;
                 }
                 umma::fence_smem_to_async();
+#ifdef XW_TC_PROF
+                pf_[9] += clock64() - tim_;
+#endif
                 umma::mbar_arrive(mDPh + hh_);
                 published = true;
                 if (k == 0) {
@@ -692,9 +698,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 const uint32_t m0 = __float_as_uint(mv.x), m1 = __float_as_uint(mv.y);
                 XW_PF(3, mbar_wait_or_trap(mR, pR))
                 umma::fence_after();
-                umma::tmem_ld56(lane_addr + tc.DR, h);
-                umma::fence_before();
-                apply_sign_masks_2x28(h, m0, m1);
+                XW_PF(10, umma::tmem_ld56(lane_addr + tc.DR, h);
+                umma::fence_before())
+                XW_PF(11, apply_sign_masks_2x28(h, m0, m1))
 #pragma unroll
                 for (int o = HV; o < KP; ++o) h[o] = 0.f;
             }
@@ -707,6 +713,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
         bool pending = false;
         int it = 0;
         XW_PF_DECL
+        const int flush_tiles = a.flush_tiles > 0 ? a.flush_tiles : 1;
         zero_acc(lane_addr + tc.WH, lane_addr + tc.WI, kin);
         umma::tmem_wait_st();
         umma::fence_before();
@@ -730,6 +737,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     for (int c = 0; c < 13; ++c) rv4[c] = ld_scratch(sb + (size_t)((k - 1) * 14 + c) * 128, pol);
                 }
                 if (pending) { XW_PF(1, mbar_wait_or_trap(mPh + hh_, pP)) pending = false; }     // this half's images are free again
+#ifdef XW_TC_PROF
+                const long long tim_ = clock64();
+#endif
                 if (k > 0) {
 #pragma unroll
                     for (int c = 0; c < 13; ++c) {
@@ -760,6 +770,9 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                     }
                 }
                 umma::fence_smem_to_async();
+#ifdef XW_TC_PROF
+                pf_[8] += clock64() - tim_;
+#endif
                 XW_PF(2, mbar_wait_or_trap(mDPh + hh_, pDP))   // R has written this half's delta_k image
                 XW_PF(3, asm volatile("bar.sync %0, 64;" ::"r"(4 + hh_) : "memory"))       // the 64 threads of this half
                 if ((j & 63) == 0) {
@@ -771,6 +784,10 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 }
                 pending = true;
             }
+            // The accumulators are flushed into the CTA's fp32 gradient image every `flush_tiles` tiles (and after the CTA's last
+            // tile): the flush is on the critical path of the R <-> P hand-off (about 1.6 layer times per flush), while
+            // a tensor-core accumulator may well sum a few tiles' worth of terms (accuracy measured: tools/tc_prof.py acc)
+            if ((it + 1) % flush_tiles != 0 && tix + gridDim.x < ntiles) continue;
             XW_PF(4, mbar_wait_or_trap(mPh + hh_, pP))
             pending = false;
 #ifdef XW_TC_PROF

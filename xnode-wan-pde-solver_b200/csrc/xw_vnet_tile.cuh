@@ -366,6 +366,7 @@ struct VtileBwdArgs {
     const float* wbuf;       // optional [n*L]
     float* delta0_out;       // optional [n*L][52]
     int tm_packed;           // k_vnet_tc_bwd3: force the fully packed tensor-memory layout (test hook, XW_TC_TMEM_PACKED=1)
+    int flush_tiles;         // k_vnet_tc_bwd3: tiles per flush of the weight-gradient accumulators (0 = 1)
 };
 
 template <int HV, int QR>

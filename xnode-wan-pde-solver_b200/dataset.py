@@ -256,8 +256,8 @@ class _SphereDomain:
         return groups
 
     def bound_pad(self, x):
-        raise NotImplementedError("bound_pad for the hourglass (per-path entry times, src/dataset.py:127-152) is not "
-                                  "supported: evaluate from inside the domain on the cube or the cone")
+        raise NotImplementedError("bound_pad of %s: evaluate from inside the domain on the cube, the cone or the hourglass"
+                                  % type(self).__name__)
 
 
 class NSphere_TCone(_SphereDomain):
@@ -372,6 +372,43 @@ class NSphere_THourglass(_SphereDomain):
         dist = x[:, :, 1:].pow(2).sum(2).sqrt()
         span = self.T - self.T0
         return torch.where(t <= span / 2, self.r * (span - t) - dist, self.r * t - dist)
+
+    def bound_pad(self, x):
+        """integration grids for a batch that starts inside the hourglass after T0 (reference src/dataset.py:127-152).
+        Unlike the cube and the cone the paths do not share one grid: a batch whose first time lies in the growing half
+        contains paths that were inside all along (|x| <= r (T-T0)/2: integrated from T0) and paths that entered at
+        t = |x| / r (integrated from there), so every path gets its own filled grid.  Paths are then ordered by the
+        LENGTH of their grid (stable) and paths of equal length form one group that is integrated on the grid -- and
+        read at the positions -- of its FIRST path (the reference keeps only `next(r)` of each group).  A path whose first
+        point already sits on the boundary (w <= 1e-5) keeps the prepended entry time in its grid but has its positions
+        computed without it (the reference's `t_[k][i[k]:]`).  Returns (path indices per group, positions per group,
+        grid per group); `NeuralODE` concatenates the groups in this order, as the reference does."""
+        n = x.shape[0]
+        times = x[:, :, 0]
+        half = (self.T - self.T0) / 2
+        if bool(x[0, 0, 0] < half):
+            start = torch.full_like(times[:, 0], self.T0)
+            on_bdry = None
+        else:
+            nrm = x[:, 0, 1:].pow(2).sum(-1).sqrt()
+            start = torch.where(nrm <= self.r * half, torch.full_like(nrm, self.T0), nrm / self.r)
+            on_bdry = (self.func_w(x[:, 0].unsqueeze(1)) <= 1e-5).reshape(-1)
+        seqs = torch.cat((start.unsqueeze(1), times), dim=1)
+        grids, poss = [], []
+        for k in range(n):
+            pos_k, grid_k = fillt(seqs[k], self.T, self.T0, self.N_t)
+            if on_bdry is not None:
+                pos_k = fillt(seqs[k][1:], self.T, self.T0, self.N_t)[0] if bool(on_bdry[k]) else pos_k[1:]
+            grids.append(grid_k)
+            poss.append(pos_k)
+        order = sorted(range(n), key=lambda k: grids[k].shape[0])
+        path_i, pos_g, grid_g = [], [], []
+        for k in order:
+            if grid_g and grids[k].shape[0] == grid_g[-1].shape[0]:
+                path_i[-1].append(k)
+            else:
+                path_i.append([k]); pos_g.append(poss[k]); grid_g.append(grids[k])
+        return [torch.tensor(q) for q in path_i], pos_g, grid_g
 
     def V(self):
         tc = 2 * ((1 - self.T0) ** (self.dim + 1) / (self.dim + 1) -

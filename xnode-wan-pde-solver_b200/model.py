@@ -211,7 +211,7 @@ class NeuralODE(nn.Module):
             raise NotImplementedError("evaluation from inside the domain takes the dense [N, L, C] layout")
         path_i, pos, grid = self.domain.bound_pad(inputs.detach())
         if path_i is not None:
-            raise NotImplementedError("per-path integration grids (hourglass bound_pad) are not supported")
+            return self._evaluate_grouped(inputs, path_i, pos, grid)
         if grid.numel() < 2 or int(pos.max()) >= grid.numel():
             raise RuntimeError("fillt produced a %d-point grid for the requested times (no gap larger than "
                                "(T - T0) / N_t between them): the reference fails on this input too" % grid.numel())
@@ -221,6 +221,24 @@ class NeuralODE(nn.Module):
         ts = hotpath.as_f32(grid.to(Xf.device))
         u = hotpath.xnode_eval(self.spec(), self.kernel_parameters(), Xf, 1, L * Cc, ts, s0, N)
         return u[:, pos.to(u.device).long()].double().unsqueeze(2)
+
+    def _evaluate_grouped(self, inputs, path_i, pos, grids):
+        """hourglass (reference src/model.py:104-107, the `path_i is not None` branch): one integration per group of
+        paths on the group's own grid, rows of the result in GROUP order (the reference concatenates the groups)."""
+        s0 = hotpath.as_f32(self.initial_scalar(inputs.detach(), "g"))
+        Xf = hotpath.as_f32(inputs)
+        L, Cc = Xf.shape[1], Xf.shape[2]
+        outs = []
+        for pi, ps, grid in zip(path_i, pos, grids):
+            if grid.numel() < 2 or int(ps.max()) >= grid.numel():
+                raise RuntimeError("fillt produced a %d-point grid for the requested times: the reference fails on this "
+                                   "input too" % grid.numel())
+            sel = pi.to(Xf.device).long()
+            Xg = Xf[sel].contiguous()
+            u = hotpath.xnode_eval(self.spec(), self.kernel_parameters(), Xg, 1, L * Cc, hotpath.as_f32(grid.to(Xf.device)),
+                                   s0[sel].contiguous(), Xg.shape[0])
+            outs.append(u[:, ps.to(u.device).long()])
+        return torch.cat(outs, 0).double().unsqueeze(2)
 
     def forward(self, inputs: torch.Tensor):
         if torch.is_grad_enabled() and not (inputs.shape[1] == 1):
