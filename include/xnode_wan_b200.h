@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define XW_ABI_VERSION 2
+#define XW_ABI_VERSION 3
 
 enum { XW_SOLVER_EULER = 0, XW_SOLVER_MIDPOINT = 1, XW_SOLVER_RK4 = 2 };
 enum { XW_DOMAIN_CUBE = 0, XW_DOMAIN_CONE = 1, XW_DOMAIN_HOURGLASS = 2 };
@@ -48,12 +48,23 @@ typedef struct xw_domain {
     float p0, p1, p2;
 } xw_domain;
 
-/* PDE coefficients as structure instead of the reference's dense tensors (src/training.py:25-41):
- * c(X,u) = c0 + c1*u; a: NULL = identity, else constant [d*d] row-major; b: NULL = 0, else [d] */
+/* PDE coefficients as structure instead of the reference's dense tensors a[d,d,N,L], b[d,N,L], c[N,L,1]
+ * (src/training.py:25-41).  The common case is constant: c(X,u) = c0 + c1*u; a: NULL = identity, else [d*d] row-major;
+ * b: NULL = 0, else [d]; a_sn = b_sn = 0, A_val = A_der = NULL.
+ * General callables (the reference accepts any func_a(X,i,j), func_b(X,i), func_c(X,u)):
+ *   - a, b that depend on X: only their values on time-row 0 of every path enter the loss (src/loss.py:66-69 multiplies
+ *     them with du, which lives on row 0 because the XNODE reads x from row 0, src/model.py:99): pass a[n][d*d] /
+ *     b[n][d] per path with a_sn = d*d / b_sn = d (elements between consecutive paths; 0 = one constant matrix / vector);
+ *   - c that depends on X or is not affine in u: A_val[n*L] = c(X,u) u and A_der[n*L] = d(c(X,u) u)/du per point,
+ *     evaluated by the host with the user's callable at u = xw_xnode_eval(...) (bit-identical to the u the interior
+ *     forward computes); when given they replace c0, c1. */
 typedef struct xw_coef {
     float c0, c1;
     const float* a;
     const float* b;
+    long long a_sn, b_sn;
+    const float* A_val;
+    const float* A_der;
 } xw_coef;
 
 /* strided view of per-point (t, x): t at t[n*t_sn + l*t_sl], x_j at x[n*x_sn + l*x_sl + j] */

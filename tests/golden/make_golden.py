@@ -35,6 +35,9 @@ CASES = {
     "cube_d4_aconst": ({'N_r': 72, 'N_b': 40, 'dim': 4, 'alpha': 10}, "Ex4_3_funcs", 8, True),
 }
 A_CONST = {"cube_d4_aconst": 9}      # case -> seed of the constant matrix a = I + 0.3 * randn(d, d)
+# a_ij(X) varying over the sample + c(X, u) non-affine (tests/_general_coef.py); stored under extra/ (the generic parity
+# tests glob tests/golden/*.npz and assume structured coefficients)
+GENERAL = {"general_coef_cube_d3": ({'N_r': 56, 'N_b': 40, 'dim': 3, 'alpha': 10}, "Ex4_3_funcs", 12, True)}
 
 
 SPHERE_CASES = {
@@ -110,6 +113,9 @@ def run_case(name, over, funcs_name, seed, rand_bias):
         d_ = params['dim']
         coef_a = np.eye(d_) + 0.3 * np.random.default_rng(A_CONST[name]).standard_normal((d_, d_))
         solver.func_a = lambda X_, i, j: torch.full(X_.shape[:-1], float(np.float32(coef_a[i, j])))
+    if name in GENERAL:
+        from tests import _general_coef as GC
+        solver.func_a, solver.func_c = GC.func_a, GC.func_c
     domain, batches = rr.sample(solver)
     assert len(batches) == 1
     b = batches[0]
@@ -120,7 +126,7 @@ def run_case(name, over, funcs_name, seed, rand_bias):
     sp = params['shape_param']
     meta = dict(params={k: (v if not callable(v) else str(v)) for k, v in params.items() if k != 'domain'},
                 funcs=funcs_name, seed=seed, domain=["cube", float(sp[0]), float(sp[1])], V=c['V'],
-                c0=0.0, c1=-1.0)
+                c0=0.0, c1=-1.0, general_coef=name in GENERAL)
     arrays = dict(
         X=X.numpy(), XV=XV.numpy(), BX=BX.numpy(),
         h=ou['h'], f=ou['f'], g=ou['g'],
@@ -139,7 +145,7 @@ def run_case(name, over, funcs_name, seed, rand_bias):
     for i, p in enumerate(solver.v_net.parameters()):
         arrays["thv_%02d" % i] = p.detach().numpy()
         arrays["gv_%02d" % i] = ov['grads'][i]
-    path = os.path.join(OUT, name + ".npz")
+    path = os.path.join(OUT, "extra" if name in GENERAL else "", name + ".npz")
     np.savez_compressed(path, **arrays)
     print("%-28s loss_u=%.10e loss_v=%.10e I=%.6e  (%d KB)" % (
         name, ou['loss'], ov['loss'], c['I'], os.path.getsize(path) // 1024))
@@ -155,3 +161,7 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         run_sphere_case(name, *spec)
+    for name, spec in GENERAL.items():
+        if only and name not in only:
+            continue
+        run_case(name, *spec)

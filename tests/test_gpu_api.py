@@ -7,7 +7,7 @@ import torch
 import xnode_wan_b200 as xw
 from oracle import closed_form as cf
 from tests import _golden as G
-from tests.test_host_api_emu import eval_phase, make_solver
+from tests.test_host_api_emu import eval_phase, general_forms_agree_with_structure, make_solver
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -25,6 +25,27 @@ def test_reference_api_matches_golden_on_gpu(name):
             assert abs(val.components[k].item() - float(z[k])) <= 1e-4 * abs(float(z[k]))
         for a, b in zip(grads, gold_g):
             assert G.rel(a, b) < 1e-3
+
+
+def test_general_coefficients_match_reference_golden_on_gpu():
+    """a_ij(X) varying over the sample and c(X, u) quadratic in u (tests/_general_coef.py): golden of the unmodified
+    reference with those callables (dense a[d,d,N,L] there; per-path a on time-row 0 + per-point A(u), dA/du here)"""
+    case = G.load("extra/general_coef_cube_d3")
+    s, _ = make_solver(case, DEV)
+    z = case["z"]
+    for phase, gold_l, gold_g in (("u", float(z["loss_u"]), case["gu"]), ("v", float(z["loss_v"]), case["gv"])):
+        val, grads = eval_phase(s, case, phase, DEV)
+        assert abs(val.item() - gold_l) <= 1e-4 * abs(gold_l) + 1e-6
+        for k in ("I", "S"):
+            assert abs(val.components[k].item() - float(z[k])) <= 1e-4 * abs(float(z[k]))
+        for a, b in zip(grads, gold_g):
+            assert G.rel(a, b) < 1e-3
+
+
+def test_general_coefficient_forms_agree_with_structure_on_gpu():
+    case = G.load("cube_d4_ex43")
+    s, _ = make_solver(case, DEV)
+    general_forms_agree_with_structure(s, case, DEV)
 
 
 def test_forward_only_modules_match_golden_on_gpu():

@@ -28,6 +28,9 @@ def make_solver(case, device="cpu"):
     if "coef_a" in case["z"].files:          # the constant a != I this golden was made with
         A = case["z"]["coef_a"]
         prob.func_a = lambda X_, i, j: torch.full(X_.shape[:-1], float(A[i, j]))
+    if case["meta"].get("general_coef"):     # a_ij(X) varying over the sample, c(X, u) non-affine
+        from tests import _general_coef as GC
+        prob.func_a, prob.func_c = GC.func_a, GC.func_c
     s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, device,
                            "./", func_u_sol=prob.func_u_sol, p=2, log_json=False)
     with torch.no_grad():
@@ -54,7 +57,8 @@ def eval_phase(s, case, phase, device="cpu"):
 
 
 @pytest.mark.parametrize("name", ["cube_d5_alpha1_randbias", "cube_d3_small_nets", "cube_d4_ex43", "cube_d3_rk4",
-                                  "cube_d4_aconst", "cone_d5_g2", "hourglass_d5_g2_reentry", "hourglass_d5_g18"])
+                                  "cube_d4_aconst", "cone_d5_g2", "hourglass_d5_g2_reentry", "hourglass_d5_g18",
+                                  "extra/general_coef_cube_d3"])
 def test_reference_api_matches_golden(emu, name):
     case = G.load(name)
     s, _ = make_solver(case)
@@ -67,6 +71,47 @@ def test_reference_api_matches_golden(emu, name):
         assert abs(comp["I"].item() - float(z["I"])) <= 1e-4 * abs(float(z["I"]))
         for a, b in zip(grads, gold_g):
             assert a.dtype == np.float64 and G.rel(a, b) < 1e-3
+
+
+def general_forms_agree_with_structure(s, case, device="cpu"):
+    """per-path a / b and a callable c that HAPPEN to be constant / affine must give what the structured forms give
+    (same kernels, other operand paths): pins the per-path b form, which no reference golden can (np.sum ambiguity of
+    src/loss.py:69)"""
+    z = case["z"]
+    X, XV, BX = (torch.from_numpy(z[k]).to(device) for k in ("X", "XV", "BX"))
+    d, n = s.setup["dim"], X.shape[0]
+    g_ = torch.Generator().manual_seed(5)
+    A = (torch.eye(d) + 0.3 * torch.randn(d, d, generator=g_)).float()
+    B = (0.4 * torch.randn(d, generator=g_)).float()
+    dom = s.new_domain()
+    out = {}
+    for form in ("structure", "general"):
+        if form == "structure":
+            a, b, c = xw.CoefA(A), xw.CoefB(B), xw.CoefC(0.25, -1.5)
+        else:
+            a = xw.CoefA(per_path=A.unsqueeze(0).expand(n, d, d).contiguous())
+            b = xw.CoefB(per_path=B.unsqueeze(0).expand(n, d).contiguous())
+            c = xw.CoefC(func=lambda X_, u: 0.25 - 1.5 * u)
+        for phase in ("u", "v"):
+            s.optimizer_u.zero_grad(); s.optimizer_v.zero_grad()
+            pv, pu = s.v_net(XV), s.u_net(X)
+            h, f, g = s.func_h(X[:, 0, :]), s.func_f(X), s.func_g(BX)
+            L = xw.loss(s.config["alpha"], a, b, c, h, f, g, s.setup, dom, device)
+            val = L.u(pu, pv, s.u_net, X, XV, BX) if phase == "u" else L.v(pu, pv, X, XV)
+            val.backward()
+            net = s.u_net if phase == "u" else s.v_net
+            out[form, phase] = (val.item(), [q.grad.detach().cpu().numpy().copy() for q in net.parameters()])
+    for phase in ("u", "v"):
+        (l0, g0), (l1, g1) = out["structure", phase], out["general", phase]
+        assert abs(l0 - l1) <= 1e-6 * abs(l0)
+        for x, y in zip(g0, g1):
+            assert G.rel(y, x) < 1e-5 or np.linalg.norm(x) == 0.0
+
+
+def test_general_coefficient_forms_agree_with_structure(emu):
+    case = G.load("cube_d4_ex43")
+    s, _ = make_solver(case)
+    general_forms_agree_with_structure(s, case)
 
 
 def test_state_dict_names_match_reference_layout(emu):
@@ -129,10 +174,8 @@ def test_unsupported_inputs_raise(emu):
     s, prob = make_solver(case)
     z = case["z"]
     X = torch.from_numpy(z["X"])
-    with pytest.raises(NotImplementedError):
-        xw.training.classify_coefficients(X, s.setup, prob.func_a, prob.func_b, lambda X_, u: -u * u)
-    with pytest.raises(NotImplementedError):
-        xw.training.classify_coefficients(X, s.setup, lambda X_, i, j: X_[:, :, 1] * (i == j), prob.func_b, prob.func_c)
+    # (coefficients that vary over the sample or are not affine in u are no longer refused: they classify as
+    # per-path / callable forms, test_coefficient_classification)
     with pytest.raises(RuntimeError):
         xw.NeuralODE(20, 1, prob.func_h, prob.func_g, s.setup, 10, 8, s.new_domain(), solver="dopri5")
     with pytest.raises(RuntimeError):
@@ -343,7 +386,7 @@ def test_coefficient_cache_is_keyed_on_the_callables(emu):
         A = torch.eye(3) * (k + 1.0)
         fa = (lambda A_: (lambda X_, i, j: torch.full(X_.shape[:-1], float(A_[i, j]))))(A)
         a, b, c = xw.training.classify_coefficients(X, s.setup, fa, prob.func_b, prob.func_c)
-        seen.append(None if a.matrix is None else float(a.matrix[0, 0]))
+        seen.append(None if a[0] == "identity" else float(a[1][0, 0]))
         del fa
         gc.collect()
     assert seen == [None, 2.0, 3.0, 4.0]
@@ -356,8 +399,30 @@ def test_coefficient_cache_is_keyed_on_the_callables(emu):
         if X_.shape[0] > 0 and i == j:
             out = out + (X_[:, :, 1] == X[last, 0, 1]).float()
         return out
-    with pytest.raises(NotImplementedError):
-        xw.training.classify_coefficients(X, s.setup, fa_var, prob.func_b, prob.func_c)
+    assert xw.training.classify_coefficients(X, s.setup, fa_var, prob.func_b, prob.func_c)[0] == ("per_path",)
+
+
+def test_coefficient_classification(emu):
+    """constant / affine callables become structure, everything else the per-path / callable forms; func_eval then
+    evaluates a, b on time-row 0 of every path (reference: dense a[d,d,N,L], src/training.py:32-41)"""
+    from tests import _general_coef as GC
+    case = G.load("cube_d3_small_nets")
+    s, prob = make_solver(case)
+    z = case["z"]
+    X, BX = torch.from_numpy(z["X"]), torch.from_numpy(z["BX"])
+    kinds = xw.training.classify_coefficients(X, s.setup, prob.func_a, prob.func_b, prob.func_c)
+    assert kinds[0] == ("identity",) and kinds[1] == ("zero",) and kinds[2][0] == "affine"
+    assert xw.training.classify_coefficients(X, s.setup, prob.func_a, prob.func_b, lambda X_, u: -u * u)[2] == ("callable",)
+    assert xw.training.classify_coefficients(X, s.setup, prob.func_a, prob.func_b, lambda X_, u: X_[..., 1:2] + 0 * u)[2] == ("callable",)
+    fb = lambda X_, i: 0.5 * X_[..., 1 + i]
+    h, f, g, a, b, c = xw.func_eval(X, BX, s.setup, None, GC.func_a, fb, GC.func_c, prob.func_h, prob.func_f, prob.func_g)
+    d = s.setup["dim"]
+    assert a.matrix is None and tuple(a.per_path.shape) == (X.shape[0], d, d)
+    for i in range(d):
+        for j in range(d):
+            assert torch.allclose(a.per_path[:, i, j], GC.func_a(X, i, j)[:, 0].float())
+        assert torch.allclose(b.per_path[:, i], fb(X, i)[:, 0].float())
+    assert c.func is GC.func_c
 
 
 def test_vcache_grows_with_the_batch_and_capi_checks_capacity(emu):

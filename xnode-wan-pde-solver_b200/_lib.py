@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, LIB_NAME)
 SOLVERS = {"euler": 0, "midpoint": 1, "rk4": 2}
 DOMAINS = {"cube": 0, "cone": 1, "hourglass": 2}
 NSUMS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 SUM_S1, SUM_S2, SUM_S3, SUM_VV, SUM_INIT, SUM_BDRY = 0, 1, 2, 3, 4, 5
 
 
@@ -29,7 +29,8 @@ class Domain(C.Structure):
 
 
 class Coef(C.Structure):
-    _fields_ = [("c0", C.c_float), ("c1", C.c_float), ("a", C.c_void_p), ("b", C.c_void_p)]
+    _fields_ = [("c0", C.c_float), ("c1", C.c_float), ("a", C.c_void_p), ("b", C.c_void_p),
+                ("a_sn", C.c_longlong), ("b_sn", C.c_longlong), ("A_val", C.c_void_p), ("A_der", C.c_void_p)]
 
 
 class Points(C.Structure):

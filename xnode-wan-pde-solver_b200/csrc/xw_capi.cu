@@ -181,6 +181,8 @@ int plan_vtile_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
 // tiles, 2.7e-3 without flushing); 4 keeps it at the level of the other tensors (dWi 8.6e-6) and takes the flush off the
 // critical path (26.8 -> 25.2 ms).  XW_TC_FLUSH overrides (tests).
 int tc_flush_tiles() { static const int v = []() { const char* e = getenv("XW_TC_FLUSH"); const int k = e ? atoi(e) : 4; return k > 0 ? k : 4; }(); return v; }
+// k_vnet_tc_fwd: MMAs of a layer issued by three warps instead of one thread (XW_TC_SPLIT=0/1)
+int tc_split_issue() { static const int v = []() { const char* e = getenv("XW_TC_SPLIT"); return e ? atoi(e) : 0; }(); return v; }
 int tc_tmem_packed() { static const int v = []() { const char* e = getenv("XW_TC_TMEM_PACKED"); return e && e[0] == '1' ? 1 : 0; }(); return v; }
 bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
 int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
@@ -540,6 +542,8 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         !sums || !cot_u || !cot_v || !workspace)
         return fail("NULL pointer argument");
     if (dom->kind < 0 || dom->kind > 2) return fail("unknown domain kind %d", dom->kind);
+    if ((coef->A_val == nullptr) != (coef->A_der == nullptr)) return fail("xw_coef: A_val and A_der go together");
+    if (coef->a_sn < 0 || coef->b_sn < 0) return fail("xw_coef: negative path stride");
     if (vcache_mode < 0 || vcache_mode > 2 || (vcache_mode != 0 && !vcache)) return fail("bad vcache arguments");
     if (vcache_mode != 0 && vcache_floats < xw_vcache_floats(m, n, L))
         return fail("test-function cache too small: %zu floats < %zu for n=%d, L=%d", vcache_floats, xw_vcache_floats(m, n, L), n, L);
@@ -574,12 +578,13 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     xw::VnetFwdArgs b{};
     b.d = m->d; b.Hvr = m->Hv; b.nv = m->nv; b.n = n; b.L = L; b.theta = theta_v; b.p = view_of(xv);
     b.dom_kind = dom->kind; b.dp0 = dom->p0; b.dp1 = dom->p1; b.dp2 = dom->p2;
-    b.c0 = coef->c0; b.c1 = coef->c1; b.ca = coef->a; b.cb = coef->b;
+    b.c0 = coef->c0; b.c1 = coef->c1; b.ca = coef->a; b.cb = coef->b; b.ca_sn = coef->a_sn; b.cb_sn = coef->b_sn;
     b.u = ubuf; b.du = du; b.h = h; b.f = f; b.sums = sums; b.cot_u = cot_u; b.cot_v = cot_v; b.v_out = nullptr;
     b.gcache = vcache_mode == 1 ? gcache : nullptr;
     if (vcache_mode == 2) {          // sample and theta_v unchanged: reuse the cached test-function values
         xw::CombineArgs q{};
         q.d = m->d; q.n = n; q.L = L; q.c0 = coef->c0; q.c1 = coef->c1; q.ca = coef->a; q.cb = coef->b;
+        q.ca_sn = coef->a_sn; q.cb_sn = coef->b_sn; q.Aval = coef->A_val; q.Ader = coef->A_der;
         q.vcache = vcache; q.gcache = gcache; q.u = ubuf; q.du = du; q.h = h; q.f = f;
         q.sums = sums; q.cot_u = cot_u; q.cot_v = cot_v;
         XW_LAUNCH(xw::k_weak_combine, grid_for((long long)n * L, 256, 8), 256, 4 * 32 * 8, stream, q);
@@ -613,7 +618,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
     xw::VtileFwdArgs t{};
     t.d = m->d; t.Hvr = m->Hv; t.nv = m->nv; t.n = n; t.L = L; t.theta = theta_v; t.p = view_of(xv);
     t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
-    t.c0 = coef->c0; t.c1 = coef->c1; t.u = ubuf; t.h = h; t.f = f; t.sums = sums; t.cot_u = cot_u; t.cot_v = cot_v;
+    t.c0 = coef->c0; t.c1 = coef->c1; t.Aval = coef->A_val; t.Ader = coef->A_der; t.u = ubuf; t.h = h; t.f = f; t.sums = sums; t.cot_u = cot_u; t.cot_v = cot_v;
     t.vcache = vcache_mode == 1 ? vcache : nullptr;
 #ifndef XW_EMU
     xw_dims mvirt = *m;
@@ -652,6 +657,7 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         if (XW_SET_SMEM(xw::tc::k_vnet_tc_fwd, sm)) return 1;
         const long long nt = ((long long)n * L + 63) / 64;
         const int g3 = (int)std::max<long long>(1, std::min<long long>((nt + ng - 1) / ng, (long long)device()->sms));
+        t.split_issue = tc_split_issue();
         xw::tc::k_vnet_tc_fwd<<<g3, 128 * ng, sm, (cudaStream_t)stream>>>(t, ng);
         g_last_vnet_fwd = 3;
         return XW_CHECK_LAUNCH("k_vnet_tc_fwd");

@@ -270,6 +270,7 @@ struct VnetFwdArgs {
     const float* theta; PointsView p;
     int dom_kind; float dp0, dp1, dp2;
     float c0, c1; const float* ca; const float* cb;
+    long long ca_sn, cb_sn;  // elements between consecutive paths' a / b (0: one constant matrix / vector)
     const float* u; const float* du; const float* h; const float* f;
     double* sums; float* cot_u; float* cot_v; float* v_out;
     float* gcache;           // MODE 2, optional: [n*d] grad_x phi at time-row 0 (for k_weak_combine)
@@ -311,7 +312,7 @@ XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
                 float q;
                 if (a.ca) {
                     q = 0.f;
-                    for (int j = 0; j < d; ++j) q = fmaf(a.ca[i * d + j], dun[j], q);
+                    for (int j = 0; j < d; ++j) q = fmaf(a.ca[n * a.ca_sn + i * d + j], dun[j], q);
                 } else {
                     q = dun[i];
                 }
@@ -319,7 +320,7 @@ XW_GLOBAL void k_vnet_points(VnetFwdArgs a) {
             }
             if (a.cb) {
                 float bq = 0.f;
-                for (int j = 0; j < d; ++j) bq = fmaf(a.cb[j], dun[j], bq);
+                for (int j = 0; j < d; ++j) bq = fmaf(a.cb[n * a.cb_sn + j], dun[j], bq);
                 s31 = fmaf(phi, bq, s31);
             }
             acc[2] += (double)s31;
@@ -707,6 +708,8 @@ XW_GLOBAL void k_adam_step(double* p, const float* g, double* m, double* v, long
 struct CombineArgs {
     int d, n, L;
     float c0, c1; const float* ca; const float* cb;
+    long long ca_sn, cb_sn;
+    const float* Aval; const float* Ader;
     const float* vcache; const float* gcache;
     const float* u; const float* du; const float* h; const float* f;
     double* sums; float* cot_u; float* cot_v;
@@ -724,7 +727,9 @@ XW_GLOBAL void k_weak_combine(CombineArgs a) {
         const int l = (int)(p - n * L);
         const f4 c = ld4(a.vcache + 4 * p);
         float cu, cv;
-        weak_point_terms(c.x, c.y, c.z, c.w, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, a.c0, a.c1, acc, cu, cv);
+        float Au, Ap;
+        weak_A(a.c0, a.c1, a.Aval, a.Ader, p, a.u[p], Au, Ap);
+        weak_point_terms(c.x, c.y, c.z, c.w, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, Au, Ap, acc, cu, cv);
         a.cot_u[p] = cu;
         a.cot_v[p] = cv;
         if (l == 0) {
@@ -735,7 +740,7 @@ XW_GLOBAL void k_weak_combine(CombineArgs a) {
                 float q;
                 if (a.ca) {
                     q = 0.f;
-                    for (int j = 0; j < d; ++j) q = fmaf(a.ca[i * d + j], dun[j], q);
+                    for (int j = 0; j < d; ++j) q = fmaf(a.ca[n * a.ca_sn + i * d + j], dun[j], q);
                 } else {
                     q = dun[i];
                 }
@@ -743,7 +748,7 @@ XW_GLOBAL void k_weak_combine(CombineArgs a) {
             }
             if (a.cb) {
                 float bq = 0.f;
-                for (int j = 0; j < d; ++j) bq = fmaf(a.cb[j], dun[j], bq);
+                for (int j = 0; j < d; ++j) bq = fmaf(a.cb[n * a.cb_sn + j], dun[j], bq);
                 s31 = fmaf(c.x * c.z, bq, s31);
             }
             acc[2] += (double)s31;

@@ -131,6 +131,51 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tA_hi, uint32
     }
 }
 
+// The same product issued by THREE warps, one 3xTF32 term each.  One thread cannot issue tcgen05.mma faster than one per ~46
+// cycles whatever the shape (measured, profiles/r02y_mma_issue_bench.txt: 45.6 cycles per MMA at N = 24, 56; 28.4 at N = 56
+// with two or more issuing warps = the pipe's own 128 N / 256), so a layer's 21 MMAs take 960 cycles from one thread against
+// 590 of tensor-pipe time.  Warp iw of the three calls this (all 32 lanes; lane 0 issues): iw = 0: A_lo x B_hi, and its
+// first MMA initialises the accumulator; warps 1, 2 (A_hi x B_lo, A_hi x B_hi) accumulate and therefore issue only after
+// that first MMA is in the pipe: tcgen05.fence::before_thread_sync + named barrier `bar_id` (96 threads) +
+// tcgen05.fence::after_thread_sync orders the asynchronous MMAs of the three threads.  Every issuer commits to `mbar`,
+// which must have been initialised with a count of 3.
+template <int KS>
+__device__ __forceinline__ void issue_3xtf32_split(int iw, int lane, int bar_id, uint32_t tD, uint32_t tA_hi, uint32_t tA_lo,
+                                                   const float* b_hi, const float* b_lo, int ksteps_rt, uint32_t idesc, uint64_t* mbar) {
+    constexpr uint64_t kStep = (2 * NP * 16) >> 4;        // two 16-byte chunks of k per MMA
+    const uint64_t db = umma::smem_desc(iw == 1 ? b_lo : b_hi, NP * 16, 128);
+    const uint32_t ta = iw == 0 ? tA_lo : tA_hi;
+    const int ks_n = KS > 0 ? KS : ksteps_rt;
+    if (iw == 0) {
+        if (lane == 0) { umma::fence_after(); umma::mma_tf32_ts(tD, ta, db, idesc, 0u); }
+        umma::fence_before();
+        asm volatile("bar.arrive %0, 96;" ::"r"(bar_id) : "memory");
+        if (lane == 0) {
+            if (KS > 0) {
+#pragma unroll
+                for (int ks = 1; ks < (KS > 0 ? KS : 1); ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
+            } else {
+#pragma unroll 1
+                for (int ks = 1; ks < ks_n; ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
+            }
+            umma::commit(mbar);
+        }
+    } else {
+        asm volatile("bar.sync %0, 96;" ::"r"(bar_id) : "memory");
+        if (lane == 0) {
+            umma::fence_after();
+            if (KS > 0) {
+#pragma unroll
+                for (int ks = 0; ks < (KS > 0 ? KS : 1); ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
+            } else {
+#pragma unroll 1
+                for (int ks = 0; ks < ks_n; ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
+            }
+            umma::commit(mbar);
+        }
+    }
+}
+
 // split 56 fp32 values into the hi / lo A operand of this thread's row
 __device__ __forceinline__ void store_a_row(uint32_t lane_addr, int KA, const float (&v)[KP]) {
     uint32_t r[KP];
@@ -173,7 +218,7 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid >> 7, wq = warp & 3;
     const bool is_tan = lane >= 16;
     stage_images(w, a.theta, a.d, a.Hvr, kin);
-    if (tid < 4) umma::mbar_init(mbars + tid, 1);
+    if (tid < 4) umma::mbar_init(mbars + tid, a.split_issue ? 3 : 1);
     if (warp == 0) umma::tmem_alloc(slot, 512);
     umma::fence_before();
     __syncthreads();
@@ -217,7 +262,9 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
         umma::tmem_wait_st();
         umma::fence_before();
         umma::group_sync(1 + wg);
-        if (issuer) {
+        if (a.split_issue) {
+            if (wq < 3) issue_3xtf32_split<0>(wq, lane, 4 + wg, tbase + colD, tbase + colA, tbase + colA + KA, w.wi_hi, w.wi_lo, kin / 8, idesc, mbar);
+        } else if (issuer) {
             umma::fence_after();
             issue_3xtf32<0>(tbase + colD, tbase + colA, tbase + colA + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
             umma::commit(mbar);
@@ -241,7 +288,9 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
             umma::tmem_wait_st();
             umma::fence_before();
             umma::group_sync(1 + wg);
-            if (issuer) {
+            if (a.split_issue) {
+                if (wq < 3) issue_3xtf32_split<KP / 8>(wq, lane, 4 + wg, tbase + colD, tbase + colA, tbase + colA + KA, w.wh_hi, w.wh_lo, 0, idesc, mbar);
+            } else if (issuer) {
                 umma::fence_after();
                 issue_3xtf32<KP / 8>(tbase + colD, tbase + colA, tbase + colA + KA, w.wh_hi, w.wh_lo, 0, idesc);
                 umma::commit(mbar);
@@ -268,7 +317,9 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
             if (a.wbuf) { W.w = a.wbuf[p]; W.dw_t = a.dwtbuf[p]; }     // (virtual input: the coordinates are not spatial)
             else W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, tval, xr, a.d);
             float cu, cv;
-            weak_point_terms(v, dv_t, W.w, W.dw_t, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, a.c0, a.c1, accs, cu, cv);
+            float Au, Ap;
+            weak_A(a.c0, a.c1, a.Aval, a.Ader, p, a.u[p], Au, Ap);
+            weak_point_terms(v, dv_t, W.w, W.dw_t, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, Au, Ap, accs, cu, cv);
             a.cot_u[p] = cu;
             a.cot_v[p] = cv;
             if (a.vcache) { f4 cch; cch.x = v; cch.y = dv_t; cch.z = W.w; cch.w = W.dw_t; st4(a.vcache + 4 * p, cch); }
@@ -1032,7 +1083,7 @@ __global__ void __launch_bounds__(384) k_vnet_tc_row0(VnetFwdArgs a) {
                         float q;
                         if (a.ca) {
                             q = 0.f;
-                            for (int jj = 0; jj < d; ++jj) q = fmaf(a.ca[i * d + jj], dun[jj], q);
+                            for (int jj = 0; jj < d; ++jj) q = fmaf(a.ca[nn * a.ca_sn + i * d + jj], dun[jj], q);
                         } else {
                             q = dun[i];
                         }
@@ -1044,7 +1095,7 @@ __global__ void __launch_bounds__(384) k_vnet_tc_row0(VnetFwdArgs a) {
         if (valid) {
             if (a.cb) {
                 float bq = 0.f;
-                for (int jj = 0; jj < d; ++jj) bq = fmaf(a.cb[jj], dun[jj], bq);
+                for (int jj = 0; jj < d; ++jj) bq = fmaf(a.cb[nn * a.cb_sn + jj], dun[jj], bq);
                 s31 = fmaf(phi, bq, s31);
             }
             accs[2] += (double)s31;

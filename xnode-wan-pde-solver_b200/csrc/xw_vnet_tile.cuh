@@ -184,22 +184,32 @@ struct VtileFwdArgs {
     const float* theta; PointsView p;
     int dom_kind; float dp0, dp1, dp2;
     float c0, c1;
+    const float* Aval; const float* Ader;   // optional per-point A(u) = c(X,u) u and dA/du (general c: host-evaluated)
     const float* u; const float* h; const float* f;
     double* sums; float* cot_u; float* cot_v;
     float* vcache;           // optional [n*L] x (v, dv/dt, w, dw/dt): lets later sub-steps on the same sample
                              // and the same theta_v skip the v net entirely (k_weak_combine)
     const float* wbuf;       // optional [n*L] domain weight and
     const float* dwtbuf;     // optional [n*L] its time derivative (tensor-core forward on the virtual net, d > 54)
+    int split_issue;         // k_vnet_tc_fwd: a layer's MMAs issued by three warps (one 3xTF32 term each)
 };
 
 // the weak-form integrands of one point from (v, dv/dt, w, dw/dt) and (u, f, h): src/loss.py:64-73
 // without the time-row-0 gradient term; accumulates into acc[0..3], writes the cotangent seeds
+// the zeroth-order term A(u) = c(X, u) u and its derivative: the affine structure c = c0 + c1 u in closed form, or -- for
+// a coefficient that depends on X or is not affine in u (src/training.py:30, src/loss.py:70 accept any callable) -- the
+// per-point values the host evaluated with the user's callable at the u of xw_xnode_eval (xw_coef.A_val / A_der)
+XW_DEV void weak_A(float c0, float c1, const float* Aval, const float* Ader, long long p, float u, float& A, float& Ap) {
+    if (Aval) { A = Aval[p]; Ap = Ader[p]; return; }
+    const float cu_ = fmaf(c1, u, c0);
+    A = cu_ * u;
+    Ap = fmaf(c1, u, cu_);
+}
+
 XW_DEV void weak_point_terms(float v, float dv_t, float w, float dw_t, float u, float fv, float hn, int l, int L,
-                             float c0, float c1, double (&acc)[4], float& cu, float& cv) {
+                             float A, float Ap, double (&acc)[4], float& cu, float& cv) {
     const float phi = v * w;
     const float dphi0 = fmaf(w, dv_t, v * dw_t);
-    const float cu_ = fmaf(c1, u, c0);
-    const float A = cu_ * u, Ap = fmaf(c1, u, cu_);
     float s1 = 0.f;
     cu = Ap * phi;
     cv = w * (A + fv);
@@ -330,7 +340,9 @@ k_vnet_tile_fwd(VtileFwdArgs a) {
                 const float* xr = xin + r * XLD;
                 const DomW W = domain_w(a.dom_kind, a.dp0, a.dp1, a.dp2, xr[0], xr + 1, a.d);
                 float cu, cv;
-                weak_point_terms(v, dv_t, W.w, W.dw_t, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, a.c0, a.c1, accs, cu, cv);
+                float Au, Ap;
+                weak_A(a.c0, a.c1, a.Aval, a.Ader, p, a.u[p], Au, Ap);
+                weak_point_terms(v, dv_t, W.w, W.dw_t, a.u[p], a.f[p], l == 0 ? a.h[n] : 0.f, l, L, Au, Ap, accs, cu, cv);
                 a.cot_u[p] = cu;
                 a.cot_v[p] = cv;
                 if (a.vcache) { f4 cch; cch.x = v; cch.y = dv_t; cch.z = W.w; cch.w = W.dw_t; st4(a.vcache + 4 * p, cch); }

@@ -94,16 +94,25 @@ class DomainSpec:
 
 @dataclass
 class CoefSpec:
-    """structured PDE coefficients: c(X,u) = c0 + c1*u; a None=identity or constant [d,d];
-    b None=0 or constant [d]"""
+    """structured PDE coefficients (include/xnode_wan_b200.h, xw_coef): c(X,u) = c0 + c1*u; a None=identity, a constant
+    [d,d] matrix or per-path values [N,d,d] (a_per_path); b None=0, a constant [d] vector or per-path [N,d];
+    A_val / A_der: optional per-point [N*L] values of A(u) = c(X,u) u and dA/du for a general c (replace c0, c1)"""
     c0: float = 0.0
     c1: float = 0.0
     a: Optional[torch.Tensor] = None
     b: Optional[torch.Tensor] = None
+    a_per_path: bool = False
+    b_per_path: bool = False
+    A_val: Optional[torch.Tensor] = None
+    A_der: Optional[torch.Tensor] = None
 
     def c(self):
+        a_sn = self.a.shape[-1] * self.a.shape[-2] if (self.a is not None and self.a_per_path) else 0
+        b_sn = self.b.shape[-1] if (self.b is not None and self.b_per_path) else 0
         return _lib.Coef(float(self.c0), float(self.c1), self.a.data_ptr() if self.a is not None else None,
-                         self.b.data_ptr() if self.b is not None else None)
+                         self.b.data_ptr() if self.b is not None else None, a_sn, b_sn,
+                         self.A_val.data_ptr() if self.A_val is not None else None,
+                         self.A_der.data_ptr() if self.A_der is not None else None)
 
 
 def as_f32(t):

@@ -14,21 +14,24 @@ from .paths import CollapsedPaths
 
 
 class CoefA:
-    """a_ij: identity (matrix=None) or a constant [d,d] matrix"""
-    def __init__(self, matrix=None):
-        self.matrix = matrix
+    """a_ij: identity (matrix=None), a constant [d,d] matrix, or -- for a_ij(X) that varies over the sample -- its values
+    on time-row 0 of every path, per_path[N,d,d] (the only ones that enter the loss: src/loss.py:66-68 multiplies a with
+    du, which lives on row 0)"""
+    def __init__(self, matrix=None, per_path=None):
+        self.matrix, self.per_path = matrix, per_path
 
 
 class CoefB:
-    """b_i: zero (vector=None) or a constant [d] vector"""
-    def __init__(self, vector=None):
-        self.vector = vector
+    """b_i: zero (vector=None), a constant [d] vector, or per_path[N,d] (values on time-row 0, as for a)"""
+    def __init__(self, vector=None, per_path=None):
+        self.vector, self.per_path = vector, per_path
 
 
 class CoefC:
-    """c(X,u) = c0 + c1*u"""
-    def __init__(self, c0=0.0, c1=0.0):
-        self.c0, self.c1 = float(c0), float(c1)
+    """c(X,u) = c0 + c1*u, or any callable func(X, u) (src/training.py:30): then A(u) = c(X,u) u and dA/du are
+    evaluated per point with the callable (PyTorch autograd, elementwise) at the current u before every kernel pass"""
+    def __init__(self, c0=0.0, c1=0.0, func=None):
+        self.c0, self.c1, self.func = float(c0), float(c1), func
 
 
 def domain_spec(domain):
@@ -110,12 +113,26 @@ class loss:
             b.Nb_glob = self.Nb_glob
         return b
 
-    def _coef(self, dev):
-        a = self.a.matrix
-        bb = self.b.vector
+    def _coef(self, dev, A_val=None, A_der=None):
+        a_pp, b_pp = self.a.per_path is not None, self.b.per_path is not None
+        a = self.a.per_path if a_pp else self.a.matrix
+        bb = self.b.per_path if b_pp else self.b.vector
         return hotpath.CoefSpec(self.c.c0, self.c.c1,
                                 hotpath.as_f32(a).to(dev) if a is not None else None,
-                                hotpath.as_f32(bb).to(dev) if bb is not None else None)
+                                hotpath.as_f32(bb).to(dev) if bb is not None else None, a_pp, b_pp, A_val, A_der)
+
+    def _general_A(self, u_mod, X):
+        """A(u) = c(X,u) u and dA/du per point for a callable c: u by the forward-only XNODE kernel (the numbers the
+        interior forward pass computes), the callable and its u-derivative by PyTorch (elementwise on [N,L])"""
+        with torch.no_grad():
+            u = u_mod.evaluate(X)                                     # [N, L, 1] float64
+        Xd = X.dense() if hasattr(X, "dense") else X
+        u_t = u.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            cval = self.c.func(Xd.detach(), u_t)
+            A = cval.reshape(u_t.shape[0], -1).to(u_t.dtype) * u_t.reshape(u_t.shape[0], -1)
+            dA, = torch.autograd.grad(A.sum(), u_t)
+        return hotpath.as_f32(A), hotpath.as_f32(dA.reshape(A.shape))
 
     def _single_time_group(self, phase, u_mod, v_mod, X, XV, border):
         """Interior group with ONE time point at T0 (first group of the sphere domains).  The reference
@@ -136,10 +153,17 @@ class loss:
             n = U.shape[0]
             V = float(self.V)
             h, f = self.h.to(U.dtype), self.f[:, 0].to(U.dtype)
-            A = self.a.matrix.to(du) if self.a.matrix is not None else None
-            q = du if A is None else du @ A.T                                           # sum_l a_kl du_l
+            if self.c.func is not None:
+                raise NotImplementedError("a callable c(X, u) on a single-time-point group (the reference's rank-2 "
+                                          "shortcut broadcasts it to [n, n])")
+            if self.a.per_path is not None:
+                q = torch.einsum("nij,nj->ni", self.a.per_path.to(du), du)
+            else:
+                A = self.a.matrix.to(du) if self.a.matrix is not None else None
+                q = du if A is None else du @ A.T                                       # sum_l a_kl du_l
             s31 = (dphi[:, 1:] * q).sum(1).double()
-            s32 = ((du * self.b.vector.to(du)).sum(1).double().sum() * Phi.detach().sum()) if self.b.vector is not None else 0.0
+            bvec = self.b.per_path if self.b.per_path is not None else self.b.vector
+            s32 = ((du * bvec.to(du)).sum(1).double().sum() * Phi.detach().sum()) if bvec is not None else 0.0
             cU = self.c.c0 + self.c.c1 * U
             s1 = (V / n) * (U * Vv - h * Vv).sum()
             s2 = (V / n) * (U.detach().sum() * dphi[:, 0].double().sum())
@@ -185,7 +209,8 @@ class loss:
         vbuf, vmode = self.vcache if self.vcache is not None else (None, 0)
         if vmode and vbuf is None:
             raise RuntimeError("vcache mode without a buffer")
-        return hotpath.weak_loss(phase, spec, dom, self._coef(X.device), float(self.alpha), batch,
+        A_val, A_der = self._general_A(u_mod, X) if self.c.func is not None else (None, None)
+        return hotpath.weak_loss(phase, spec, dom, self._coef(X.device, A_val, A_der), float(self.alpha), batch,
                                  u_mod.kernel_parameters(), v_mod.flat_parameters(), group=self.group,
                                  side_effect=self.side_effect, vcache=vbuf, vmode=vmode, grad_sink=self.grad_sink)
 
@@ -233,7 +258,8 @@ class loss:
         with torch.no_grad():
             thu = hotpath.flatten_params(u_mod.kernel_parameters())
             thv = hotpath.flatten_params(v_mod.flat_parameters())
-            sums, _, _ = hotpath.forward_sums(lib, spec, dom, self._coef(X.device), thu, thv, batch, False, 0.0)
+            A_val, A_der = self._general_A(u_mod, X) if self.c.func is not None else (None, None)
+            sums, _, _ = hotpath.forward_sums(lib, spec, dom, self._coef(X.device, A_val, A_der), thu, thv, batch, False, 0.0)
             hotpath._allreduce(sums, self.group)
             I, S, init, bdry, integ = hotpath.loss_from_sums(sums, batch, dom.V, 0.0)
         return {"I": I, "S": S}[key]

@@ -20,18 +20,19 @@ _COEF_CACHE = {}
 _PROBE_PATHS = 64
 
 
-def _probe_constant(vals, what):
-    """vals: tensor over probe points -> python float if constant, else raises"""
+def _constant_value(vals):
+    """vals: tensor over probe points -> python float if all equal, else None"""
     v0 = vals.reshape(-1)[0]
-    if not bool(torch.all(vals == v0)):
-        raise NotImplementedError("%s varies over the sample: only constant coefficients are supported by the "
-                                  "fused kernels (no dense-tensor fallback)" % what)
-    return float(v0)
+    return float(v0) if bool(torch.all(vals == v0)) else None
 
 
 def classify_coefficients(X, setup, func_a, func_b, func_c):
-    """turn the user callables a_ij(X), b_i(X), c(X,u) into structure (SURVEY.md 7 'User callables').
-    Probed on a few sample paths once per (callables, dim) and cached."""
+    """the STRUCTURE of the user callables a_ij(X), b_i(X), c(X,u) (SURVEY.md 7 'User callables'), probed on a spread
+    of sample paths once per (callables, dim) and cached:
+      a: ("identity",) | ("const", A[d,d]) | ("per_path",)      b: ("zero",) | ("const", B[d]) | ("per_path",)
+      c: ("affine", c0, c1) | ("callable",)
+    Constant / affine coefficients (every shipped problem) cost nothing per sample; the other forms are evaluated per
+    sample by `func_eval` (a, b on time-row 0 of every path) or per kernel pass by the loss (c)."""
     d = setup['dim']
     # keyed on the callables THEMSELVES (strong references): an id() can be recycled by another problem's closures
     # after garbage collection and would silently hand it this problem's structure
@@ -45,32 +46,60 @@ def classify_coefficients(X, setup, func_a, func_b, func_c):
     else:
         Xs = X.dense() if hasattr(X, "dense") else X.detach()
     A = torch.empty(d, d, dtype=torch.float64)
+    a_kind = None
     for i, j in itertools.product(range(d), repeat=2):
-        A[i, j] = _probe_constant(func_a(Xs, i, j), "a[%d,%d]" % (i, j))
-    a = CoefA(None if bool(torch.equal(A, torch.eye(d, dtype=torch.float64))) else A.float())
-    B = torch.tensor([_probe_constant(func_b(Xs, i), "b[%d]" % i) for i in range(d)], dtype=torch.float64)
-    b = CoefB(None if bool(torch.all(B == 0)) else B.float())
+        v = _constant_value(func_a(Xs, i, j))
+        if v is None:
+            a_kind = ("per_path",)
+            break
+        A[i, j] = v
+    if a_kind is None:
+        a_kind = ("identity",) if bool(torch.equal(A, torch.eye(d, dtype=torch.float64))) else ("const", A.float())
+    bv = [_constant_value(func_b(Xs, i)) for i in range(d)]
+    if any(v is None for v in bv):
+        b_kind = ("per_path",)
+    else:
+        B = torch.tensor(bv, dtype=torch.float64)
+        b_kind = ("zero",) if bool(torch.all(B == 0)) else ("const", B.float())
     shape = (Xs.shape[0], Xs.shape[1], 1)
     u0 = torch.zeros(shape, dtype=torch.float64, device=Xs.device)
     c_at0, c_at1, c_at2 = (func_c(Xs, u0 + k) for k in (0.0, 1.0, 2.0))
-    c0 = _probe_constant(c_at0, "c(X, 0)")
-    c1 = _probe_constant(c_at1 - c_at0, "c(X, 1) - c(X, 0)")
-    if not bool(torch.allclose(c_at2, c_at0 + 2.0 * (c_at1 - c_at0), rtol=1e-12, atol=1e-12)):
-        raise NotImplementedError("c(X, u) is not affine in u: unsupported coefficient form")
-    out = (a, b, CoefC(c0, c1))
+    c0, c1 = _constant_value(c_at0), _constant_value(c_at1 - c_at0)
+    affine = c0 is not None and c1 is not None and bool(torch.allclose(c_at2, c_at0 + 2.0 * (c_at1 - c_at0), rtol=1e-12, atol=1e-12))
+    c_kind = ("affine", c0, c1) if affine else ("callable",)
+    out = (a_kind, b_kind, c_kind)
     _COEF_CACHE[key] = out
     return out
 
 
+def _row0(X):
+    """time-row 0 of every path as a dense [N, 1, C] tensor (what a_ij / b_i are evaluated on)"""
+    return X[:, 0, :].detach().unsqueeze(1)
+
+
 def func_eval(X: torch.Tensor, BX: torch.Tensor, setup: dict, y_output_u, func_a, func_b, func_c, func_h, func_f,
               func_g):
-    """h, f, g evaluated on the sample by the user's callables (as the reference does); a, b, c as
-    structure instead of the reference's dense [d,d,N,L] / [d,N,L] tensors (src/training.py:32-41).
-    `y_output_u` is accepted for signature parity and not evaluated."""
+    """h, f, g evaluated on the sample by the user's callables (as the reference does); a, b, c as structure
+    (`CoefA / CoefB / CoefC`) instead of the reference's dense [d,d,N,L] / [d,N,L] tensors (src/training.py:32-41):
+    constants where the callables are constant, per-path values on time-row 0 where a or b vary over the sample, the
+    callable itself for a c that depends on X or is not affine in u.  `y_output_u` is accepted for signature parity."""
     h = func_h(X[:, 0, :])
     f = func_f(X)
     g = func_g(BX)
-    a, b, c = classify_coefficients(X, setup, func_a, func_b, func_c)
+    a_kind, b_kind, c_kind = classify_coefficients(X, setup, func_a, func_b, func_c)
+    d, n = setup['dim'], X.shape[0]
+    if a_kind[0] == "per_path":
+        X0 = _row0(X)
+        a = CoefA(per_path=torch.stack([func_a(X0, i, j).reshape(n) for i, j in itertools.product(range(d), repeat=2)],
+                                       dim=1).reshape(n, d, d).float().contiguous().to(X.device))
+    else:
+        a = CoefA(a_kind[1] if a_kind[0] == "const" else None)
+    if b_kind[0] == "per_path":
+        X0 = _row0(X)
+        b = CoefB(per_path=torch.stack([func_b(X0, i).reshape(n) for i in range(d)], dim=1).float().contiguous().to(X.device))
+    else:
+        b = CoefB(b_kind[1] if b_kind[0] == "const" else None)
+    c = CoefC(c_kind[1], c_kind[2]) if c_kind[0] == "affine" else CoefC(func=func_c)
     return h.to(X.device), f.to(X.device), g.to(X.device), a, b, c
 
 
@@ -270,6 +299,11 @@ class NODE_WAN_solver:
         # allocated OUTSIDE any graph: "fresh" graphs write into it, the others read it (see _step)
         h, f, g, a, b, c = func_eval(static[0].detach(), static[2].detach(), self.setup, None, self.func_a, self.func_b,
                                      self.func_c, self.func_h, self.func_f, self.func_g)
+        if a.per_path is not None or b.per_path is not None or c.func is not None:
+            # coefficients that vary over the sample / a callable c are re-evaluated by PyTorch per sample / per pass
+            # (host-side shape logic, autograd through the user's callable): those steps run eagerly
+            self.use_cuda_graph = False
+            return
         tmp = loss(self.config['alpha'], a, b, c, h, f, g, self.setup, domain, self.device)
         if self.world > 1:
             tmp.N_glob, tmp.Nb_glob = static[0].shape[0] * self.world, static[2].shape[0] * self.world
