@@ -117,7 +117,9 @@ def test_mid_size_against_oracle(d, N, Nb):
 
 def test_large_size_properties():
     """N = 2^16 paths: sharding invariance (sum of two half-batches == whole batch: the property the
-    multi-GPU path relies on), layout invariance (collapsed == dense), determinism"""
+    multi-GPU path relies on), layout invariance (collapsed == dense), run-to-run reproducibility.  Tolerances are those
+    of fp32 rounding, not bit equality: the forward tcgen05 kernel issues the three 3xTF32 terms of a layer from three
+    warps and the order in which they reach the accumulator varies (XW_TC_SPLIT=0 runs are bit-reproducible)"""
     N = 1 << 16
     s, prob = _rand_case(20, N, N, 4)
     dom = s.new_domain(sample_device=DEV)
@@ -125,10 +127,10 @@ def test_large_size_properties():
     X, XV, BX = pts[0]
     lu, gu = _loss_and_grads(s, dom, X, XV, BX, "u")
     lu2, gu2 = _loss_and_grads(s, dom, X, XV, BX, "u")
-    assert abs(lu.item() - lu2.item()) <= 1e-9 * abs(lu.item())
+    assert abs(lu.item() - lu2.item()) <= 1e-6 * abs(lu.item())
     col = [xw.CollapsedPaths(t[0, :, 0].contiguous(), t[:, 0, 1:].contiguous()) for t in (X, XV, BX)]
     lc, gc = _loss_and_grads(s, dom, col[0], col[1], col[2], "u")
-    assert abs(lu.item() - lc.item()) <= 1e-7 * abs(lu.item())
+    assert abs(lu.item() - lc.item()) <= 1e-6 * abs(lu.item())
     for a, b in zip(gu, gc):
         assert G.rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
     # sharding: raw sums of two halves add up to the sums of the whole
@@ -152,7 +154,7 @@ def test_large_size_properties():
     h1 = sums_of(X[:N // 2], XV[:N // 2], BX[:N // 2])
     h2 = sums_of(X[N // 2:], XV[N // 2:], BX[N // 2:])
     # path 0's time grid is shared, so the halves see the same grid
-    assert np.allclose(h1 + h2, whole, rtol=1e-9, atol=1e-9 * np.abs(whole).max())
+    assert np.allclose(h1 + h2, whole, rtol=1e-6, atol=1e-7 * np.abs(whole).max())
 
 
 def test_time_varying_domain_training_runs_on_gpu():
@@ -265,4 +267,6 @@ def test_prefetched_sample_equals_synchronous_copy():
             pts.prefetch()
         X, XV, BX = pts[0]
         vals.append(_loss_and_grads(s, dom, X, XV, BX, "u")[0].item())
-    assert vals[0] == vals[1] or abs(vals[0] - vals[1]) <= 1e-9 * abs(vals[0])
+    # (not bit for bit: the forward tcgen05 kernel issues a layer's three 3xTF32 terms from three warps and the order in
+    # which they reach the accumulator varies from run to run -- fp32 rounding of v, 1e-7; XW_TC_SPLIT=0 is bit-reproducible)
+    assert abs(vals[0] - vals[1]) <= 2e-6 * abs(vals[0])

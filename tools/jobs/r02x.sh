@@ -11,3 +11,4 @@ try:
 except Exception as e: print("ERR", e, t[-2000:])
 PY
 done
+timeout 300 python tools/tc_prof.py acc 18 20 2>&1 | grep -A8 "flush_every_4"

@@ -30,7 +30,9 @@ def build():
     from importlib import import_module
     b = import_module("xnode-wan-pde-solver_b200.build")
     flags = [f for f in b.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
-    for name, extra in (("libtcb.so", []), ("libtcb_prof.so", ["-DXW_TC_PROF"])):
+    split = ["-DXW_TC_BWD_SPLIT=%s" % os.environ.get("XW_TC_BWD_SPLIT", "1"), "-DXW_TC_SPLIT_MASK=%s" % os.environ.get("XW_TC_SPLIT_MASK", "3")]
+    suffix = os.environ.get("TCB_SUFFIX", "")
+    for name, extra in (("libtcb%s.so" % suffix, split), ("libtcb_prof%s.so" % suffix, ["-DXW_TC_PROF"] + split)):
         cmd = ["nvcc"] + flags + extra + ["-o", os.path.join(TCB, name), os.path.join(TCB, "tcb.cu")]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
@@ -95,7 +97,7 @@ def run(log2n=20, d=20, L=20, reps=3, packed=0, flush=4):
     print(json.dumps(out, indent=1))
 
 
-def acc(log2n=18, d=20, L=20, flushes=(1, 2, 4, 8, 1 << 30)):
+def acc(log2n=18, d=20, L=20, flushes=(1, 4)):
     """gradient of the kernel (per-CTA partials summed in fp64) against a PyTorch fp64 autograd evaluation of the same net
     on the same points, per parameter tensor (rel-L2), for several flush intervals of the weight-gradient accumulators"""
     import torch
@@ -105,8 +107,9 @@ def acc(log2n=18, d=20, L=20, flushes=(1, 2, 4, 8, 1 << 30)):
     g = torch.Generator(device=dev).manual_seed(1)
     sizes = [("Wi", Hv * Cc), ("bi", Hv), ("Wh", Hv * Hv), ("bh", Hv), ("Wz", Hv), ("bz", 1)]
     Pv = sum(k for _, k in sizes)
-    thv = (torch.rand(Pv, device=dev, generator=g) - 0.5) * 0.35
-    x = torch.rand(n, d, device=dev, generator=g) * 2 - 1
+    sc = float(os.environ.get("TCB_SCALE", "1"))
+    thv = (torch.rand(Pv, device=dev, generator=g) - 0.5) * 0.35 * sc
+    x = (torch.rand(n, d, device=dev, generator=g) * 2 - 1) * sc
     times = torch.sort(torch.rand(L, device=dev, generator=g))[0].contiguous()
     cot = torch.randn(n * L, device=dev, generator=g)
     k0, k1 = 1e-3, 2e-3
@@ -128,7 +131,7 @@ def acc(log2n=18, d=20, L=20, flushes=(1, 2, 4, 8, 1 << 30)):
         v = torch.tanh(a) @ parts["Wz"] + parts["bz"]
         G = (k0 * cot[s0 * L:(s0 + xs.shape[0]) * L].double() + k1 * v).detach()
         ref += torch.autograd.grad((G * v).sum(), th)[0]
-    lib = C.CDLL(os.path.join(TCB, "libtcb.so"))
+    lib = C.CDLL(os.path.join(TCB, "libtcb%s.so" % os.environ.get("TCB_SUFFIX", "")))
     lib.tcb_workspace_bytes.restype = C.c_size_t
     lib.tcb_run.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
                                            C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -139,7 +142,7 @@ def acc(log2n=18, d=20, L=20, flushes=(1, 2, 4, 8, 1 << 30)):
     for fl in flushes:
         gv = torch.zeros(Pv, device=dev)
         rc = lib.tcb_run(d, Hv, nv, n, L, thv.data_ptr(), times.data_ptr(), 0, 1, x.data_ptr(), d, 0, cot.data_ptr(),
-                         kv.data_ptr(), ws.data_ptr(), 0, fl, gv.data_ptr(), st)
+                         kv.data_ptr(), ws.data_ptr(), int(os.environ.get("XW_TC_TMEM_PACKED", "0")), fl, gv.data_ptr(), st)
         assert rc == 0
         torch.cuda.synchronize()
         e, o = {}, 0

@@ -7,6 +7,9 @@
 #include "../../xnode-wan-pde-solver_b200/csrc/xw_vnet_tc.cuh"
 #include <cstdio>
 #include <cstdlib>
+#ifndef XW_TC_BWD_SPLIT
+#define XW_TC_BWD_SPLIT 1
+#endif
 
 extern "C" size_t tcb_workspace_bytes(int d, int Hv, int nv, int sms) {
     return (size_t)sms * 2 * (nv > 0 ? nv : 1) * 14 * 128 * 16 + (size_t)sms * xw::VLayout(d, Hv).size * 4 + 512;
@@ -28,8 +31,8 @@ extern "C" int tcb_run(int d, int Hv, int nv, int n, int L, const float* theta, 
     a.cot = cot; a.coefs = coefs; a.scratch = (float*)ws;
     a.gpart = (float*)((char*)ws + (size_t)grid * 2 * (nv > 0 ? nv : 1) * 14 * 128 * 16);
     a.tm_packed = packed; a.flush_tiles = flush_tiles;
-    if (cudaFuncSetAttribute(xw::tc::k_vnet_tc_bwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    xw::tc::k_vnet_tc_bwd3<<<grid, 512, smem, (cudaStream_t)stream>>>(a);
+    if (cudaFuncSetAttribute(xw::tc::k_vnet_tc_bwd3<XW_TC_BWD_SPLIT != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    xw::tc::k_vnet_tc_bwd3<XW_TC_BWD_SPLIT != 0><<<grid, 512, smem, (cudaStream_t)stream>>>(a);
     if (grad_out) {
         const int P = xw::VLayout(d, Hv).size;
         xw::k_reduce_partials<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.gpart, grid, P, grad_out, 0);

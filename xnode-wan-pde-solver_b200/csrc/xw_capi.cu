@@ -181,8 +181,16 @@ int plan_vtile_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
 // tiles, 2.7e-3 without flushing); 4 keeps it at the level of the other tensors (dWi 8.6e-6) and takes the flush off the
 // critical path (26.8 -> 25.2 ms).  XW_TC_FLUSH overrides (tests).
 int tc_flush_tiles() { static const int v = []() { const char* e = getenv("XW_TC_FLUSH"); const int k = e ? atoi(e) : 4; return k > 0 ? k : 4; }(); return v; }
-// k_vnet_tc_fwd: MMAs of a layer issued by three warps instead of one thread (XW_TC_SPLIT=0/1)
-int tc_split_issue() { static const int v = []() { const char* e = getenv("XW_TC_SPLIT"); return e ? atoi(e) : 0; }(); return v; }
+// k_vnet_tc_fwd / k_vnet_tc_bwd3: MMAs of a layer issued by three warps instead of one thread (default; 18.9 -> 17.7 ms
+// per evaluated interior forward, 25.2 -> 24.5 ms per test-function backward at 2^20 paths).  The order in which the three 3xTF32 terms reach the accumulator then varies from run to
+// run: the values agree to fp32 rounding (1e-7), not bit for bit.  XW_TC_SPLIT=0 selects the single-issuer kernel
+// (bit-reproducible runs).
+int tc_split_issue() { static const int v = []() { const char* e = getenv("XW_TC_SPLIT"); return e ? atoi(e) : 1; }(); return v; }
+// the same for the F-op / R-op of k_vnet_tc_bwd3: OFF.  It gains 3 % (25.2 -> 24.5 ms) and is exact on every direct case, but on
+// the wide-input path at d = 100 (virtual net, test_mid_size_against_oracle) the gradients came out 5e-3 off, reproducibly
+// and unexplained (the stand-alone harness with the same shapes is exact) -- not shipped until understood; XW_TC_SPLIT_BWD=1
+// selects it for experiments.
+int tc_split_bwd() { static const int v = []() { const char* e = getenv("XW_TC_SPLIT_BWD"); return e ? atoi(e) : 0; }(); return v; }
 int tc_tmem_packed() { static const int v = []() { const char* e = getenv("XW_TC_TMEM_PACKED"); return e && e[0] == '1' ? 1 : 0; }(); return v; }
 bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
 int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
@@ -654,11 +662,15 @@ int xw_interior_forward(const xw_dims* m, const xw_domain* dom, const xw_coef* c
         const int ng = std::max(1, std::min(3, 512 / (xw::tc::NP + 2 * KA)));
         size_t sm = (size_t)(2 * xw::tc::KP * xw::tc::NP + 2 * kin * xw::tc::NP + 64) * 4 + 4 * 32 * 8 + 128;
         sm = std::max(sm, (size_t)(device()->smem_optin / 2 + 1024));          // (keeps a second CTA off the SM)
-        if (XW_SET_SMEM(xw::tc::k_vnet_tc_fwd, sm)) return 1;
         const long long nt = ((long long)n * L + 63) / 64;
         const int g3 = (int)std::max<long long>(1, std::min<long long>((nt + ng - 1) / ng, (long long)device()->sms));
-        t.split_issue = tc_split_issue();
-        xw::tc::k_vnet_tc_fwd<<<g3, 128 * ng, sm, (cudaStream_t)stream>>>(t, ng);
+        if (tc_split_issue()) {
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_fwd<true>, sm)) return 1;
+            xw::tc::k_vnet_tc_fwd<true><<<g3, 128 * ng, sm, (cudaStream_t)stream>>>(t, ng);
+        } else {
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_fwd<false>, sm)) return 1;
+            xw::tc::k_vnet_tc_fwd<false><<<g3, 128 * ng, sm, (cudaStream_t)stream>>>(t, ng);
+        }
         g_last_vnet_fwd = 3;
         return XW_CHECK_LAUNCH("k_vnet_tc_fwd");
     }
@@ -751,8 +763,13 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
         t.cot = cot_v; t.coefs = coefs_dev; t.scratch = (float*)workspace; t.gpart = (float*)((char*)workspace + pl.scratch_bytes);
         t.tm_packed = tc_tmem_packed(); t.flush_tiles = tc_flush_tiles();
-        if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, pl.smem)) return 1;
-        xw::tc::k_vnet_tc_bwd3<<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
+        if (tc_split_bwd()) {
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3<true>, pl.smem)) return 1;
+            xw::tc::k_vnet_tc_bwd3<true><<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
+        } else {
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3<false>, pl.smem)) return 1;
+            xw::tc::k_vnet_tc_bwd3<false><<<pl.grid, 512, pl.smem, (cudaStream_t)stream>>>(t);
+        }
         if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
         g_last_vnet_bwd = 3;
         return reduce_partials(t.gpart, pl.grid, xw_theta_v_size(m), grad_v, accumulate, stream);
@@ -786,8 +803,13 @@ int xw_interior_backward_v(const xw_dims* m, const xw_domain* dom, const float* 
         t.dom_kind = dom->kind; t.dp0 = dom->p0; t.dp1 = dom->p1; t.dp2 = dom->p2;
         t.cot = cot_v; t.coefs = coefs_dev; t.scratch = scratch; t.gpart = gpart; t.wbuf = wbuf; t.delta0_out = d0;
         t.tm_packed = tc_tmem_packed(); t.flush_tiles = tc_flush_tiles();
-        if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3, vp.pl.smem)) return 1;
-        xw::tc::k_vnet_tc_bwd3<<<vp.pl.grid, 512, vp.pl.smem, (cudaStream_t)stream>>>(t);
+        if (tc_split_bwd()) {
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3<true>, vp.pl.smem)) return 1;
+            xw::tc::k_vnet_tc_bwd3<true><<<vp.pl.grid, 512, vp.pl.smem, (cudaStream_t)stream>>>(t);
+        } else {
+            if (XW_SET_SMEM(xw::tc::k_vnet_tc_bwd3<false>, vp.pl.smem)) return 1;
+            xw::tc::k_vnet_tc_bwd3<false><<<vp.pl.grid, 512, vp.pl.smem, (cudaStream_t)stream>>>(t);
+        }
         if (XW_CHECK_LAUNCH("k_vnet_tc_bwd3")) return 1;
         if (reduce_partials(gpart, vp.pl.grid, vp.Pv, gradv, 0, stream)) return 1;
         xw::vv::DwxArgs da{};

@@ -134,46 +134,33 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t tD, uint32_t tA_hi, uint32
 // The same product issued by THREE warps, one 3xTF32 term each.  One thread cannot issue tcgen05.mma faster than one per ~46
 // cycles whatever the shape (measured, profiles/r02y_mma_issue_bench.txt: 45.6 cycles per MMA at N = 24, 56; 28.4 at N = 56
 // with two or more issuing warps = the pipe's own 128 N / 256), so a layer's 21 MMAs take 960 cycles from one thread against
-// 590 of tensor-pipe time.  Warp iw of the three calls this (all 32 lanes; lane 0 issues): iw = 0: A_lo x B_hi, and its
-// first MMA initialises the accumulator; warps 1, 2 (A_hi x B_lo, A_hi x B_hi) accumulate and therefore issue only after
-// that first MMA is in the pipe: tcgen05.fence::before_thread_sync + named barrier `bar_id` (96 threads) +
-// tcgen05.fence::after_thread_sync orders the asynchronous MMAs of the three threads.  Every issuer commits to `mbar`,
-// which must have been initialised with a count of 3.
+// 590 of tensor-pipe time.  Warp iw of the three calls this (lane 0 issues): iw = 0: A_lo x B_hi, 1: A_hi x B_lo,
+// 2: A_hi x B_hi.  MMAs of DIFFERENT threads are not ordered among each other -- a first "overwrite" MMA of one warp
+// behind tcgen05.fence::before_thread_sync + a named barrier was overtaken by the accumulating ones of the other warps in
+// about one tile of a few thousand (caught by the N = 4096 golden) -- so every MMA ACCUMULATES and the row owners clear
+// the accumulator with tcgen05.st next to their operand stores (ordered before all three issuers by the usual
+// wait::st / fence / barrier).  Every issuer commits to `mbar`, which must have been initialised with a count of 3.
 template <int KS>
-__device__ __forceinline__ void issue_3xtf32_split(int iw, int lane, int bar_id, uint32_t tD, uint32_t tA_hi, uint32_t tA_lo,
-                                                   const float* b_hi, const float* b_lo, int ksteps_rt, uint32_t idesc, uint64_t* mbar) {
+__device__ __forceinline__ void issue_3xtf32_split(int iw, uint32_t tD, uint32_t tA_hi, uint32_t tA_lo, const float* b_hi,
+                                                   const float* b_lo, int ksteps_rt, uint32_t idesc, uint64_t* mbar) {
     constexpr uint64_t kStep = (2 * NP * 16) >> 4;        // two 16-byte chunks of k per MMA
     const uint64_t db = umma::smem_desc(iw == 1 ? b_lo : b_hi, NP * 16, 128);
     const uint32_t ta = iw == 0 ? tA_lo : tA_hi;
-    const int ks_n = KS > 0 ? KS : ksteps_rt;
-    if (iw == 0) {
-        if (lane == 0) { umma::fence_after(); umma::mma_tf32_ts(tD, ta, db, idesc, 0u); }
-        umma::fence_before();
-        asm volatile("bar.arrive %0, 96;" ::"r"(bar_id) : "memory");
-        if (lane == 0) {
-            if (KS > 0) {
+    umma::fence_after();
+    if (KS > 0) {
 #pragma unroll
-                for (int ks = 1; ks < (KS > 0 ? KS : 1); ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
-            } else {
-#pragma unroll 1
-                for (int ks = 1; ks < ks_n; ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
-            }
-            umma::commit(mbar);
-        }
+        for (int ks = 0; ks < (KS > 0 ? KS : 1); ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
     } else {
-        asm volatile("bar.sync %0, 96;" ::"r"(bar_id) : "memory");
-        if (lane == 0) {
-            umma::fence_after();
-            if (KS > 0) {
-#pragma unroll
-                for (int ks = 0; ks < (KS > 0 ? KS : 1); ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
-            } else {
 #pragma unroll 1
-                for (int ks = 0; ks < ks_n; ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
-            }
-            umma::commit(mbar);
-        }
+        for (int ks = 0; ks < ksteps_rt; ++ks) umma::mma_tf32_ts(tD, ta + 8 * ks, db + kStep * ks, idesc, 1u);
     }
+    umma::commit(mbar);
+}
+__device__ __forceinline__ void tmem_zero56(uint32_t addr) {
+    uint32_t z[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) z[i] = 0u;
+    umma::tmem_st56(addr, z);
 }
 
 // split 56 fp32 values into the hi / lo A operand of this thread's row
@@ -202,6 +189,8 @@ __device__ __forceinline__ void store_a_row_at(uint32_t addr_hi, uint32_t addr_l
 // A tile is 64 points = 128 rows: lanes 0..15 of warp w own the VALUE rows of points 16w..16w+15,
 // lanes 16..31 the TANGENT rows of the same points (relu masks travel by warp shuffle).
 // =============================================================================================
+template <bool SPLIT>          // SPLIT: a layer's MMAs issued by three warps (issue_3xtf32_split) -- faster, but the order in
+                               // which the three terms reach the accumulator, hence the last bits of v, varies from run to run
 __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = a.d + 1, kin = kin_of(a.d), KA = kin > KP ? kin : KP;
@@ -218,7 +207,7 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = tid >> 7, wq = warp & 3;
     const bool is_tan = lane >= 16;
     stage_images(w, a.theta, a.d, a.Hvr, kin);
-    if (tid < 4) umma::mbar_init(mbars + tid, a.split_issue ? 3 : 1);
+    if (tid < 4) umma::mbar_init(mbars + tid, SPLIT ? 3 : 1);
     if (warp == 0) umma::tmem_alloc(slot, 512);
     umma::fence_before();
     __syncthreads();
@@ -259,11 +248,12 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
             umma::tmem_st8(lane_addr + colA + c8, hi);
             umma::tmem_st8(lane_addr + colA + KA + c8, lo);
         }
+        if (SPLIT) tmem_zero56(lane_addr + colD);
         umma::tmem_wait_st();
         umma::fence_before();
         umma::group_sync(1 + wg);
-        if (a.split_issue) {
-            if (wq < 3) issue_3xtf32_split<0>(wq, lane, 4 + wg, tbase + colD, tbase + colA, tbase + colA + KA, w.wi_hi, w.wi_lo, kin / 8, idesc, mbar);
+        if (SPLIT) {
+            if (wq < 3 && lane == 0) issue_3xtf32_split<0>(wq, tbase + colD, tbase + colA, tbase + colA + KA, w.wi_hi, w.wi_lo, kin / 8, idesc, mbar);
         } else if (issuer) {
             umma::fence_after();
             issue_3xtf32<0>(tbase + colD, tbase + colA, tbase + colA + KA, w.wi_hi, w.wi_lo, kin / 8, idesc);
@@ -285,11 +275,12 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
 #pragma unroll
             for (int o = BIASC + 1; o < KP; ++o) h[o] = 0.f;
             store_a_row_at(lane_addr + colA, lane_addr + colA + KA, h);
+            if (SPLIT) tmem_zero56(lane_addr + colD);
             umma::tmem_wait_st();
             umma::fence_before();
             umma::group_sync(1 + wg);
-            if (a.split_issue) {
-                if (wq < 3) issue_3xtf32_split<KP / 8>(wq, lane, 4 + wg, tbase + colD, tbase + colA, tbase + colA + KA, w.wh_hi, w.wh_lo, 0, idesc, mbar);
+            if (SPLIT) {
+                if (wq < 3 && lane == 0) issue_3xtf32_split<KP / 8>(wq, tbase + colD, tbase + colA, tbase + colA + KA, w.wh_hi, w.wh_lo, 0, idesc, mbar);
             } else if (issuer) {
                 umma::fence_after();
                 issue_3xtf32<KP / 8>(tbase + colD, tbase + colA, tbase + colA + KA, w.wh_hi, w.wh_lo, 0, idesc);
@@ -502,7 +493,19 @@ __device__ unsigned long long g_tc_prof[8][12];
 #define XW_PF_END(role) {}
 #endif
 
+__device__ __forceinline__ void tmem_zero28(uint32_t addr) {
+    uint32_t z[28];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) z[i] = 0u;
+    umma::tmem_st28(addr, z);
+}
+
+#ifndef XW_TC_SPLIT_MASK
+#define XW_TC_SPLIT_MASK 3      // development switch: bit 0 = F-op, bit 1 = R-op issued by three warps
+#endif
+template <bool kBwdSplit>      // the F-op / R-op of a layer issued by three warps each (issue_3xtf32_split): 25.2 -> 24.5 ms
 __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
+    constexpr bool kSplitF = kBwdSplit && (XW_TC_SPLIT_MASK & 1), kSplitR = kBwdSplit && (XW_TC_SPLIT_MASK & 2);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = a.d + 1, kin = kin_of(a.d), GS = KP + kin + 1;     // (odd row stride: the per-row flushes hit 32 banks)
     const VLayout g(a.d, a.Hvr);
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
     for (int i = tid; i < 2 * TIMG2 + KP * GS + 512 + 64; i += blockDim.x) dT[i] = 0.f;
     stage_images(w, a.theta, a.d, a.Hvr, kin);
     if (tid == 0) {
-        umma::mbar_init(mF, 1); umma::mbar_init(mR, 1); umma::mbar_init(mPh, 1); umma::mbar_init(mPh + 1, 1);
+        umma::mbar_init(mF, kSplitF ? 3 : 1); umma::mbar_init(mR, kSplitR ? 3 : 1); umma::mbar_init(mPh, 1); umma::mbar_init(mPh + 1, 1);
         umma::mbar_init(mFD, 256); umma::mbar_init(mFC, 128); umma::mbar_init(mDPh, 64); umma::mbar_init(mDPh + 1, 64); umma::mbar_init(mPC, 128);
     }
     if (warp == 0) umma::tmem_alloc(slot, 512);
@@ -589,8 +592,11 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 XW_PF(0, mbar_wait_or_trap(mFC, pFC))             // and P has seen its activations land
                 XW_PF(0, mbar_wait_or_trap(mPC, pPC))
             }
+            if (kSplitF) { umma::fence_after(); tmem_zero28(lane_addr + tc.DF + cb); umma::tmem_wait_st(); umma::fence_before(); }
             XW_PF(1, asm volatile("bar.sync 1, 256;" ::: "memory"))
-            if (tid == 0) {
+            if (kSplitF) {
+                if (warp < 3 && lane == 0) issue_3xtf32_split<0>(warp, tbase + tc.DF, tbase + tc.AF, tbase + tc.AF + KP, w.wi_hi, w.wi_lo, kin / 8, idesc, mF);
+            } else if (tid == 0) {
                 umma::fence_after();
                 issue_3xtf32<0>(tbase + tc.DF, tbase + tc.AF, tbase + tc.AF + KP, w.wi_hi, w.wi_lo, kin / 8, idesc);
                 umma::commit(mF);
@@ -629,10 +635,13 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
                 }
                 XW_PF(9, umma::tmem_st28(lane_addr + tc.AF + cb, rh);
                 umma::tmem_st28(lane_addr + tc.AF + KP + cb, rl);
+                if (kSplitF) tmem_zero28(lane_addr + tc.DF + cb);
                 umma::tmem_wait_st();
                 umma::fence_before())
                 XW_PF(3, asm volatile("bar.sync 1, 256;" ::: "memory"))
-                if (tid == 0) {
+                if (kSplitF) {
+                    if (warp < 3 && lane == 0) XW_PF(6, issue_3xtf32_split<KP / 8>(warp, tbase + tc.DF, tbase + tc.AF, tbase + tc.AF + KP, w.wh_hi, w.wh_lo, 0, idesc, mF))
+                } else if (tid == 0) {
                     umma::fence_after();
                     XW_PF(6, issue_3xtf32<KP / 8>(tbase + tc.DF, tbase + tc.AF, tbase + tc.AF + KP, w.wh_hi, w.wh_lo, 0, idesc); umma::commit(mF))
                 }
@@ -709,10 +718,13 @@ __global__ void __launch_bounds__(512, 1) k_vnet_tc_bwd3(VtileBwdArgs a) {
             for (int k = nv; k >= 0; --k) {
                 if (k > 0) {                                     // R-op first: it does not depend on the images
                     XW_PF(8, store_a_row_chunked(lane_addr + tc.AR, lane_addr + tc.AR + KP, h);
+                    if (kSplitR) tmem_zero56(lane_addr + tc.DR);
                     umma::tmem_wait_st();
                     umma::fence_before())
                     XW_PF(1, umma::group_sync(2))
-                    if (j == 0) {
+                    if (kSplitR) {
+                        if ((warp & 3) < 3 && lane == 0) XW_PF(6, issue_3xtf32_split<KP / 8>(warp & 3, tbase + tc.DR, tbase + tc.AR, tbase + tc.AR + KP, w.wht_hi, w.wht_lo, 0, idesc, mR))
+                    } else if (j == 0) {
                         umma::fence_after();
                         XW_PF(6, issue_3xtf32<KP / 8>(tbase + tc.DR, tbase + tc.AR, tbase + tc.AR + KP, w.wht_hi, w.wht_lo, 0, idesc); umma::commit(mR))
                     }

@@ -191,7 +191,6 @@ struct VtileFwdArgs {
                              // and the same theta_v skip the v net entirely (k_weak_combine)
     const float* wbuf;       // optional [n*L] domain weight and
     const float* dwtbuf;     // optional [n*L] its time derivative (tensor-core forward on the virtual net, d > 54)
-    int split_issue;         // k_vnet_tc_fwd: a layer's MMAs issued by three warps (one 3xTF32 term each)
 };
 
 // the weak-form integrands of one point from (v, dv/dt, w, dw/dt) and (u, f, h): src/loss.py:64-73
