@@ -28,8 +28,6 @@ constexpr int HV = 50;          // compiled capacity of the hidden width
 constexpr int KP = 56;          // padded contraction length (units 0..49, bias column 50, zeros)
 constexpr int NP = 56;          // MMA N (output units, padded)
 constexpr int BIASC = 50;
-constexpr int D_COL = 0;        // accumulator columns [0, 64)
-constexpr int A_COL = 64;       // A_hi at [64, 64 + KA), A_lo at [64 + KA, 64 + 2 KA)
 
 XW_HD constexpr int kin_of(int d) { return (d + 2 + 7) / 8 * 8; }      // (t, x, 1) padded to k-steps of 8
 
@@ -164,16 +162,6 @@ __device__ __forceinline__ void tmem_zero56(uint32_t addr) {
 }
 
 // split 56 fp32 values into the hi / lo A operand of this thread's row
-__device__ __forceinline__ void store_a_row(uint32_t lane_addr, int KA, const float (&v)[KP]) {
-    uint32_t r[KP];
-#pragma unroll
-    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
-    umma::tmem_st56(lane_addr + A_COL, r);
-#pragma unroll
-    for (int i = 0; i < KP; ++i) r[i] = __float_as_uint(v[i] - __uint_as_float(r[i]));
-    umma::tmem_st56(lane_addr + A_COL + KA, r);
-}
-
 __device__ __forceinline__ void store_a_row_at(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[KP]) {
     uint32_t r[KP];
 #pragma unroll
@@ -326,53 +314,19 @@ __global__ void __launch_bounds__(384) k_vnet_tc_fwd(VtileFwdArgs a, int ngroups
 // =============================================================================================
 // v net backward on the tensor cores:  parameter gradients of sum_p G[p] v[p],  G = k0*cot_v + k1*v + k2*w
 //
-// A tile is 128 points, thread = point = TMEM lane.  Per tile:
-//   forward : input layer + nv hidden layers as in the forward kernel (value rows only); the post-relu
-//             activations r_0..r_{nv-1} are parked in a per-CTA scratch (global memory, L2 resident,
-//             each thread re-reads exactly what it wrote);
-//   reverse : for k = nv..1   delta_k -> A operand (tensor memory) AND its transpose into shared memory;
-//             r_{k-1} (with a ones column for the bias) transposed into shared memory;
-//             R-op  delta_{k-1} = relu'(r_{k-1}) . (delta_k Wh)      [128 x 56] x [56 x 56]   (A from TMEM)
-//             P-op  dWh += delta_k^T r_{k-1}                         [56 x 128] x [128 x 56]  (both from smem,
-//                   K = the 128 points; the accumulator lives in tensor memory for the whole tile);
-//   input   : dWi += delta_0^T (t, x, 1) the same way;
-//   flush   : threads 0..55 add their accumulator rows (dWh | dbh | dWi | dbi) into an fp32 image in
-//             shared memory, so that no tensor-core accumulator ever sums more than one tile.
-// The transposed images are ordinary K-major operands ([k/4][row][4], chunk stride padded to 228 floats:
-// the 32 lanes of a warp hit 32 different banks with their scalar stores).
-// =============================================================================================
-constexpr int TCS = 228;                     // chunk stride of the transposed images (floats)
-constexpr int TIMG = 32 * TCS;               // one transposed image: 128 points = 32 chunks
-constexpr int WH_COL = 192;                  // dWh accumulator columns [192, 248)
-constexpr int WI_COL = 256;                  // dWi accumulator columns [256, 256 + kin)
-
-__device__ __forceinline__ int t_off(int row, int r) { return (r >> 2) * TCS + (row >> 3) * 32 + (row & 7) * 4 + (r & 3); }
-
-// out[m][n] (+)= sum_{r<128} A^T-image[m][r] * B^T-image[n][r]   (3xTF32, 16 k-steps of 8 points)
-__device__ __forceinline__ void issue_pop(uint32_t tD, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
-                                          uint32_t idesc, uint32_t accumulate) {
-    constexpr uint64_t kStep = (2 * TCS * 4) >> 4;
-    const uint64_t ah = umma::smem_desc(a_hi, TCS * 4, 128), al = umma::smem_desc(a_lo, TCS * 4, 128);
-    const uint64_t bh = umma::smem_desc(b_hi, TCS * 4, 128), bl = umma::smem_desc(b_lo, TCS * 4, 128);
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-            umma::mma_tf32(tD, (t == 0 ? al : ah) + kStep * ks, (t == 1 ? bl : bh) + kStep * ks, idesc, (t | ks) ? 1u : accumulate);
-    }
-}
-
-// =============================================================================================
-// The same backward as a three-stage warp-specialised pipeline (384 threads, one CTA per SM):
-//   F (warps 0-3)  : forward recompute of tile t+1, output layer, cotangent G, dWz, delta_nv -> mailbox (D_f)
-//   R (warps 4-7)  : the delta chain of tile t: delta_k -> A_r (tensor memory) and its transposed hi/lo image
-//                    (shared memory), R-op, relu mask
-//   P (warps 8-11) : builds the transposed image of (r_{k-1} | 1), issues the weight-gradient MMAs (P-op,
-//                    M = 64) as soon as both images stand, flushes the accumulators per tile
-// Thread j of every group owns point row j = TMEM lane j (a warp reaches lane quadrant warp % 4).
-// The tensor pipe then always has queued work from three independent issuers.  Every cross-group
-// hand-off is an mbarrier with a bounded wait; F's activations and relu masks travel through a
-// double-buffered per-CTA scratch in global memory (L2 resident).
+// A tile is 128 points, thread = point = TMEM lane; a three-stage warp-specialised pipeline over tiles (512 threads,
+// one CTA per SM):
+//   F (warps 0-7)  : forward recompute of tile t+1 (input layer + nv hidden layers, value rows only; two warps per lane
+//                    quadrant, 28 columns each), post-relu activations r_0..r_{nv-1} and relu masks -> a double-buffered
+//                    per-CTA scratch (global memory, L2 resident), output layer, cotangent G, dWz | dbz, delta_nv -> mailbox;
+//   R (warps 8-11) : the delta chain of tile t:  R-op  delta_{k-1} = relu'(r_{k-1}) . (delta_k Wh)   [128 x 56] x [56 x 56]
+//                    (A from tensor memory), and the transposed hi/lo image of delta_k in shared memory;
+//   P (warps 12-15): transposed hi/lo image of (r_{k-1} | 1) from the scratch and the
+//                    P-op  dWh | dbh += delta_k^T (r_{k-1} | 1)   [56 x 128] x [128 x 56]  (both operands from shared memory,
+//                    K = the 128 points, two 64-point halves with their own images / barriers / issuers);
+//                    input layer: dWi | dbi += delta_0^T (t, x, 1) the same way; the accumulators live in tensor memory
+//                    and are flushed into an fp32 image in shared memory every few tiles (xw_capi.cu, tc_flush_tiles).
+// Every cross-role hand-off is an mbarrier with a time-bounded wait.
 // =============================================================================================
 // Tensor-memory columns of k_vnet_tc_bwd3 (512 in all): accumulators D_f (56), D_r (56), dWh (112: the r_hi | r_lo blocks),
 // dWi (kin) and the TS-form A operands A_f, A_r (hi | lo, 112 each) = 448 + kin.  Up to kin = 48 every accumulator starts on a
