@@ -119,3 +119,71 @@ def test_many_iterations_ragged_sizes_stay_finite_and_deterministic():
     assert all(np.isfinite(x) and np.isfinite(y) for x, y in a), a
     for (x0, y0), (x1, y1) in zip(a, b):      # fp32 atomics in the reductions: not bit-exact, but close
         assert abs(x0 - x1) <= 1e-3 * abs(x0) + 1e-6 and abs(y0 - y1) <= 1e-3 * abs(y0) + 1e-6, (a, b)
+
+
+@pytest.mark.parametrize("d", [20, 50, 100])
+def test_forward_values_agree_point_by_point_with_the_fp32_kernels(lib, d):
+    """Every ROW of the tensor-core forward -- v and dv/dt of every point (test-function cache) and both cotangent seeds
+    -- against the FP32 tile engine on the same 2^15+13 paths, several launches.  Sums and gradients (the golden tests)
+    average over the points; this pins each of them: a tile whose MMAs raced (three issuing warps accumulate into one
+    tensor-memory accumulator, xw_vnet_tc.cuh issue_3xtf32_split) or a k-step that got lost would show up here as a row
+    that is off by far more than fp32 rounding.  d = 50 is the widest direct input (kin = 56), d = 100 runs on the virtual
+    net of input width Hv."""
+    import ctypes as C
+    L_ = xw._lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(100 + d)
+    n, L = (1 << 15) + 13, 20
+    dims = L_.Dims(d, 20, 10, 8, 50, 9, 1)
+    dom = L_.Domain(0, -1.0, 1.0, 0.0)
+    Pu, Pv = lib.theta_sizes(dims)
+    thu = (torch.rand(Pu, device=dev, generator=g) - 0.5) * 0.5
+    thv = (torch.rand(Pv, device=dev, generator=g) - 0.5) * (0.5 if d <= 50 else 0.3)
+    x = torch.rand(n, d, device=dev, generator=g) * 2 - 1
+    xv = torch.rand(n, d, device=dev, generator=g) * 2 - 1
+    times = torch.sort(torch.rand(L, device=dev, generator=g))[0].contiguous()
+    times[0] = 0.0
+    h = torch.randn(n, device=dev, generator=g)
+    gh = torch.zeros(n, d, device=dev)
+    f = torch.randn(n * L, device=dev, generator=g)
+    coef = L_.Coef(0.0, -1.0, None, None)
+    pts = L_.Points(times.data_ptr(), 0, 1, xv.data_ptr(), d, 0)
+    wsb = lib.workspace_bytes(dims, n, L)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+    nvc = lib.cdll.xw_vcache_floats(C.byref(dims), n, L)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(impl):
+        old = os.environ.get("XW_VNET_IMPL")
+        os.environ["XW_VNET_IMPL"] = impl
+        try:
+            sums = torch.zeros(L_.NSUMS, dtype=torch.float64, device=dev)
+            cu, cv = torch.zeros(n * L, device=dev), torch.zeros(n * L, device=dev)
+            vc = torch.zeros(nvc, device=dev)
+            lib.call("xw_interior_forward", C.byref(dims), C.byref(dom), C.byref(coef), thu.data_ptr(), thv.data_ptr(),
+                     x.data_ptr(), d, times.data_ptr(), L, C.byref(pts), h.data_ptr(), gh.data_ptr(), f.data_ptr(), n,
+                     sums.data_ptr(), cu.data_ptr(), cv.data_ptr(), None, ws.data_ptr(), wsb, st, None, vc.data_ptr(), 1, None,
+                     nvc, 0)
+            torch.cuda.synchronize()
+            return vc[:4 * n * L].view(n * L, 4).clone(), cu, cv, sums.cpu().numpy()
+        finally:
+            if old is None:
+                os.environ.pop("XW_VNET_IMPL", None)
+            else:
+                os.environ["XW_VNET_IMPL"] = old
+    ref_vc, ref_cu, ref_cv, ref_s = run("tile")
+    vs, ts = float(ref_vc[:, 0].abs().max()), float(ref_vc[:, 1].abs().max())
+    assert vs > 1e-3 and ts > 1e-5
+    for rep in range(4):
+        vc, cu, cv, s = run("tc")
+        assert (lib.cdll.xw_last_vnet_impl() & 15) == 3
+        # v is continuous in the pre-activations: EVERY point agrees to fp32 rounding (an MMA covers all 128 rows of a
+        # tile, value and tangent rows alike: a lost or raced update would move v)
+        assert float((vc[:, 0] - ref_vc[:, 0]).abs().max()) <= 2e-5 * vs, (d, rep)
+        assert float((cu - ref_cu).abs().max()) <= 5e-5 * float(ref_cu.abs().max()), (d, rep)
+        assert float((cv - ref_cv).abs().max()) <= 5e-5 * float(ref_cv.abs().max()), (d, rep)
+        # dv/dt is NOT continuous: a pre-activation within rounding of 0 flips its relu mask and moves the tangent of that
+        # point by O(weight) -- a few points in 10^5 between any two fp32 evaluation orders (3e8 pre-activations here)
+        off = ((vc[:, 1] - ref_vc[:, 1]).abs() > 5e-5 * ts).float().mean().item()
+        assert off <= 5e-4, (d, rep, off)
+        assert np.allclose(s[:5], ref_s[:5], rtol=1e-4, atol=1e-4 * np.abs(ref_s[:5]).max())
