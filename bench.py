@@ -390,6 +390,20 @@ def run_ours(args):
                    "h2d_bytes_per_step": sum(t.nbytes for t in host_nlc), "d2h_bytes_per_step": 16, "loss_u": last.get("lu_nlc"),
                    "layout": "reference [N,L,C] fp32 from pinned host memory (what /root/reference/src/dataset.py:321 moves)"}
         del host_nlc
+    # ------------------------------------------------------------------ opt-in kernel variants on the same resident sample
+    # XW_TC_SPLIT=1: a layer's tcgen05 MMAs of the forward kernel issued by three warps (faster; values reproducible to fp32
+    # rounding instead of bit for bit: xw_capi.cu tc_split_issue).  The headline `value` is the DEFAULT configuration.
+    variants = {}
+    if world == 1:
+        os.environ["XW_TC_SPLIT"] = "1"
+        try:
+            for _ in range(2):
+                step_resident()
+            ms_v = timed(step_resident, args.steps)
+            variants["XW_TC_SPLIT=1"] = {"ms_per_step": ms_v, "value": pp_step / (ms_v * 1e-3), "unit": "path-points/s",
+                                         "note": "forward tcgen05 kernel with three issuing warps per tile stream (not bit-reproducible from run to run)"}
+        finally:
+            os.environ.pop("XW_TC_SPLIT", None)
     del solver, points
     torch.cuda.empty_cache()
 
@@ -514,6 +528,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "loss_u": last.get("lu"), "loss_v": last.get("lv")},
             "e2e_nlc": e2e_nlc,
             "strong": strong,
+            "variants": variants,
             "shard_check": check,
             "gpu_launches": launches,
             "roofline": roofline,

@@ -153,9 +153,10 @@ def test_forward_values_agree_point_by_point_with_the_fp32_kernels(lib, d):
     nvc = lib.cdll.xw_vcache_floats(C.byref(dims), n, L)
     st = torch.cuda.current_stream().cuda_stream
 
-    def run(impl):
-        old = os.environ.get("XW_VNET_IMPL")
+    def run(impl, split="0"):
+        old, old_s = os.environ.get("XW_VNET_IMPL"), os.environ.get("XW_TC_SPLIT")
         os.environ["XW_VNET_IMPL"] = impl
+        os.environ["XW_TC_SPLIT"] = split
         try:
             sums = torch.zeros(L_.NSUMS, dtype=torch.float64, device=dev)
             cu, cv = torch.zeros(n * L, device=dev), torch.zeros(n * L, device=dev)
@@ -167,15 +168,16 @@ def test_forward_values_agree_point_by_point_with_the_fp32_kernels(lib, d):
             torch.cuda.synchronize()
             return vc[:4 * n * L].view(n * L, 4).clone(), cu, cv, sums.cpu().numpy()
         finally:
-            if old is None:
-                os.environ.pop("XW_VNET_IMPL", None)
-            else:
-                os.environ["XW_VNET_IMPL"] = old
+            for k, v in (("XW_VNET_IMPL", old), ("XW_TC_SPLIT", old_s)):
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
     ref_vc, ref_cu, ref_cv, ref_s = run("tile")
     vs, ts = float(ref_vc[:, 0].abs().max()), float(ref_vc[:, 1].abs().max())
     assert vs > 1e-3 and ts > 1e-5
-    for rep in range(4):
-        vc, cu, cv, s = run("tc")
+    for rep in range(6):           # the default single-issuer kernel twice, the three-issuer variant (XW_TC_SPLIT=1) four times
+        vc, cu, cv, s = run("tc", "0" if rep < 2 else "1")
         assert (lib.cdll.xw_last_vnet_impl() & 15) == 3
         # v is continuous in the pre-activations: EVERY point agrees to fp32 rounding (an MMA covers all 128 rows of a
         # tile, value and tangent rows alike: a lost or raced update would move v)

@@ -181,11 +181,13 @@ int plan_vtile_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
 // tiles, 2.7e-3 without flushing); 4 keeps it at the level of the other tensors (dWi 8.6e-6) and takes the flush off the
 // critical path (26.8 -> 25.2 ms).  XW_TC_FLUSH overrides (tests).
 int tc_flush_tiles() { static const int v = []() { const char* e = getenv("XW_TC_FLUSH"); const int k = e ? atoi(e) : 4; return k > 0 ? k : 4; }(); return v; }
-// k_vnet_tc_fwd / k_vnet_tc_bwd3: MMAs of a layer issued by three warps instead of one thread (default; 18.9 -> 17.7 ms
-// per evaluated interior forward, 25.2 -> 24.5 ms per test-function backward at 2^20 paths).  The order in which the three 3xTF32 terms reach the accumulator then varies from run to
-// run: the values agree to fp32 rounding (1e-7), not bit for bit.  XW_TC_SPLIT=0 selects the single-issuer kernel
-// (bit-reproducible runs).
-int tc_split_issue() { static const int v = []() { const char* e = getenv("XW_TC_SPLIT"); return e ? atoi(e) : 1; }(); return v; }
+// k_vnet_tc_fwd: MMAs of a layer issued by three warps instead of one thread (XW_TC_SPLIT=1; 18.9 -> 17.2 ms per evaluated
+// interior forward at 2^20 paths).  The order in which the three 3xTF32 terms reach the accumulator then varies from run to
+// run: v agrees to fp32 rounding (1e-7) at every point, not bit for bit -- and dv/dt, which is discontinuous where a
+// pre-activation crosses 0, may land on the other side of a relu kink at the few points that sit within rounding of one.
+// The DEFAULT is the single-issuer kernel: bit-reproducible runs (and tests).  Read per call, so that one process can
+// measure both (bench.py `variants`).
+int tc_split_issue() { const char* e = getenv("XW_TC_SPLIT"); return e ? atoi(e) : 0; }
 // the same for the F-op / R-op of k_vnet_tc_bwd3: OFF (XW_TC_SPLIT_BWD=1 selects it).  It gains 3 % (25.2 -> 24.5 ms) and is as
 // accurate as the single-issuer kernel against fp64 (tools/tc_prof.py acc), but it lands on the other side of a relu kink
 // more often: the parameter gradient of this net is DISCONTINUOUS where a pre-activation crosses 0, so any two fp32
@@ -193,7 +195,7 @@ int tc_split_issue() { static const int v = []() { const char* e = getenv("XW_TC
 // rounding of 0 (seed sweep at d = 20 and d = 100, 6 seeds each: single issuer 1-2 configurations off by 2e-4..6e-4 in dWi,
 // three issuers 3 off by 9e-4..1e-2; the others 4e-6).  The deterministic kernel keeps test_mid_size_against_oracle
 // reproducible run after run; the run-to-run varying one would make it flaky.
-int tc_split_bwd() { static const int v = []() { const char* e = getenv("XW_TC_SPLIT_BWD"); return e ? atoi(e) : 0; }(); return v; }
+int tc_split_bwd() { const char* e = getenv("XW_TC_SPLIT_BWD"); return e ? atoi(e) : 0; }
 int tc_tmem_packed() { static const int v = []() { const char* e = getenv("XW_TC_TMEM_PACKED"); return e && e[0] == '1' ? 1 : 0; }(); return v; }
 bool vtc_bwd_ok(const xw_dims* m) { return xw::tc::kin_of(m->d) <= xw::tc::KP; }
 int plan_vtc_bwd(const xw_dims* m, int n, int L, VtileBwdPlan* p) {
