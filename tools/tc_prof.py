@@ -30,7 +30,7 @@ def build():
     from importlib import import_module
     b = import_module("xnode-wan-pde-solver_b200.build")
     flags = [f for f in b.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
-    split = ["-DXW_TC_BWD_SPLIT=%s" % os.environ.get("XW_TC_BWD_SPLIT", "1"), "-DXW_TC_SPLIT_MASK=%s" % os.environ.get("XW_TC_SPLIT_MASK", "3")]
+    split = ["-DXW_TC_BWD_SPLIT=%s" % os.environ.get("XW_TC_BWD_SPLIT", "0"), "-DXW_TC_SPLIT_MASK=%s" % os.environ.get("XW_TC_SPLIT_MASK", "3")]
     suffix = os.environ.get("TCB_SUFFIX", "")
     for name, extra in (("libtcb%s.so" % suffix, split), ("libtcb_prof%s.so" % suffix, ["-DXW_TC_PROF"] + split)):
         cmd = ["nvcc"] + flags + extra + ["-o", os.path.join(TCB, name), os.path.join(TCB, "tcb.cu")]
@@ -57,7 +57,7 @@ def run(log2n=20, d=20, L=20, reps=3, packed=0, flush=4):
     st = torch.cuda.current_stream().cuda_stream
     out = {"log2n": log2n, "dim": d, "packed": packed, "flush_tiles": flush}
     for name in ("libtcb.so", "libtcb_prof.so"):
-        lib = C.CDLL(os.path.join(TCB, name))
+        lib = C.CDLL(os.path.join(TCB, name.replace(".so", os.environ.get("TCB_SUFFIX", "") + ".so")))
         lib.tcb_workspace_bytes.restype = C.c_size_t
         lib.tcb_run.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
                                                C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

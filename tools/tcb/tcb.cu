@@ -8,7 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #ifndef XW_TC_BWD_SPLIT
-#define XW_TC_BWD_SPLIT 1
+#define XW_TC_BWD_SPLIT 0
 #endif
 
 extern "C" size_t tcb_workspace_bytes(int d, int Hv, int nv, int sms) {
