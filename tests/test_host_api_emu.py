@@ -629,3 +629,72 @@ def test_on_device_sphere_samplers_build_the_reference_groups(cls):
     assert [g.shape[0] for g in bd] == [n for n in want if n]
     for g in bd:
         assert g.shape[1] == 1 and float(dev.func_w(g).abs().max()) < 1e-9           # on the sphere of that time
+
+
+def test_error_norms_keep_the_solution_values_with_the_sample(emu):
+    """stop() -> rel_err runs after every u sub-iteration on the same sample (reference src/training.py:142): func_u_sol
+    is evaluated once per sample, the numbers equal the straightforward evaluation, an in-place edit of the sample drops
+    the kept values"""
+    case = G.load("cube_d3_small_nets")
+    s, prob = make_solver(case)
+    torch.manual_seed(2)
+    dom = s.new_domain()
+    X = dom.interior(40)
+    calls = [0]
+    sol = lambda Z: (calls.__setitem__(0, calls[0] + 1), prob.func_u_sol(Z))[1]
+
+    def plain(Z):
+        pred = s.u_net(Z).materialize().squeeze()
+        u = prob.func_u_sol(Z)
+        return ((dom.V() * torch.mean(torch.abs(u - pred) ** 2)) ** 0.5) / ((dom.V() * torch.mean(torch.abs(u) ** 2)) ** 0.5)
+    r1 = xw.rel_err(X, s.u_net, sol, 2, dom.V(), 40)
+    r2 = xw.rel_err(X, s.u_net, sol, 2, dom.V(), 40)
+    assert calls[0] == 1
+    assert float(r1) == float(r2) == float(plain(X))
+    X[:, :, 1].mul_(0.5)                    # the sample changes in place: version counter moves
+    r3 = xw.rel_err(X, s.u_net, sol, 2, dom.V(), 40)
+    assert calls[0] == 2 and float(r3) == float(plain(X)) and float(r3) != float(r1)
+    other = lambda Z: prob.func_u_sol(Z) * 2.0          # another callable on the same sample is not served from the cache
+    n = xw.L_norm(X, s.u_net, 2, other, dom.V(), 40, error=False)
+    assert abs(float(n) - 2.0 * float(xw.L_norm(X, s.u_net, 2, sol, dom.V(), 40, error=False))) < 1e-12
+
+
+def test_train_draws_its_samples_in_the_reference_order(emu, monkeypatch):
+    """train() draws the next iteration's domain and sample while the GPU still runs the v-steps; the ORDER of the draws
+    (domain_k, sample_k, logging sample_k, domain_k+1, ...; reference src/training.py:114-115, 165) must not change, or a
+    seed would no longer give the reference's samples"""
+    case = G.load("cube_d3_small_nets")
+    seen = []
+
+    def record_train(log_l2):
+        s, _ = make_solver(case)
+        s.iterations, s.keep_l2_history = 3, log_l2
+        torch.manual_seed(11)
+        seen.clear()
+        real_domain = s.new_domain
+        s.new_domain = lambda **kw: (seen.append(("domain",)), real_domain(**kw))[1]
+        real_loader = xw.training.Comb_loader
+
+        class Loader(real_loader):
+            def __init__(self, *a):
+                super().__init__(*a)
+                seen.append(("sample", float(self.interioru[0, 0, 1]), float(self.boundary[-1, 0, 2])))
+        monkeypatch.setattr(xw.training, "Comb_loader", Loader)
+        s.train()
+        monkeypatch.setattr(xw.training, "Comb_loader", real_loader)
+        return list(seen)
+
+    def sequential(log_l2):
+        s, _ = make_solver(case)
+        torch.manual_seed(11)
+        out = []
+        n_r, n_b = s.local_counts()
+        for k in range(3):
+            dom = s.new_domain()
+            out.append(("domain",))
+            for _ in range(2 if log_l2 else 1):
+                p = xw.Comb_loader(n_r, n_b, dom, "cpu")
+                out.append(("sample", float(p.interioru[0, 0, 1]), float(p.boundary[-1, 0, 2])))
+        return out
+    for log_l2 in (True, False):
+        assert record_train(log_l2) == sequential(log_l2)

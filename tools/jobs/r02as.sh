@@ -1,0 +1,2 @@
+#!/bin/bash
+PROBE_COLD=1 PROBE_SYNC=0 timeout 300 python tools/ttt_probe.py 2>&1 | tail -1

@@ -47,6 +47,7 @@ def stop(sv, points, domain):
     trace.append(r)
     return False
 s.stop = stop
+s.keep_l2_history = False        # as bench.py's time_to_target: the per-iteration L2 on a fresh sample is logging only
 pr = cProfile.Profile()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
@@ -57,6 +58,6 @@ torch.cuda.synchronize()
 out["train_40_outer_iterations_s"] = time.perf_counter() - t0
 out["train_ms_per_sub_iter"] = 1e3 * out["train_40_outer_iterations_s"] / 80
 buf = io.StringIO()
-pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
 print(buf.getvalue()[:6000], file=sys.stderr)
 print(json.dumps(out))

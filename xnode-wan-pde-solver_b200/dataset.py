@@ -48,6 +48,7 @@ class Hypercube:
         self.dim, self.T0, self.T, self.N_t = dim, T0, T, N_t
         self.sample_device = sample_device
         self.collapsed = collapsed      # yield CollapsedPaths(times, x) instead of dense [N, L, C]
+        self.pin_host = False           # host-sampled dense tensors in page-locked memory (asynchronous H2D; set by the solver)
         if times is None:
             times = torch.empty(N_t).uniform_(T0, T).sort(0).values
             times[0], times[-1] = T0, T
@@ -64,6 +65,9 @@ class Hypercube:
         if self.collapsed:
             return CollapsedPaths(self.times.to(x.device), x[:, 0, :].contiguous())
         t = self.times.to(x.device).reshape(1, self.N_t, 1).expand(n, self.N_t, 1)
+        if self.pin_host and x.device.type == "cpu":
+            out = torch.empty(n, self.N_t, self.dim + 1, dtype=x.dtype, pin_memory=True)
+            return torch.cat((t, x.expand(n, self.N_t, self.dim)), dim=2, out=out)
         return torch.cat((t, x.expand(n, self.N_t, self.dim)), dim=2)
 
     def interior(self, N_r: int):
@@ -153,7 +157,7 @@ class Comb_loader:
         stream = stream or _copy_stream(dev)
         stream.wait_stream(torch.cuda.current_stream(dev))        # the tensors being replaced may still be in use
         with torch.cuda.stream(stream):
-            trip = (self._dev(self.interioru, "h"), self._dev(self.interiorv, "h"), self._dev(self.boundary, "h"))
+            trip = tuple(self._dev(t, "h", publish=False) for t in (self.interioru, self.interiorv, self.boundary))
             ev = torch.cuda.Event()
             ev.record(stream)
         self._cache[0] = trip
@@ -163,10 +167,20 @@ class Comb_loader:
     def __len__(self):
         return len(self.interioru) if isinstance(self.interioru, list) else 1
 
-    def _dev(self, t, start):
+    def _dev(self, t, start, publish=True):
         out = t.to(self.device, non_blocking=True)
         out._xw_start = start
+        if publish:
+            self._publish(t, out)
         return out
+
+    @staticmethod
+    def _publish(t, out):
+        """the error norms evaluated on this sample (aux.L_norm <- stop(), every u sub-iteration) reuse the device copy
+        instead of moving the host tensor again; the version counter guards against in-place edits of the sample.
+        (A prefetched copy is published once the consumer's stream has been ordered after it, in __getitem__.)"""
+        if out is not t:
+            t._xw_dev = ((t.times._version, t.x._version) if hasattr(t, "times") else t._version, out)
 
     def __getitem__(self, idx):
         is_list = isinstance(self.interioru, list)
@@ -180,6 +194,8 @@ class Comb_loader:
             for t in trip:                      # the caching allocator must not recycle them while `cur` still reads
                 for part in ((t.times, t.x) if hasattr(t, "times") else (t,)):
                     part.record_stream(cur)
+            for t, out in zip((self.interioru, self.interiorv, self.boundary), trip):
+                self._publish(t, out)
             self._pending = None
         if idx not in self._cache:      # one H2D per sample (the reference re-copies on every access)
             if is_list:

@@ -184,6 +184,21 @@ class NeuralODE(nn.Module):
             return self.h(inputs[:, 0, :])
         return self.g(inputs[:, 0, :].unsqueeze(1)).reshape(-1)
 
+    def _initial_scalar_f32(self, inputs, kind):
+        """h / g on time-row 0 as the kernels take it; it does not depend on the parameters, so repeated evaluations on
+        one sample (stop() after every u sub-iteration, reference src/training.py:142) compute it once"""
+        ver = (inputs.times._version, inputs.x._version) if isinstance(inputs, CollapsedPaths) else inputs._version
+        fn = self.h if kind == "h" else self.g
+        kept = getattr(inputs, "_xw_s0", None)
+        if kept is not None and kept[0] == ver and kept[1] is fn:
+            return kept[2]
+        s0 = hotpath.as_f32(self.initial_scalar(inputs.detach(), kind))
+        try:
+            inputs._xw_s0 = (ver, fn, s0)
+        except AttributeError:
+            pass
+        return s0
+
     def evaluate(self, inputs):
         kind = self.start_kind(inputs)
         if inputs.shape[1] == 1 and kind == "h":
@@ -192,7 +207,7 @@ class NeuralODE(nn.Module):
             return self.final_linear(self.initial_layers(h_))
         if kind == "pad":
             return self._evaluate_from_inside(inputs)
-        s0 = hotpath.as_f32(self.initial_scalar(inputs.detach(), kind))
+        s0 = self._initial_scalar_f32(inputs, kind)
         if isinstance(inputs, CollapsedPaths):
             xs, ts = hotpath.as_f32(inputs.x), hotpath.as_f32(inputs.times)
             u = hotpath.xnode_eval(self.spec(), self.kernel_parameters(), xs, 0, xs.shape[1], ts, s0, xs.shape[0])

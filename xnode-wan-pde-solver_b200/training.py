@@ -181,6 +181,18 @@ class NODE_WAN_solver:
         self.av_l = 0
         self.history = {"loss_u": [], "loss_v": [], "L2": [], "time": []}
 
+    @property
+    def av_l(self):
+        """loss of the last u sub-iteration (reference src/training.py:136); synchronises on first access"""
+        if self._av_pending is not None:
+            self._av_value = sum(v.item() for v in self._av_pending)
+            self._av_pending = None
+        return self._av_value
+
+    @av_l.setter
+    def av_l(self, value):
+        self._av_pending, self._av_value = None, value
+
     def new_domain(self, **kw):
         s = self.setup
         if getattr(self, "sample_on_device", False):
@@ -188,6 +200,8 @@ class NODE_WAN_solver:
         if getattr(self, "collapsed_layout", False) and self.domain is _dataset.Hypercube:
             kw.setdefault("collapsed", True)       # (only the cube repeats ONE time grid for every path)
         dom = self.domain(s['shape_param'], s['dim'], s['T0'], s['T'], s['N_t'], **kw)
+        if torch.device(self.device).type == "cuda" and hasattr(dom, "pin_host") and kw.get("sample_device") is None:
+            dom.pin_host = True         # samples drawn on the host land in page-locked memory: their H2D copy is asynchronous
         if getattr(self, "world", 1) > 1:          # the time grid must be the same on every rank
             t = dom.times.to(self.device)
             torch.distributed.broadcast(t, src=0)
@@ -410,18 +424,26 @@ class NODE_WAN_solver:
         t_start = time.time()
         times = [t_start]
         loss_u = loss_v = None
+        ahead = None
         for k in range(self.iterations):
-            domain = self.new_domain()
             n_r, n_b = self.local_counts()
-            points = Comb_loader(n_r, n_b, domain, self.device)
+            if ahead is None:
+                domain = self.new_domain()
+                points = Comb_loader(n_r, n_b, domain, self.device)
+            else:
+                domain, points = ahead
             for i in range(self.n1):
                 loss_u = self.sub_step("u", domain, points)
-                self.av_l = sum(v.item() for v in self._last_losses)     # (all-reduced sums: identical on every rank)
+                # `av_l` (sum of the batch losses; all-reduced sums: identical on every rank) is read from the device the
+                # first time someone looks at it: stop() enqueues its evaluation behind the sub-step BEFORE the host
+                # waits for the loss value, so its host-side work runs while the GPU is still busy with the sub-step
+                self._av_pending = list(self._last_losses)
+                stopped = self.stop is not None and self._agree(self.stop(self, points.interioru, domain))
                 past_losses.append(self.av_l)
                 if self.log_json and self.rank == 0:
                     with open('losses_NODE_' + str(self.setup['dim']) + '.json', 'w') as fh:
                         json.dump(past_losses, fh)
-                if self.stop is not None and self._agree(self.stop(self, points.interioru, domain)):
+                if stopped:
                     if self.rank == 0:
                         torch.save(self.u_net.state_dict(), os.path.join(self.path, 'best_model_weights_NODE.pth'))
                         print('Stopping Criterion Reached')
@@ -434,10 +456,18 @@ class NODE_WAN_solver:
             for j in range(self.n2):
                 loss_v = self.sub_step("v", domain, points)
             self._warm += 1
-            L2 = None
+            # Nothing above waited for the v-steps: the host draws the samples it needs next WHILE the GPU runs them --
+            # the logging sample of this iteration, then the domain and sample of the next one, in the order the
+            # reference draws them (src/training.py:114-115, 165), so the RNG stream is the reference's.
+            L2 = fresh = None
             if self.func_u_sol is not None and (self.log_json or report or self.keep_l2_history):
                 # (reference src/training.py:165-170: a fresh sample and one more forward, for logging only)
                 fresh = Comb_loader(n_r, n_b, domain, self.device)
+            ahead = None
+            if k + 1 < self.iterations:
+                domain_next = self.new_domain()
+                ahead = (domain_next, Comb_loader(n_r, n_b, domain_next, self.device).prefetch())
+            if fresh is not None:
                 L2 = L_norm(fresh.interioru, self.u_net, self.p, self.func_u_sol, domain.V(), n_r)
                 if self.world > 1:         # shards of equal size: the global L^p error is the p-mean of the shard errors
                     Lp = L2.detach().double() ** self.p
