@@ -270,3 +270,21 @@ def test_prefetched_sample_equals_synchronous_copy():
     # (not bit for bit: the forward tcgen05 kernel issues a layer's three 3xTF32 terms from three warps and the order in
     # which they reach the accumulator varies from run to run -- fp32 rounding of v, 1e-7; XW_TC_SPLIT=0 is bit-reproducible)
     assert abs(vals[0] - vals[1]) <= 2e-6 * abs(vals[0])
+
+
+def test_boundary_pass_beside_the_interior_forward_gives_the_same_step(monkeypatch):
+    """small samples run the boundary pass on a second stream beside the interior forward (hotpath.forward_sums):
+    same loss and gradients as the sequential order (the two passes share nothing but disjoint slots of `sums`)"""
+    case = G.load("cube_d5_alpha1_randbias")
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("XW_CONCURRENT_BOUNDARY", flag)
+        s, _ = make_solver(case, DEV)
+        val, grads = eval_phase(s, case, "u", DEV)
+        torch.cuda.synchronize()
+        out[flag] = (val.item(), {k: val.components[k].item() for k in ("I", "S", "init", "bdry")}, grads)
+    assert abs(out["0"][0] - out["1"][0]) <= 1e-9 * abs(out["0"][0])
+    for k, v in out["0"][1].items():
+        assert abs(v - out["1"][1][k]) <= 1e-9 * abs(v) + 1e-300
+    for a, b in zip(out["0"][2], out["1"][2]):
+        assert G.rel(a, b) < 1e-6

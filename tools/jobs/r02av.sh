@@ -1,0 +1,9 @@
+#!/bin/bash
+PROBE_SYNC=1 timeout 300 python tools/ttt_probe.py 2>&1 | tail -1
+PROBE_SYNC=0 timeout 300 python tools/ttt_probe.py 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --nlc-max-gb 0 > gpurun_out/r02av_bench.json 2>gpurun_out/r02av_bench.err; echo rc=$?
+python - <<'PY'
+import json
+t=open("gpurun_out/r02av_bench.json").read(); j=json.loads(t[t.index('{"metric'):]); print({k:v for k,v in j["time_to_target"].items() if k in ("sub_iters","seconds","ms_per_sub_iter","final_rel_l2")})
+PY

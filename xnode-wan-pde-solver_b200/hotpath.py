@@ -11,6 +11,7 @@ runs in the sm_100a kernels behind the C ABI (include/xnode_wan_b200.h).  No CPU
 tensors or a missing library raise.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -228,6 +229,22 @@ class _Workspace:
 
 
 _WS = _Workspace()
+_WS_SIDE = _Workspace()           # workspace of the boundary pass when it runs beside the interior forward (forward_sums)
+_SIDE_STREAMS = {}
+CONCURRENT_BOUNDARY_MAX_PATHS = 16384     # one lane per path: below this a launch is less than one wave of the XNODE kernels
+
+
+def _side_stream(dev):
+    if dev not in _SIDE_STREAMS:
+        _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
+    return _SIDE_STREAMS[dev]
+
+
+def _concurrent_boundary(n, nb):
+    flag = os.environ.get("XW_CONCURRENT_BOUNDARY")
+    if flag is not None:
+        return flag == "1"
+    return max(n, nb) <= CONCURRENT_BOUNDARY_MAX_PATHS
 
 
 def flatten_params(params):
@@ -279,6 +296,16 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
     cot_u = torch.empty(N * L, dtype=torch.float32, device=dev)
     cot_v = torch.empty(N * L, dtype=torch.float32, device=dev)
     cdom, ccoef, pts = dom.c(), coef.c(), batch.points()
+    # Small samples (the shipped N = 4000: 125 warps on 148 SMs) leave most of the GPU idle and every kernel is one
+    # dependent chain per path: the boundary pass (forward + reverse sweep of its own paths, own slots of `sums`, own
+    # gradient buffer) does not depend on the interior forward, so it runs beside it on a second stream with its own
+    # workspace.  Under CUDA-graph capture the fork / join become parallel branches of the graph.  Full waves gain nothing.
+    side, ws_b, st_b = None, ws, st
+    if with_boundary and dev.type == "cuda" and _concurrent_boundary(N, batch.Nb):
+        side = _side_stream(dev)
+        ws_b = _WS_SIDE.get(dev, wsb)
+        side.wait_stream(torch.cuda.current_stream(dev))                # fork: inputs, `sums` and the gradient buffer are ready
+        st_b = C.c_void_p(side.cuda_stream)
     _call(lib, "xw_interior_forward", dev, C.byref(dims), C.byref(cdom), C.byref(ccoef), _ptr(theta_u), _ptr(theta_v),
              C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), L, C.byref(pts),
              _ptr(batch.h), _ptr(batch.grad_h), _ptr(batch.f), N, _ptr(sums), _ptr(cot_u), _ptr(cot_v), None,
@@ -288,7 +315,9 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
         gscale = float(alpha) / (batch.Nb_glob * batch.Lb)
         _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
                  batch.xb_sn, _ptr(batch.times_b), batch.Lb, _ptr(batch.sb), _ptr(batch.g), batch.Nb, gscale,
-                 _ptr(sums), _ptr(boundary_grad), 0, _ptr(ws), ws.numel(), st)
+                 _ptr(sums), _ptr(boundary_grad), 0, _ptr(ws_b), ws_b.numel(), st_b)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)          # join: everything after this sees both passes
     return sums, cot_u, cot_v
 
 
