@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define XW_ABI_VERSION 3
+#define XW_ABI_VERSION 4
 
 enum { XW_SOLVER_EULER = 0, XW_SOLVER_MIDPOINT = 1, XW_SOLVER_RK4 = 2 };
 enum { XW_DOMAIN_CUBE = 0, XW_DOMAIN_CONE = 1, XW_DOMAIN_HOURGLASS = 2 };
@@ -167,6 +167,15 @@ int xw_interior_backward_v(const xw_dims* dims, const xw_domain* dom, const floa
  * (optional): receives the updated parameters in fp32 = the theta_u / theta_v argument of the next forward call. */
 int xw_adam_step(double* params, const float* grad, double* exp_avg, double* exp_avg_sq, long long* step,
                  float* params_f32, int n, double lr, double beta1, double beta2, double eps, void* stream);
+
+/* The scalars of one sub-step from the (all-reduced) sums, in fp64 on the device, one launch (ABI v4).  Replaces the
+ * arithmetic of /root/reference/src/loss.py:64-76 (I, S), :78-90 (init, bdry, int) and :92-96 (loss u / v) on the eight
+ * sums, and forms the coefficients `coefs_dev` of the backward entries above:
+ *   out[0] = loss: phase 0 (u): log(I^2) - log(S) + alpha (init + bdry);  phase 1 (v): -(log(I^2) - log(S))
+ *   out[1..4] = I, S, init, bdry          out[5..7] = k0, k1, k2
+ * n_glob, nb_glob: GLOBAL path counts (all ranks); nb_glob = 0: no boundary batch (bdry = 0). */
+int xw_loss_scalars(const double* sums, int phase, double V, double n_glob, double L, double nb_glob, double Lb,
+                    double alpha, double side, double* out, void* stream);
 
 /* FP32-FMA micro-benchmark used as the roofline denominator: runs `iters`
  * dependent-chain FFMA blocks on every SM and returns the FLOP count in *flops_host. */

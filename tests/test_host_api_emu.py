@@ -698,3 +698,28 @@ def test_train_draws_its_samples_in_the_reference_order(emu, monkeypatch):
         return out
     for log_l2 in (True, False):
         assert record_train(log_l2) == sequential(log_l2)
+
+
+def test_loss_scalars_entry_equals_the_torch_arithmetic(emu):
+    """xw_loss_scalars (one launch) against hotpath.loss_from_sums + the coefficient formulas it replaced"""
+    import ctypes as C
+    from types import SimpleNamespace
+    hp = xw.hotpath
+    g = torch.Generator().manual_seed(5)
+    for phase, nb in (("u", 37), ("v", 0), ("u", 0)):
+        sums = torch.rand(8, dtype=torch.float64, generator=g) + 0.1
+        sums[0] -= 0.6
+        V, N, L, Lb, alpha, side = 32.0, 4000, 20, 20, 1e8, 1.0
+        out = torch.empty(8, dtype=torch.float64)
+        rc = emu.cdll.xw_loss_scalars(C.c_void_p(sums.data_ptr()), 0 if phase == "u" else 1, V, float(N), float(L), float(nb),
+                                      float(Lb), alpha, side, C.c_void_p(out.data_ptr()), None)
+        assert rc == 0
+        b = SimpleNamespace(N_glob=N, L=L, Nb_glob=nb, Lb=Lb)
+        I, S, init, bdry, integ = hp.loss_from_sums(sums, b, V, alpha)
+        want = [integ + alpha * (init + bdry) if phase == "u" else -integ, I, S, init, bdry,
+                (2.0 / I) * (V / (N * L)) * (1 if phase == "u" else -1), torch.tensor(2.0 * alpha / N) if phase == "u" else 2.0 / sums[3],
+                torch.tensor(side)]
+        for a, w in zip(out.tolist(), want):
+            assert abs(a - float(w)) <= 1e-14 * abs(float(w)) + 1e-300
+    bad = emu.cdll.xw_loss_scalars(C.c_void_p(sums.data_ptr()), 2, 1.0, 1.0, 1.0, 0.0, 1.0, 1.0, 1.0, C.c_void_p(out.data_ptr()), None)
+    assert bad != 0

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, LIB_NAME)
 SOLVERS = {"euler": 0, "midpoint": 1, "rk4": 2}
 DOMAINS = {"cube": 0, "cone": 1, "hourglass": 2}
 NSUMS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 SUM_S1, SUM_S2, SUM_S3, SUM_VV, SUM_INIT, SUM_BDRY = 0, 1, 2, 3, 4, 5
 
 
@@ -65,6 +65,7 @@ _SIGS = {
     "xw_interior_backward_v": (C.c_int, [C.POINTER(Dims), C.POINTER(Domain), _P, C.POINTER(Points), _P, C.c_int,
                                          C.c_int, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "xw_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
+    "xw_loss_scalars": (C.c_int, [_P, C.c_int] + [C.c_double] * 7 + [_P, _P]),
     "xw_fma_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), _P]),
     "xw_umma_probe": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
 }

@@ -509,6 +509,16 @@ int xw_adam_step(double* params, const float* grad, double* exp_avg, double* exp
     return XW_CHECK_LAUNCH("k_adam_step");
 }
 
+int xw_loss_scalars(const double* sums, int phase, double V, double n_glob, double L, double nb_glob, double Lb,
+                    double alpha, double side, double* out, void* stream) {
+    if (!sums || !out) return fail("NULL pointer argument");
+    if (phase != 0 && phase != 1) return fail("phase must be 0 (u) or 1 (v), got %d", phase);
+    if (!(n_glob >= 1.0) || !(L >= 1.0) || nb_glob < 0.0 || (nb_glob > 0.0 && !(Lb >= 1.0))) return fail("bad sample counts");
+    if (!device()) return fail("no CUDA device");
+    XW_LAUNCH(xw::k_loss_scalars, 1, 32, 0, stream, sums, phase, V, n_glob, L, nb_glob, Lb, alpha, side, out);
+    return XW_CHECK_LAUNCH("k_loss_scalars");
+}
+
 int xw_xnode_eval(const xw_dims* m, const float* theta_u, const float* x, long long x_sn, const float* times,
                   int L, const float* s0, int n, float* u_out, void* stream) {
     if (check_dims(m)) return 1;

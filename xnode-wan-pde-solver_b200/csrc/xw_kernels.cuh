@@ -700,6 +700,31 @@ XW_GLOBAL void k_adam_step(double* p, const float* g, double* m, double* v, long
 }
 
 // =============================================================================================
+// The scalars of one sub-step from the (all-reduced) Monte-Carlo sums, on the device in fp64, one launch instead of ~22
+// one-element torch kernels between the forward and the backward kernels (at the shipped N = 4000 those were a tenth of
+// a graph-replayed sub-step).  Reference: I, S (src/loss.py:64-76), init / bdry / int (:78-90), loss u / v (:92-96);
+// k[] = the cotangent coefficients the backward entries take (include/xnode_wan_b200.h).
+//   out[0] loss   out[1] I   out[2] S   out[3] init   out[4] bdry   out[5..7] k0, k1, k2
+// =============================================================================================
+XW_GLOBAL void k_loss_scalars(const double* sums, int phase, double V, double n, double L, double nb, double Lb, double alpha,
+                              double side, double* out) {
+    if (XW_TID != 0 || XW_BID != 0) return;
+    const double I = (V / n) * sums[0] - (V / (n * L)) * (sums[1] - sums[2]);
+    const double S = V * sums[3] / (n * L);
+    const double init = sums[4] / n;
+    const double bdry = nb > 0.0 ? sums[5] / (nb * Lb) : 0.0;
+    const double integ = log(I * I) - log(S);
+    out[1] = I; out[2] = S; out[3] = init; out[4] = bdry;
+    if (phase == 0) {
+        out[0] = integ + alpha * (init + bdry);
+        out[5] = (2.0 / I) * (V / (n * L)); out[6] = 2.0 * alpha / n; out[7] = side;
+    } else {
+        out[0] = -integ;
+        out[5] = -(2.0 / I) * (V / (n * L)); out[6] = 2.0 / sums[3]; out[7] = side;
+    }
+}
+
+// =============================================================================================
 // weak-form sums from the CACHED test-function values: when the sample and theta_v are unchanged
 // (2nd u-step and the v-step of one outer iteration, src/training.py:125-162) only u, du change, so
 // the v net need not be evaluated again.  One thread per point; time-row-0 threads add the

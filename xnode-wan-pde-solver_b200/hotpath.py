@@ -24,7 +24,7 @@ from . import _lib
 PROFILE = None
 CALLS = {}                    # C-ABI entry name -> number of calls (always counted)
 KERNELS_PER_CALL = {"xw_interior_forward": 2, "xw_boundary_u": 3, "xw_interior_backward_u": 3,
-                    "xw_interior_backward_v": 2, "xw_xnode_eval": 1, "xw_vnet_eval": 1}
+                    "xw_interior_backward_v": 2, "xw_xnode_eval": 1, "xw_vnet_eval": 1, "xw_loss_scalars": 1}
 
 
 LAUNCHES = [0]                # kernels launched by this package (counted per C-ABI call)
@@ -351,21 +351,21 @@ class WeakLoss(torch.autograd.Function):
         sums, cot_u, cot_v = forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, phase == "u", alpha, gb,
                                           vcache, vmode, yh)
         _allreduce(sums, group)
-        I, S, init, bdry, integ = loss_from_sums(sums, batch, dom.V, alpha)
         ctx.phase, ctx.lib, ctx.spec, ctx.dom, ctx.batch, ctx.group = phase, lib, spec, dom, batch, group
         ctx.nu_params, ctx.side, ctx.sink = nu_params, 1.0 if side_effect else 0.0, sink
         ctx.meta = [(tuple(p.shape), p.dtype) for p in params]
-        N, L = batch.N_glob, batch.L
+        # loss, I, S, init, bdry and the backward's coefficients k[3] from the sums: one launch (xw_loss_scalars) instead
+        # of ~22 one-element torch kernels; `loss_from_sums` below is the same arithmetic in torch (tests compare them)
+        sc = torch.empty(8, dtype=torch.float64, device=dev)
+        _call(lib, "xw_loss_scalars", dev, _ptr(sums), 0 if phase == "u" else 1, float(dom.V), float(batch.N_glob), float(batch.L),
+              float(batch.Nb_glob if phase == "u" else 0), float(max(batch.Lb, 1)), float(alpha), ctx.side, _ptr(sc), _stream(dev))
+        k = sc[5:8]
         if phase == "u":
-            k = torch.stack([(2.0 / I) * (dom.V / (N * L)), torch.full_like(I, 2.0 * alpha / N), torch.full_like(I, ctx.side)])
             ctx.save_for_backward(theta_u, cot_u, k, gb, yh)
-            out = integ + alpha * (init + bdry)
         else:
-            k = torch.stack([-(2.0 / I) * (dom.V / (N * L)), 2.0 / sums[_lib.SUM_VV], torch.full_like(I, ctx.side)])
             ctx.save_for_backward(theta_v, cot_v, k)
-            out = -integ
-        ctx.components = dict(I=I, S=S, init=init, bdry=bdry)
-        return out
+        ctx.components = dict(I=sc[1], S=sc[2], init=sc[3], bdry=sc[4])
+        return sc[0].clone()
 
     @staticmethod
     def backward(ctx, go):
