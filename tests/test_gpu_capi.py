@@ -68,3 +68,28 @@ def test_capi_dense_a_b_matches_oracle(lib):
         assert G.rel(x, y) < 1e-3
     for x, y in zip(r["grads_v"], rv["grads"]):
         assert G.rel(x, y) < 1e-3
+
+
+def test_loss_scalars_kernel_against_fp64_arithmetic(lib):
+    """xw_loss_scalars on the device against the same formulas in numpy fp64 (reference src/loss.py:64-96; the cotangent
+    coefficients of the backward entries), both phases, with and without a boundary batch"""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(3)
+    for phase, nb in ((0, 4000.0), (1, 0.0), (0, 0.0)):
+        s = rng.random(8) + 0.1
+        s[0] -= 0.6
+        V, n, L, Lb, alpha, side = 2.0 ** 20, 1048576.0, 20.0, 20.0, 1e8, 1.0
+        sums = torch.tensor(s, dtype=torch.float64, device="cuda:0")
+        out = torch.zeros(8, dtype=torch.float64, device="cuda:0")
+        lib.call("xw_loss_scalars", C.c_void_p(sums.data_ptr()), phase, V, n, L, nb, Lb, alpha, side, C.c_void_p(out.data_ptr()),
+                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        got = out.cpu().numpy()
+        I = (V / n) * s[0] - (V / (n * L)) * (s[1] - s[2])
+        S = V * s[3] / (n * L)
+        init, bdry = s[4] / n, (s[5] / (nb * Lb) if nb else 0.0)
+        integ = np.log(I * I) - np.log(S)
+        want = [integ + alpha * (init + bdry), I, S, init, bdry, (2 / I) * (V / (n * L)), 2 * alpha / n, side] if phase == 0 else \
+               [-integ, I, S, init, bdry, -(2 / I) * (V / (n * L)), 2 / s[3], side]
+        for a, w in zip(got, want):
+            assert abs(a - w) <= 1e-13 * abs(w) + 1e-300, (phase, nb, a, w)
