@@ -65,7 +65,7 @@ class Hypercube:
         if self.collapsed:
             return CollapsedPaths(self.times.to(x.device), x[:, 0, :].contiguous())
         t = self.times.to(x.device).reshape(1, self.N_t, 1).expand(n, self.N_t, 1)
-        if self.pin_host and x.device.type == "cpu":
+        if self.pin_host and x.device.type == "cpu" and n * self.N_t * (self.dim + 1) * x.element_size() <= (256 << 20):
             out = torch.empty(n, self.N_t, self.dim + 1, dtype=x.dtype, pin_memory=True)
             return torch.cat((t, x.expand(n, self.N_t, self.dim)), dim=2, out=out)
         return torch.cat((t, x.expand(n, self.N_t, self.dim)), dim=2)
