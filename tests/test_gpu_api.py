@@ -288,3 +288,46 @@ def test_boundary_pass_beside_the_interior_forward_gives_the_same_step(monkeypat
         assert abs(v - out["1"][1][k]) <= 1e-9 * abs(v) + 1e-300
     for a, b in zip(out["0"][2], out["1"][2]):
         assert G.rel(a, b) < 1e-6
+
+
+def test_train_loop_matches_a_plain_loop_over_the_same_pieces():
+    """train() (next sample drawn ahead in page-locked memory and prefetched, stop() enqueued before the loss is read,
+    CUDA-graph replay, boundary pass on a second stream) against the straightforward loop of the reference
+    (src/training.py:113-162: domain, sample, n1 x (u sub-step, stop), n2 x v sub-step) run eagerly on the same seeds:
+    the same stop() values in the same order, the same recorded losses"""
+    def solver(graph):
+        torch.manual_seed(21)
+        np.random.seed(21)
+        p = xw.problems.cube_params(dim=5, N_r=4000, N_b=4000, iterations=8)
+        prob = xw.problems.ex4_1()
+        s = xw.NODE_WAN_solver(p, prob.func_a, prob.func_b, prob.func_c, prob.func_h, prob.func_f, prob.func_g, DEV, "./",
+                               func_u_sol=prob.func_u_sol, p=2, log_json=False, use_cuda_graph=True)
+        s.use_cuda_graph = graph
+        s.keep_l2_history = False
+        return s
+
+    def watch(trace):
+        def stop(sv, points, domain):
+            trace.append(xw.rel_err(points, sv.u_net, sv.func_u_sol, sv.p, domain.V(), sv.params['N_r']).item())
+            return False
+        return stop
+    a, ta = solver(True), []
+    a.stop = watch(ta)
+    hist = a.train()
+    b, tb, lb = solver(False), [], []
+    stop_b = watch(tb)
+    for k in range(8):
+        dom = b.new_domain()
+        dom.pin_host = False                              # plain pageable samples, synchronous copies
+        pts = xw.Comb_loader(4000, 4000, dom, DEV)
+        for _ in range(b.n1):
+            lu = b.sub_step("u", dom, pts)
+            stop_b(b, pts.interioru, dom)
+        for _ in range(b.n2):
+            lv = b.sub_step("v", dom, pts)
+        lb.append((lu.item(), lv.item()))
+    assert len(ta) == len(tb) == 16
+    for k, (x, y) in enumerate(zip(ta, tb)):               # (training amplifies last-bit differences: see the test above)
+        assert abs(x - y) <= (1e-5 if k < 8 else 1e-3) * abs(y), (k, x, y)
+    for k, ((u1, v1), u0, v0) in enumerate(zip(lb, hist["loss_u"], hist["loss_v"])):
+        assert abs(u0 - u1) <= (1e-5 if k < 4 else 1e-3) * abs(u1) and abs(v0 - v1) <= 1e-3 * max(abs(v1), 1.0), (k, u0, u1, v0, v1)
