@@ -240,6 +240,14 @@ def _side_stream(dev):
     return _SIDE_STREAMS[dev]
 
 
+DEFER_BOUNDARY_JOIN = os.environ.get("XW_DEFER_BOUNDARY_JOIN", "1") == "1"
+
+
+def _is_distributed(group):
+    return group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                 and torch.distributed.get_world_size() > 1)
+
+
 def _concurrent_boundary(n, nb):
     flag = os.environ.get("XW_CONCURRENT_BOUNDARY")
     if flag is not None:
@@ -283,9 +291,11 @@ def vcache_buffer(lib, spec, batch, dev):
 
 
 def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, alpha, boundary_grad=None,
-                 vcache=None, vmode=0, y_hist=None):
+                 vcache=None, vmode=0, y_hist=None, defer=None):
     """launches the forward kernels; returns (sums[8] fp64 device tensor, cot_u, cot_v).
-    vcache/vmode: 0 none, 1 evaluate the v net and fill `vcache`, 2 reuse `vcache` (same sample, same theta_v)"""
+    vcache/vmode: 0 none, 1 evaluate the v net and fill `vcache`, 2 reuse `vcache` (same sample, same theta_v).
+    defer: a dict -- when the boundary pass runs on the second stream, do NOT join it here but hand the stream back in
+    defer["side"]; the caller joins (WeakLoss, under CUDA-graph capture only)."""
     dev = theta_u.device
     dims = spec.c()
     st = _stream(dev)
@@ -316,7 +326,11 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
         _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
                  batch.xb_sn, _ptr(batch.times_b), batch.Lb, _ptr(batch.sb), _ptr(batch.g), batch.Nb, gscale,
                  _ptr(sums), _ptr(boundary_grad), 0, _ptr(ws_b), ws_b.numel(), st_b)
-        if side is not None:
+        if side is not None and defer is not None:
+            defer["side"] = side                                      # the caller joins ...
+            defer["keep"] = ws_b      # ... and keeps the side branch's workspace alive until then: the allocator would hand a
+            #                           freed block to the next allocation on the main stream while the side stream still uses it
+        elif side is not None:
             torch.cuda.current_stream(dev).wait_stream(side)          # join: everything after this sees both passes
     return sums, cot_u, cot_v
 
@@ -348,24 +362,48 @@ class WeakLoss(torch.autograd.Function):
         if phase == "u":       # XNODE state history for the interior backward (saves its forward sweep)
             dims_ = spec.c()
             yh = torch.empty(int(lib.cdll.xw_yhist_floats(C.byref(dims_), batch.N, batch.L)), dtype=torch.float32, device=dev)
+        # Under CUDA-graph capture on one rank the boundary pass (second stream, small samples: forward_sums) is joined
+        # only AFTER the interior backward has been launched: the interior's cotangent coefficients k[] need the interior
+        # sums alone, so the graph gets two branches -- interior forward -> backward | boundary pass -> loss value -- that
+        # meet in front of the optimiser.  (Eagerly the loss tensor must be complete on the caller's stream when forward
+        # returns, so the join stays in forward_sums; with several ranks the all-reduce of the sums needs both passes.)
+        defer = {} if (phase == "u" and dev.type == "cuda" and DEFER_BOUNDARY_JOIN and not _is_distributed(group)
+                       and torch.cuda.is_current_stream_capturing()) else None
         sums, cot_u, cot_v = forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, phase == "u", alpha, gb,
-                                          vcache, vmode, yh)
+                                          vcache, vmode, yh, defer)
+        side = defer.get("side") if defer else None
+        ctx.pending_side = side
+        # (same for `sums`: the side branch adds the boundary sum to it and reads it for the loss value after forward returned)
+        ctx.pending_keep = (defer.get("keep"), sums) if side is not None else None
         _allreduce(sums, group)
         ctx.phase, ctx.lib, ctx.spec, ctx.dom, ctx.batch, ctx.group = phase, lib, spec, dom, batch, group
         ctx.nu_params, ctx.side, ctx.sink = nu_params, 1.0 if side_effect else 0.0, sink
         ctx.meta = [(tuple(p.shape), p.dtype) for p in params]
         # loss, I, S, init, bdry and the backward's coefficients k[3] from the sums: one launch (xw_loss_scalars) instead
         # of ~22 one-element torch kernels; `loss_from_sums` below is the same arithmetic in torch (tests compare them)
-        sc = torch.empty(8, dtype=torch.float64, device=dev)
-        _call(lib, "xw_loss_scalars", dev, _ptr(sums), 0 if phase == "u" else 1, float(dom.V), float(batch.N_glob), float(batch.L),
-              float(batch.Nb_glob if phase == "u" else 0), float(max(batch.Lb, 1)), float(alpha), ctx.side, _ptr(sc), _stream(dev))
-        k = sc[5:8]
+        sargs = (float(dom.V), float(batch.N_glob), float(batch.L))
+        nb_lb = (float(batch.Nb_glob if phase == "u" else 0), float(max(batch.Lb, 1)))
+        if side is None:
+            sc = torch.empty(8, dtype=torch.float64, device=dev)
+            _call(lib, "xw_loss_scalars", dev, _ptr(sums), 0 if phase == "u" else 1, *sargs, *nb_lb, float(alpha), ctx.side,
+                  _ptr(sc), _stream(dev))
+            k = sc[5:8]
+        else:
+            main = torch.cuda.current_stream(dev)
+            sck = torch.empty(8, dtype=torch.float64, device=dev)          # k[] (and I, S, init) from the interior sums:
+            _call(lib, "xw_loss_scalars", dev, _ptr(sums), 0, *sargs, 0.0, 1.0, float(alpha), ctx.side, _ptr(sck), _stream(dev))
+            k = sck[5:8]                                                    # nb = 0: the boundary slot is not read
+            side.wait_stream(main)                                          # interior sums are final for the side branch
+            with torch.cuda.stream(side):
+                sc = torch.empty(8, dtype=torch.float64, device=dev)
+                _call(lib, "xw_loss_scalars", dev, _ptr(sums), 0, *sargs, *nb_lb, float(alpha), ctx.side, _ptr(sc), _stream(dev))
+                out = sc[0].clone()
         if phase == "u":
             ctx.save_for_backward(theta_u, cot_u, k, gb, yh)
         else:
             ctx.save_for_backward(theta_v, cot_v, k)
         ctx.components = dict(I=sc[1], S=sc[2], init=sc[3], bdry=sc[4])
-        return sc[0].clone()
+        return sc[0].clone() if side is None else out
 
     @staticmethod
     def backward(ctx, go):
@@ -381,11 +419,19 @@ class WeakLoss(torch.autograd.Function):
             ws = _WS.get(dev, lib.workspace_bytes(dims, batch.N, batch.L))
             ks = k.clone()
             ks[0:2] *= go.to(ks.dtype)
-            grad = torch.mul(gb, go.to(gb.dtype), out=sink) if sink is not None else (gb * go.to(gb.dtype)).contiguous()
+            side = getattr(ctx, "pending_side", None)
+            if side is None:
+                grad = torch.mul(gb, go.to(gb.dtype), out=sink) if sink is not None else (gb * go.to(gb.dtype)).contiguous()
+            else:                    # the boundary pass may still be running: its gradient is added after the join below
+                grad = sink if sink is not None else torch.empty_like(gb)
             _call(lib, "xw_interior_backward_u", dev, C.byref(dims), _ptr(theta_u),
                      C.c_void_p(batch.x.data_ptr() + 4 * batch.x_off), batch.x_sn, _ptr(batch.times), batch.L,
-                     _ptr(batch.h), _ptr(cot_u), batch.N, _ptr(ks), _ptr(grad), 1, _ptr(ws), ws.numel(), st,
+                     _ptr(batch.h), _ptr(cot_u), batch.N, _ptr(ks), _ptr(grad), 1 if side is None else 0, _ptr(ws), ws.numel(), st,
                      _ptr(batch.s0), _ptr(yh))
+            if side is not None:
+                torch.cuda.current_stream(dev).wait_stream(side)      # join: boundary gradient and loss value are final
+                grad.addcmul_(gb, go.to(gb.dtype).expand_as(gb))
+                ctx.pending_side = ctx.pending_keep = None
             _allreduce(grad, ctx.group)
             if sink is not None:
                 return none + (None,) * len(ctx.meta)
