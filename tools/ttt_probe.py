@@ -69,7 +69,7 @@ if __name__ == "__main__":
     print(json.dumps({"warm": run(100, True)}))
 
 
-def cold(n_solvers=4, iters=40):
+def cold(n_solvers=6, iters=40):
     """per-outer-iteration wall time of fresh solvers (eager first iteration, graph captures, then replay)"""
     import gc
     out = []
@@ -90,6 +90,8 @@ def cold(n_solvers=4, iters=40):
         s.new_domain = nd
         s.stop = lambda sv, points, domain: bool(xw.rel_err(points, sv.u_net, sv.func_u_sol, sv.p, domain.V(), sv.params['N_r']).item() < 0)
         gc.collect()
+        if os.environ.get("PROBE_EMPTY"):
+            torch.cuda.empty_cache()
         torch.cuda.synchronize()
         ev = []
 
@@ -136,9 +138,14 @@ def cold(n_solvers=4, iters=40):
         t1 = time.perf_counter()
         d = [round(1e3 * (b - a), 2) for a, b in zip([t0] + marks, marks + [t1])]
         out.append({"seed": seed, "wall_s": round(t1 - t0, 4), "between_domain_draws_ms": d[:8], "max_later_ms": max(d[8:]), "median_later_ms": sorted(d[8:])[len(d[8:]) // 2],
-                    "events_over_2ms": [e for e in ev if not isinstance(e[1], float) or e[1] > 2.0]})
+                    "events_over_10ms": [e for e in ev if isinstance(e[1], float) and e[1] > 10.0]})
+        if os.environ.get("PROBE_KEEP"):
+            KEEP.append(s)
         del s
     return out
+
+
+KEEP = []
 
 
 if __name__ == "__main__" and os.environ.get("PROBE_COLD"):
