@@ -10,6 +10,7 @@ PyTorch is plumbing here (device memory, streams, torch.distributed); all arithm
 runs in the sm_100a kernels behind the C ABI (include/xnode_wan_b200.h).  No CPU fallback: CPU
 tensors or a missing library raise.
 """
+import contextlib
 import ctypes as C
 import os
 from dataclasses import dataclass, field
@@ -216,10 +217,25 @@ class _Workspace:
 
     def __init__(self):
         self.buf = {}
+        self.graph_buf = {}
+
+    def reserve_for_graphs(self, dev, nbytes):
+        """a persistent scratch, allocated EAGERLY (outside any capture), that the graphs captured afterwards use: graphs
+        replay one after the other on one stream, so they can share it -- a private copy per graph and per call is
+        3 x 1.8 GB x 4 graphs at 2^20 paths and does not fit at d = 100, 2^22 paths (17 GB each).  Whoever captures keeps
+        the returned tensor alive for as long as its graphs live; a larger request replaces the buffer for LATER captures."""
+        b = self.graph_buf.get(dev)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            self.graph_buf[dev] = b
+        return b
 
     def get(self, dev, nbytes):
         if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
-            # a captured graph must own its scratch (the shared buffer may be re-grown later)
+            b = self.graph_buf.get(dev)
+            if b is not None and b.numel() >= nbytes:
+                return b
+            # otherwise the graph owns its scratch (the shared eager buffer below may be re-grown later)
             return torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         b = self.buf.get(dev)
         if b is None or b.numel() < nbytes:
@@ -231,7 +247,15 @@ class _Workspace:
 _WS = _Workspace()
 _WS_SIDE = _Workspace()           # workspace of the boundary pass when it runs beside the interior forward (forward_sums)
 _SIDE_STREAMS = {}
-CONCURRENT_BOUNDARY_MAX_PATHS = 16384     # one lane per path: below this a launch is less than one wave of the XNODE kernels
+# largest sample whose boundary pass runs beside the interior forward (None: any).  Measured on B200 (profiles/README
+# r02bf): at the shipped N = 4000 a launch is less than one wave and the two passes simply run side by side (-12 % per
+# outer iteration); at 2^17 paths per rank (configs[3] split over 8 GPUs) the tail of one kernel overlaps the head of
+# the next, 11.28 -> 10.94 ms per step (10.58 under graph replay, where the join is deferred); at 2^20 77.1 -> 76.7 ms.
+# Eagerly the limit stays at one wave: bench.py times every C-ABI entry with CUDA events inside the timed region, and
+# overlapping entries would blur the per-kernel roofline figures for 0.6 % of the step; under capture (no per-call events)
+# any size runs the two branches.
+CONCURRENT_BOUNDARY_MAX_PATHS = 16384
+CONCURRENT_BOUNDARY_MAX_WORKSPACE = 4 << 30
 
 
 def _side_stream(dev):
@@ -248,11 +272,13 @@ def _is_distributed(group):
                                  and torch.distributed.get_world_size() > 1)
 
 
-def _concurrent_boundary(n, nb):
+def _concurrent_boundary(n, nb, ws_bytes):
     flag = os.environ.get("XW_CONCURRENT_BOUNDARY")
     if flag is not None:
         return flag == "1"
-    return max(n, nb) <= CONCURRENT_BOUNDARY_MAX_PATHS
+    # (every captured graph owns its workspaces: a second one of 17 GB per graph -- d = 100, 2^22 paths -- does not fit)
+    return max(n, nb) <= CONCURRENT_BOUNDARY_MAX_PATHS or \
+        (torch.cuda.is_current_stream_capturing() and ws_bytes <= CONCURRENT_BOUNDARY_MAX_WORKSPACE)
 
 
 def flatten_params(params):
@@ -306,12 +332,13 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
     cot_u = torch.empty(N * L, dtype=torch.float32, device=dev)
     cot_v = torch.empty(N * L, dtype=torch.float32, device=dev)
     cdom, ccoef, pts = dom.c(), coef.c(), batch.points()
-    # Small samples (the shipped N = 4000: 125 warps on 148 SMs) leave most of the GPU idle and every kernel is one
-    # dependent chain per path: the boundary pass (forward + reverse sweep of its own paths, own slots of `sums`, own
-    # gradient buffer) does not depend on the interior forward, so it runs beside it on a second stream with its own
-    # workspace.  Under CUDA-graph capture the fork / join become parallel branches of the graph.  Full waves gain nothing.
+    # The boundary pass (forward + reverse sweep of its own paths, own slots of `sums`, own gradient buffer) does not depend
+    # on the interior forward, so it runs beside it on a second stream with its own workspace.  Small samples (the shipped
+    # N = 4000: 125 warps on 148 SMs) leave most of the GPU idle and every kernel is one dependent chain per path: the two
+    # passes run side by side; with full waves the tail of one kernel overlaps the head of the next (a few per cent).
+    # Under CUDA-graph capture the fork / join become parallel branches of the graph.
     side, ws_b, st_b = None, ws, st
-    if with_boundary and dev.type == "cuda" and _concurrent_boundary(N, batch.Nb):
+    if with_boundary and dev.type == "cuda" and _concurrent_boundary(N, batch.Nb, wsb):
         side = _side_stream(dev)
         ws_b = _WS_SIDE.get(dev, wsb)
         side.wait_stream(torch.cuda.current_stream(dev))                # fork: inputs, `sums` and the gradient buffer are ready
@@ -323,9 +350,10 @@ def forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, with_boundary, a
           _ptr(y_hist), vcache.numel() if (vmode and vcache is not None) else 0, y_hist.numel() if y_hist is not None else 0)
     if with_boundary:
         gscale = float(alpha) / (batch.Nb_glob * batch.Lb)
-        _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
-                 batch.xb_sn, _ptr(batch.times_b), batch.Lb, _ptr(batch.sb), _ptr(batch.g), batch.Nb, gscale,
-                 _ptr(sums), _ptr(boundary_grad), 0, _ptr(ws_b), ws_b.numel(), st_b)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):   # (_call's timing events follow)
+            _call(lib, "xw_boundary_u", dev, C.byref(dims), _ptr(theta_u), C.c_void_p(batch.xb.data_ptr() + 4 * batch.xb_off),
+                     batch.xb_sn, _ptr(batch.times_b), batch.Lb, _ptr(batch.sb), _ptr(batch.g), batch.Nb, gscale,
+                     _ptr(sums), _ptr(boundary_grad), 0, _ptr(ws_b), ws_b.numel(), st_b)
         if side is not None and defer is not None:
             defer["side"] = side                                      # the caller joins ...
             defer["keep"] = ws_b      # ... and keeps the side branch's workspace alive until then: the allocator would hand a

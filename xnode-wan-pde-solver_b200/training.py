@@ -322,7 +322,16 @@ class NODE_WAN_solver:
         if self.world > 1:
             tmp.N_glob, tmp.Nb_glob = static[0].shape[0] * self.world, static[2].shape[0] * self.world
         pb = tmp._batch(self.u_net.module, static[0], static[1], static[2])
-        self._graphs = dict(static=static, graphs={}, outs={}, domain=domain, persist=((h, f, g, a, b, c), pb))
+        # one persistent scratch for all graphs of this sample size (and a second one for the boundary branch), allocated
+        # here, outside the captures (hotpath._Workspace.reserve_for_graphs); the references keep them alive with the graphs
+        from . import hotpath as _hp
+        from . import _lib as _xl
+        dev = torch.device(self.device)
+        wsb = _xl.get().workspace_bytes(self.u_net.module.spec(self.v_net.module).c(), max(pb.N, pb.Nb, 1), max(pb.L, pb.Lb, 1))
+        scratch = [_hp._WS.reserve_for_graphs(dev, wsb)]
+        if wsb <= _hp.CONCURRENT_BOUNDARY_MAX_WORKSPACE:
+            scratch.append(_hp._WS_SIDE.reserve_for_graphs(dev, wsb))
+        self._graphs = dict(static=static, graphs={}, outs={}, domain=domain, persist=((h, f, g, a, b, c), pb), scratch=scratch)
 
     def _graph_fits(self, batch):
         """the captured graphs are bound to static copies of one layout ([N,L,C] tensors or CollapsedPaths) and size"""
