@@ -429,6 +429,25 @@ def run_ours(args):
                                          "note": "forward tcgen05 kernel with three issuing warps per tile stream (not bit-reproducible from run to run)"}
         finally:
             os.environ.pop("XW_TC_SPLIT", None)
+    # use_cuda_graph=True: the same step replayed from captured graphs (one launch per sub-step; the boundary pass and the
+    # interior pass are parallel branches, hotpath.WeakLoss).  A second solver on the same resident sample; one GPU only
+    # (the headline stays the eager path: its per-entry CUDA events are what `roofline` is computed from).
+    if world == 1 and not args.graph and args.config == "m":
+        solver_g = None
+        try:
+            solver_g, _ = make_solver(xw, d, n_loc * world, dev, use_cuda_graph=True, fused_optimizer=bool(args.fused))
+            for _ in range(4):                   # eager iteration, captures, first replays
+                solver_g.train_iteration(domain, points)
+            ms_g = timed(lambda: solver_g.train_iteration(domain, points), args.steps)
+            replayed = solver_g._graphs is not None and len(solver_g._graphs["graphs"]) > 0
+            variants["use_cuda_graph=True"] = {"ms_per_step": ms_g, "value": pp_step / (ms_g * 1e-3), "unit": "path-points/s",
+                                               "graphs_replayed": bool(replayed),
+                                               "note": "NODE_WAN_solver(use_cuda_graph=True): sub-steps replayed from CUDA graphs"}
+        except Exception as e:                   # (a variant must never take the headline line down with it)
+            variants["use_cuda_graph=True"] = {"error": str(e)[:300]}
+        finally:
+            del solver_g
+            torch.cuda.empty_cache()
     del solver, points
     torch.cuda.empty_cache()
 
