@@ -396,6 +396,7 @@ class WeakLoss(torch.autograd.Function):
         # meet in front of the optimiser.  (Eagerly the loss tensor must be complete on the caller's stream when forward
         # returns, so the join stays in forward_sums; with several ranks the all-reduce of the sums needs both passes.)
         defer = {} if (phase == "u" and dev.type == "cuda" and DEFER_BOUNDARY_JOIN and not _is_distributed(group)
+                       and any(ctx.needs_input_grad)                 # (no backward, no join: a capture would end unjoined)
                        and torch.cuda.is_current_stream_capturing()) else None
         sums, cot_u, cot_v = forward_sums(lib, spec, dom, coef, theta_u, theta_v, batch, phase == "u", alpha, gb,
                                           vcache, vmode, yh, defer)
